@@ -1,0 +1,254 @@
+/*
+ * skge_b200.h -- C ABI of libskge_b200.so: hand-written sm_100a kernels for the
+ * scikit-kge embedding-training and filtered-ranking hot path.
+ *
+ * The reference (unmeshvrije/scikit-kge) has no FFI: its extension points are
+ * Python duck-typed hooks.  Every entry point below names the reference
+ * function(s) it replaces (paths relative to the reference root); the Python
+ * package scikit-kge_b200/skge binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates or frees caller-visible memory: scratch space
+ *     is a caller-provided workspace sized by the matching *_workspace_bytes();
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and keeps no
+ *     global mutable state;
+ *   - every function returns 0 on success, a negative code on failure
+ *     (-cudaError_t for CUDA errors, SKGE_E* below otherwise); the message is
+ *     available from skge_last_error() (thread-local);
+ *   - index arrays are int32; parameters, AdaGrad state and gradients are fp32,
+ *     row-major: E[N][d], R[M][d], W[M][d][d];
+ *   - triples travel as three SoA arrays s[], o[], p[] (the reference's tuples
+ *     are (s, o, p): skge/util.py:104-110).
+ */
+#ifndef SKGE_B200_H
+#define SKGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *skge_stream_t; /* cudaStream_t */
+
+#define SKGE_API __attribute__((visibility("default")))
+
+#define SKGE_EINVAL (-10001)     /* bad argument */
+#define SKGE_EWORKSPACE (-10002) /* workspace too small */
+#define SKGE_ENODEVICE (-10003)  /* no sm_100 device: there is no CPU fallback */
+
+enum { SKGE_OPT_SGD = 0, SKGE_OPT_ADAGRAD = 1 };                       /* skge/param.py:124-158 */
+enum { SKGE_POST_NONE = 0, SKGE_POST_NORMALIZE = 1, SKGE_POST_NORMLESS1 = 2 }; /* skge/param.py:161-174 */
+enum { SKGE_AF_LINEAR = 0, SKGE_AF_SIGMOID = 1, SKGE_AF_TANH = 2, SKGE_AF_RELU = 3 }; /* skge/actfun.py:13-57 */
+enum { SKGE_MODEL_TRANSE = 0, SKGE_MODEL_HOLE = 1, SKGE_MODEL_RESCAL = 2 };
+enum { SKGE_RANK_L1 = 0, SKGE_RANK_DOT = 1 };
+
+/* ---- library ---------------------------------------------------------- */
+SKGE_API int skge_version(void);
+SKGE_API const char *skge_last_error(void);
+/* 0 if the current device is sm_100; SKGE_ENODEVICE otherwise. */
+SKGE_API int skge_check_device(void);
+
+/* ---- scores: Model._scores(ss, ps, os) -------------------------------- */
+/* skge/transe.py:25-46 : -sum|E[s]+R[p]-E[o]| (l1) or -sum(.)^2 (no sqrt). */
+SKGE_API int skge_scores_transe(const float *E, const float *R, const int32_t *s, const int32_t *p,
+                       const int32_t *o, int64_t n, int d, int l1, float *out, skge_stream_t stream);
+/* skge/hole.py:19-20 : sum_k R[p]_k ccorr(E[s],E[o])_k. */
+SKGE_API int skge_scores_hole(const float *E, const float *R, const int32_t *s, const int32_t *p,
+                     const int32_t *o, int64_t n, int d, float *out, skge_stream_t stream);
+/* skge/rescal.py:31-35 : E[s]^T W[p] E[o]. */
+SKGE_API int skge_scores_rescal(const float *E, const float *W, const int32_t *s, const int32_t *p,
+                       const int32_t *o, int64_t n, int d, float *out, skge_stream_t stream);
+
+/* ---- pairwise-margin minibatch: Model._pairwise_gradients + _batch_step -- */
+/*
+ * A minibatch is P (positive, negative) pairs given as six index arrays.
+ * `valid` (nullable, uint8[P]) masks pairs the sampler could not produce.
+ * counts (device int32[4]) receives {nviolations, U_E, U_R, 0}.
+ *
+ * *_grads returns exactly the reference's dict {'E': (ge, eidx), 'R': (gr, ridx)}:
+ * ge[U_E][d] / gr[U_R][d] are the per-row MEANS over occurrences among the
+ * violating pairs and eidx / ridx are ascending (skge/util.py:53-101).  The
+ * caller sizes ge/eidx for min(4P, N) rows and gr/ridx for min(2P, M) rows.
+ * nviolations == 0 is the reference's "return None" (skge/transe.py:90-91).
+ *
+ * *_step fuses the gradient with the parameter update of
+ * StochasticTrainer._batch_step (skge/base.py:1306-1316): rows of E then R are
+ * updated in place from gradients of the PRE-update parameters, by SGD or
+ * AdaGrad (skge/param.py:124-158), followed by the row post-hook.
+ * nviol_accum (nullable, device int64) += nviolations; ent_violations
+ * (nullable, int32[N]) += 1 per distinct entity of each violating pair
+ * (skge/transe.py:78-83); upd_counts_* (nullable) += 1 per updated row
+ * (skge/param.py:149-150).
+ */
+SKGE_API size_t skge_pair_workspace_bytes(int64_t P, int d, int rows_per_pair, int64_t N, int64_t M);
+
+/* skge/transe.py:48-165 */
+SKGE_API int skge_transe_pair_grads(const float *E, const float *R, const int32_t *sp, const int32_t *op,
+                           const int32_t *pp, const int32_t *sn, const int32_t *on,
+                           const int32_t *pn, const uint8_t *valid, int64_t P, int64_t N,
+                           int64_t M, int d, int l1, float margin, float *pscores,
+                           float *nscores, float *ge, int32_t *eidx, float *gr, int32_t *ridx,
+                           int32_t *counts, int32_t *ent_violations, void *ws, size_t ws_bytes,
+                           skge_stream_t stream);
+SKGE_API int skge_transe_pair_step(float *E, float *R, float *p2E, float *p2R, const int32_t *sp,
+                          const int32_t *op, const int32_t *pp, const int32_t *sn,
+                          const int32_t *on, const int32_t *pn, const uint8_t *valid, int64_t P,
+                          int64_t N, int64_t M, int d, int l1, float margin, int opt, float lr,
+                          int postE, int postR, int32_t *counts, int64_t *nviol_accum,
+                          int32_t *ent_violations, int32_t *upd_counts_E, int32_t *upd_counts_R,
+                          void *ws, size_t ws_bytes, skge_stream_t stream);
+
+/* skge/hole.py:44-100 (af: skge/actfun.py; rparam on R rows only, hole.py:83) */
+SKGE_API int skge_hole_pair_grads(const float *E, const float *R, const int32_t *sp, const int32_t *op,
+                         const int32_t *pp, const int32_t *sn, const int32_t *on,
+                         const int32_t *pn, const uint8_t *valid, int64_t P, int64_t N, int64_t M,
+                         int d, int af, float margin, float rparam, float *pscores,
+                         float *nscores, float *ge, int32_t *eidx, float *gr, int32_t *ridx,
+                         int32_t *counts, void *ws, size_t ws_bytes, skge_stream_t stream);
+SKGE_API int skge_hole_pair_step(float *E, float *R, float *p2E, float *p2R, const int32_t *sp,
+                        const int32_t *op, const int32_t *pp, const int32_t *sn,
+                        const int32_t *on, const int32_t *pn, const uint8_t *valid, int64_t P,
+                        int64_t N, int64_t M, int d, int af, float margin, float rparam, int opt,
+                        float lr, int postE, int postR, int32_t *counts, int64_t *nviol_accum,
+                        int32_t *upd_counts_E, int32_t *upd_counts_R, void *ws, size_t ws_bytes,
+                        skge_stream_t stream);
+
+/* ---- logistic minibatch: Model._gradients + _batch_step ---------------- */
+/*
+ * n labelled examples (s, o, p, y = +-1).  loss (device double, nullable) is
+ * SET to sum logaddexp(0, -y*score) (skge/hole.py:26, skge/rescal.py:52);
+ * loss_accum (nullable) += that value.  counts = {n, U_E, U_second, 0}.
+ */
+SKGE_API size_t skge_logistic_workspace_bytes(int model, int64_t n, int d, int64_t N, int64_t M);
+
+/* skge/hole.py:22-42 */
+SKGE_API int skge_hole_logistic_grads(const float *E, const float *R, const int32_t *s, const int32_t *o,
+                             const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
+                             int d, float rparam, float *ge, int32_t *eidx, float *gr,
+                             int32_t *ridx, int32_t *counts, double *loss, void *ws,
+                             size_t ws_bytes, skge_stream_t stream);
+SKGE_API int skge_hole_logistic_step(float *E, float *R, float *p2E, float *p2R, const int32_t *s,
+                            const int32_t *o, const int32_t *p, const float *y, int64_t n,
+                            int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                            int postE, int postR, int32_t *counts, double *loss_accum,
+                            int32_t *upd_counts_E, int32_t *upd_counts_R, void *ws,
+                            size_t ws_bytes, skge_stream_t stream);
+/* skge/rescal.py:37-76 ; gw[U_W][d][d], pidx ascending */
+SKGE_API int skge_rescal_logistic_grads(const float *E, const float *W, const int32_t *s, const int32_t *o,
+                               const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
+                               int d, float rparam, float *ge, int32_t *eidx, float *gw,
+                               int32_t *pidx, int32_t *counts, double *loss, void *ws,
+                               size_t ws_bytes, skge_stream_t stream);
+SKGE_API int skge_rescal_logistic_step(float *E, float *W, float *p2E, float *p2W, const int32_t *s,
+                              const int32_t *o, const int32_t *p, const float *y, int64_t n,
+                              int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                              int postE, int postW, int32_t *counts, double *loss_accum,
+                              int32_t *upd_counts_E, int32_t *upd_counts_W, void *ws,
+                              size_t ws_bytes, skge_stream_t stream);
+
+/* ---- ParameterUpdate.__call__(gradient, idx): skge/param.py:108-158 ----- */
+/* param[idx] is updated from g[U][rowlen] (idx unique), then post on those rows.
+ * p2 is AdaGrad's accumulator (ignored for SGD). rowlen = d, or d*d for W. */
+SKGE_API int skge_sparse_update(float *param, float *p2, const float *g, const int32_t *idx, int64_t U,
+                       int64_t rowlen, int opt, float lr, int post, int32_t *upd_counts,
+                       skge_stream_t stream);
+/* normalize / normless1 on rows idx (skge/param.py:161-174); idx == NULL: rows 0..U-1. */
+SKGE_API int skge_rows_post(float *param, const int32_t *idx, int64_t U, int64_t rowlen, int post,
+                   skge_stream_t stream);
+
+/* ---- negative sampling: skge/sample.py:10-46, 91-110 ------------------- */
+/*
+ * The training-triple set is an open-addressing hash table of packed 64-bit
+ * (s, o, p) keys built on the device.  skge_sample_corrupt emits, for each of
+ * B positives, n_per rounds x the modes in modes_mask (bit0: subject, bit1:
+ * object, bit2: predicate; ascending) one (positive, negative) pair: up to
+ * ntries Philox draws of the corrupted slot, rejected while the candidate is a
+ * training triple (and, with lcwa != 0, while (s', p') was never seen:
+ * skge/sample.py:103-110, needs sp_table).  Output pair index =
+ * (b * n_per + r) * nmodes + m.  out_valid[i] = 0 where all tries failed (the
+ * reference skips those, sample.py:22-24).
+ */
+SKGE_API size_t skge_tripleset_bytes(int64_t T);
+SKGE_API int skge_tripleset_build(void *table, size_t table_bytes, const int32_t *s, const int32_t *o,
+                         const int32_t *p, int64_t T, int pair_keys_only, skge_stream_t stream);
+SKGE_API int skge_tripleset_contains(const void *table, size_t table_bytes, const int32_t *s,
+                            const int32_t *o, const int32_t *p, int64_t n, uint8_t *out,
+                            skge_stream_t stream);
+SKGE_API int skge_sample_corrupt(const void *table, size_t table_bytes, const void *sp_table,
+                        size_t sp_table_bytes, const int32_t *s, const int32_t *o,
+                        const int32_t *p, const int32_t *batch_idx, int64_t B, int n_per,
+                        int modes_mask, int64_t N, int64_t M, int ntries, uint64_t seed,
+                        uint64_t offset, int32_t *out_sp, int32_t *out_op, int32_t *out_pp,
+                        int32_t *out_sn, int32_t *out_on, int32_t *out_pn, uint8_t *out_valid,
+                        skge_stream_t stream);
+
+/* ---- filtered ranking: FilteredRankingEval.positions -------------------- */
+/*
+ * skge/base.py:913-1031 with the per-model scorers of skge/run_transe.py:13-29
+ * and skge/run_hole.py:10-19.  A query j is (kind[j], given[j], rel[j],
+ * target[j]): kind 0 ranks target as the object of (given, rel, ?), kind 1 as
+ * the subject of (?, rel, given).  Every model reduces to one query vector per
+ * query and one sweep over the entity table:
+ *     TransE : score(e) = -sum_i |e_i - q_i|   q = E[s]+R[p]  or  E[o]-R[p]
+ *     HolE   : score(e) =  sum_i  e_i * q_i    q = cconv(R[p],E[s]) or ccorr(R[p],E[o])
+ *     RESCAL : score(e) =  sum_i  e_i * q_i    q = W[p]^T E[s]   or  W[p] E[o]
+ * rank = 1 + #{e : score(e) > score(target)} (equal to the reference's argsort
+ * position whenever the target's score is not tied).
+ *
+ * skge_rank_make_queries writes q64 (exact, fp64), q32 (its fp32 rounding, for
+ * the coarse sweep), tscore (exact fp64 target score), qnorm (||q||_2) and eps,
+ * a bound on the coarse sweep's error: coarse_rel * ||q||_2 * enorm_max for the
+ * DOT models (enorm_max >= max row norm of E), coarse_rel * (|tscore| +
+ * ||q||_1 / (d+2)) for L1.  The coarse sweeps count entities whose score exceeds
+ * tscore by more than eps and append the undecided (query, entity) pairs
+ * (|score - tscore| <= eps) to a candidate list; skge_rank_rescore settles
+ * candidates and filter entries in fp64 from the fp32 master table, so shard
+ * boundaries never change a result.
+ */
+SKGE_API int skge_rank_make_queries(int model, const float *E, const float *RW, const uint8_t *kind,
+                           const int32_t *given, const int32_t *rel, const int32_t *target,
+                           int64_t Q, int d, float enorm_max, float coarse_rel, double *q64,
+                           float *q32, double *tscore, float *eps, float *qnorm,
+                           skge_stream_t stream);
+/* CUDA-core coarse sweep in fp32 over rows [0, n_shard) of Eshard (global ids
+ * shard_base + row).  cnt_gt[Q] += definite wins; candidates appended at
+ * *cand_count (device, atomically); entries beyond cand_cap are dropped but
+ * still counted, so the caller can detect overflow. */
+SKGE_API int skge_rank_sweep(int op, const float *Eshard, int64_t n_shard, int64_t shard_base, int d,
+                    const float *q32, const double *tscore, const float *eps, int64_t Q,
+                    int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
+                    unsigned long long *cand_count, skge_stream_t stream);
+/* fp64 settlement of (query, entity) pairs: cnt[q] += 1 where
+ * score64(q, e) > tscore[q]; pairs with e == target[q] are ignored when
+ * target != NULL.  npairs_dev (device, nullable) overrides npairs and is
+ * clamped to it.  Efull is the full fp32 table (global entity ids). */
+SKGE_API int skge_rank_rescore(int op, const float *Efull, int d, const double *q64, const double *tscore,
+                      const int32_t *pair_q, const int32_t *pair_e, int64_t npairs,
+                      const unsigned long long *npairs_dev, const int32_t *target, int32_t *cnt,
+                      skge_stream_t stream);
+/* N scores of one query against the whole table, in fp64 (evaluator hooks
+ * scores_o / scores_s of skge/run_transe.py:20-29, skge/run_hole.py:15-19). */
+SKGE_API int skge_rank_scores_one(int op, const float *E, int64_t N, int d, const double *q64, double *out,
+                         skge_stream_t stream);
+
+/* tcgen05 path for the DOT models (HolE / RESCAL): the entity shard and the
+ * query block are re-laid out as fp16 hi/lo split tiles (UMMA K-major core
+ * matrices, 128 rows x 64 k per tile) and contracted on the 5th-gen tensor
+ * cores with fp32 accumulation in TMEM; the epilogue compares against the
+ * per-query thresholds straight out of TMEM and never stores a score. */
+SKGE_API size_t skge_rank_packed_bytes(int64_t rows, int d); /* bytes of ONE (hi or lo) packed array */
+SKGE_API int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_scale,
+                       float scalar_scale, void *hi, void *lo, skge_stream_t stream);
+SKGE_API int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
+                         const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
+                         const float *thr_lo, const float *thr_hi, int32_t *cnt_gt,
+                         int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
+                         unsigned long long *cand_count, skge_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKGE_B200_H */

@@ -1,0 +1,372 @@
+// Logistic-loss minibatch kernels (HolE, RESCAL) and their C entry points.
+//   HolE._gradients   : skge/hole.py:22-42
+//   RESCAL._gradients : skge/rescal.py:37-76
+//   StochasticTrainer._process_batch / _batch_step : skge/base.py:1293-1316
+#include "common.cuh"
+#include "hole_math.cuh"
+#include "segment.cuh"
+
+namespace skge {
+
+// loss term logaddexp(0, -ys) and fs = -(y * sigmoid(-ys))  (skge/hole.py:26-28)
+__device__ __forceinline__ void logistic_terms(float y, float raw, float *loss, float *fs) {
+  float ys = y * raw;
+  float m = -ys;
+  *loss = fmaxf(m, 0.f) + log1pf(expf(-fabsf(m)));
+  *fs = -(y / (1.0f + expf(ys)));
+}
+
+// One CTA per example; thread k owns component k.
+//   G[i][0] = fs ccorr(R[p],E[o]) -> s   G[i][1] = fs cconv(E[s],R[p]) -> o   G[i][2] = fs ccorr(E[s],E[o]) -> p
+__global__ void hole_logistic_kernel(const float *__restrict__ E, const float *__restrict__ R,
+                                     const int32_t *__restrict__ s, const int32_t *__restrict__ o,
+                                     const int32_t *__restrict__ p, const float *__restrict__ y, int64_t n,
+                                     int d, float *__restrict__ G, double *__restrict__ loss,
+                                     double *__restrict__ loss_accum) {
+  extern __shared__ float sm[];
+  float *es = sm, *rp = es + d, *o2 = rp + d, *rr = o2 + 2 * d, *red = rr + 2 * d;
+  double lsum = 0.0;
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    __syncthreads();
+    const float *rg = R + (int64_t)p[i] * d;
+    smem_load(es, E + (int64_t)s[i] * d, d);
+    smem_load(rp, rg, d);
+    smem_load_doubled(o2, E + (int64_t)o[i] * d, d);
+    smem_load_rev_doubled(rr, rg, d);
+    __syncthreads();
+    const int k = threadIdx.x;
+    float cso = k < d ? sliding_dot(es, o2, k, d) : 0.f;
+    float raw = block_sum(k < d ? rp[k] * cso : 0.f, red);
+    float l, fs;
+    logistic_terms(y[i], raw, &l, &fs);
+    lsum += l;
+    if (k < d) {
+      float *g = G + (int64_t)i * 3 * d;
+      g[k] = fs * sliding_dot(rp, o2, k, d);
+      g[d + k] = fs * sliding_dot(es, rr, (d - k) % d, d);
+      g[2 * d + k] = fs * cso;
+    }
+  }
+  if (threadIdx.x == 0 && lsum != 0.0) {
+    if (loss) atomicAdd(loss, lsum);
+    if (loss_accum) atomicAdd(loss_accum, lsum);
+  }
+}
+
+// One CTA per example.  EW_j = sum_i E[s]_i W[p]_ij (thread j, coalesced over j);
+// WE_i = sum_j W[p]_ij E[o]_j (warp per row i, lanes over j).
+//   G[i][0] = fs * WE -> s     G[i][1] = fs * EW -> o        (skge/rescal.py:72-73)
+__global__ void rescal_logistic_kernel(const float *__restrict__ E, const float *__restrict__ W,
+                                       const int32_t *__restrict__ s, const int32_t *__restrict__ o,
+                                       const int32_t *__restrict__ p, const float *__restrict__ y, int64_t n,
+                                       int d, float *__restrict__ G, float *__restrict__ fsv,
+                                       double *__restrict__ loss, double *__restrict__ loss_accum) {
+  extern __shared__ float sm[];
+  float *es = sm, *eo = es + d, *we = eo + d, *red = we + d;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double lsum = 0.0;
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    __syncthreads();
+    smem_load(es, E + (int64_t)s[i] * d, d);
+    smem_load(eo, E + (int64_t)o[i] * d, d);
+    __syncthreads();
+    const float *w = W + (int64_t)p[i] * d * d;
+    for (int r = wid; r < d; r += nw) {
+      float a = 0.f;
+      for (int j = lane; j < d; j += 32) a = fmaf(__ldg(w + (int64_t)r * d + j), eo[j], a);
+      a = warp_sum(a);
+      if (lane == 0) we[r] = a;
+    }
+    float ew[4] = {0.f, 0.f, 0.f, 0.f};  // d <= 4 * blockDim.x (checked by the launcher)
+    for (int r = 0; r < d; ++r) {
+      float sv = es[r];
+      const float *wr = w + (int64_t)r * d;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        int j = threadIdx.x + t * blockDim.x;
+        if (j < d) ew[t] = fmaf(sv, __ldg(wr + j), ew[t]);
+      }
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int r = threadIdx.x; r < d; r += blockDim.x) part += es[r] * we[r];
+    float raw = block_sum(part, red);
+    float l, fs;
+    logistic_terms(y[i], raw, &l, &fs);
+    lsum += l;
+    float *g = G + (int64_t)i * 2 * d;
+    for (int r = threadIdx.x; r < d; r += blockDim.x) g[r] = fs * we[r];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int j = threadIdx.x + t * blockDim.x;
+      if (j < d) g[d + j] = fs * ew[t];
+    }
+    if (threadIdx.x == 0) fsv[i] = fs;
+  }
+  if (threadIdx.x == 0 && lsum != 0.0) {
+    if (loss) atomicAdd(loss, lsum);
+    if (loss_accum) atomicAdd(loss_accum, lsum);
+  }
+}
+
+// gw[u] = mean_{i in relation u} fs_i E[s_i] E[o_i]^T + rparam W[p_u]   (skge/rescal.py:61-70)
+// grid = (tiles_b, tiles_a, max segments); 32x32 output tile per CTA, 256 threads x 4 outputs.
+__global__ void __launch_bounds__(256) rescal_gw_kernel(const float *__restrict__ E, const float *__restrict__ W,
+                                                        const int32_t *__restrict__ s,
+                                                        const int32_t *__restrict__ o,
+                                                        const float *__restrict__ fsv, SegLists sl, int d,
+                                                        float rparam, float *__restrict__ gw,
+                                                        int32_t *__restrict__ pidx, int32_t *__restrict__ counts) {
+  __shared__ float ts[32][33], to[32][33], tf[32];
+  const int nseg = sl.meta[0];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && counts) counts[2] = nseg;
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty in 0..7, rows ty, ty+8, ty+16, ty+24
+  for (int seg = blockIdx.z; seg < nseg; seg += gridDim.z) {
+    int beg = sl.seg_start[seg], end = sl.seg_start[seg + 1];
+    int rel = sl.seg_key[seg];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j0 = beg; j0 < end; j0 += 32) {
+      int cnt = min(32, end - j0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < 32 * 32; t += 256) {
+        int e = t >> 5, c = t & 31;
+        float vs = 0.f, vo = 0.f;
+        if (e < cnt) {
+          int ex = sl.vals[j0 + e] >> 3;
+          if (a0 + c < d) vs = __ldg(E + (int64_t)s[ex] * d + a0 + c);
+          if (b0 + c < d) vo = __ldg(E + (int64_t)o[ex] * d + b0 + c);
+        }
+        ts[e][c] = vs;
+        to[e][c] = vo;
+      }
+      if (threadIdx.x < 32) tf[threadIdx.x] = threadIdx.x < cnt ? fsv[sl.vals[j0 + threadIdx.x] >> 3] : 0.f;
+      __syncthreads();
+      for (int e = 0; e < cnt; ++e) {
+        float fo = tf[e] * to[e][tx];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = fmaf(ts[e][ty + 8 * q], fo, acc[q]);
+      }
+    }
+    float inv = 1.0f / (float)(end - beg);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int a = a0 + ty + 8 * q, b = b0 + tx;
+      if (a < d && b < d) {
+        float v = acc[q] * inv;
+        if (rparam != 0.f) v += rparam * __ldg(W + ((int64_t)rel * d + a) * d + b);
+        gw[((int64_t)seg * d + a) * d + b] = v;
+      }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) pidx[seg] = rel;
+  }
+}
+
+static int block_threads(int d) {
+  int t = (d + 31) / 32 * 32;
+  return t < 64 ? 64 : (t > 1024 ? 1024 : t);
+}
+
+static size_t logistic_ws_bytes(int model, int64_t n, int d, int64_t M) {
+  if (n < 1) n = 1;
+  int rows = model == SKGE_MODEL_RESCAL ? 2 : 3;
+  size_t b = align_up((size_t)n * rows * d * sizeof(float));
+  b += seg_workspace_bytes((int64_t)3 * n);
+  if (model == SKGE_MODEL_RESCAL) {
+    int64_t uw = n < M ? n : M;
+    b += align_up((size_t)n * sizeof(float));                     // fs
+    b += seg_workspace_bytes(n);                                  // relation grouping
+    b += align_up((size_t)uw * d * d * sizeof(float));            // gw (step mode)
+    b += align_up((size_t)uw * sizeof(int32_t));                  // pidx (step mode)
+  }
+  return b + 1024;
+}
+
+static int hole_logistic_run(float *E, float *R, float *p2E, float *p2R, const int32_t *s, const int32_t *o,
+                             const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M, int d,
+                             float rparam, bool update, int opt, float lr, int postE, int postR, float *ge,
+                             int32_t *eidx, float *gr, int32_t *ridx, int32_t *counts, double *loss,
+                             double *loss_accum, int32_t *ucE, int32_t *ucR, void *ws, size_t ws_bytes,
+                             cudaStream_t st) {
+  SKGE_REQUIRE(E && R && s && o && p && y && counts && ws, "null argument");
+  SKGE_REQUIRE(n > 0 && d > 0 && d <= 1024 && N > 0 && M > 0, "bad sizes");
+  if (update) SKGE_REQUIRE(opt == SKGE_OPT_SGD || (p2E && p2R), "AdaGrad needs p2E/p2R");
+  else SKGE_REQUIRE(ge && eidx && gr && ridx, "null output");
+  Arena ar(ws, ws_bytes);
+  float *G = ar.take<float>((size_t)n * 3 * d);
+  if (!ar.ok()) {
+    set_error("workspace too small");
+    return SKGE_EWORKSPACE;
+  }
+  SKGE_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
+  if (loss) SKGE_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
+  size_t smem = (6 * (size_t)d + 40) * sizeof(float);
+  SKGE_CUDA(cudaFuncSetAttribute(hole_logistic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = n > kNumSMs * 16 ? kNumSMs * 16 : n;
+  hole_logistic_kernel<<<(int)blocks, block_threads(d), smem, st>>>(E, R, s, o, p, y, n, d, G, loss, loss_accum);
+  SKGE_LAUNCH_CHECK();
+  if (int rc0 = set_i32(counts, (int32_t)n, st)) return rc0;
+  RoleMap rm;
+  const int32_t *idx[3] = {s, o, p};  // entity keys ss+os, relation keys ps: hole.py:31-39
+  for (int r = 0; r < 3; ++r) { rm.idx[r] = idx[r]; rm.is_rel[r] = r == 2; rm.grow[r] = r; rm.gsign[r] = 1.f; }
+  rm.nroles = 3;
+  ParamDesc pd[2];
+  pd[0] = ParamDesc{E, p2E, postE, rparam, ucE, ge, eidx};
+  pd[1] = ParamDesc{R, p2R, postR, rparam, ucR, gr, ridx};
+  return seg_run(rm, nullptr, n, N, M, d, G, 3, pd, update, opt, lr, counts, ar, st);
+}
+
+// sparse update whose row count lives on the device: run over the maximum and
+// let rows >= *U_dev exit (idx rows beyond U are never touched).
+__global__ void __launch_bounds__(256) rescal_w_update_kernel(float *W, float *p2, const float *__restrict__ gw,
+                                                              const int32_t *__restrict__ pidx,
+                                                              const int32_t *__restrict__ counts, int64_t rowlen,
+                                                              int opt, float lr, int32_t *upd_counts) {
+  int U = counts[2];
+  for (int u = blockIdx.y; u < U; u += gridDim.y) {
+    int64_t row = pidx[u];
+    float *x = W + row * rowlen;
+    float *a2 = p2 ? p2 + row * rowlen : nullptr;
+    const float *g = gw + (int64_t)u * rowlen;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < rowlen; c += (int64_t)gridDim.x * blockDim.x) {
+      float gg = __ldg(g + c), xv = x[c];
+      if (opt == SKGE_OPT_ADAGRAD) {
+        float a = a2[c] + gg * gg;
+        a2[c] = a;
+        xv -= lr * gg / fmaxf(sqrtf(a), 1e-7f);
+      } else {
+        xv -= lr * gg;
+      }
+      x[c] = xv;
+    }
+    if (upd_counts && blockIdx.x == 0 && threadIdx.x == 0) upd_counts[row] += 1;
+  }
+}
+
+static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const int32_t *s, const int32_t *o,
+                               const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M, int d,
+                               float rparam, bool update, int opt, float lr, int postE, int postW, float *ge,
+                               int32_t *eidx, float *gw, int32_t *pidx, int32_t *counts, double *loss,
+                               double *loss_accum, int32_t *ucE, int32_t *ucW, void *ws, size_t ws_bytes,
+                               cudaStream_t st) {
+  SKGE_REQUIRE(E && W && s && o && p && y && counts && ws, "null argument");
+  SKGE_REQUIRE(n > 0 && d > 0 && d <= 1024 && N > 0 && M > 0, "bad sizes");
+  SKGE_REQUIRE(postW == SKGE_POST_NONE, "post-hooks on W are not supported");
+  if (update) SKGE_REQUIRE(opt == SKGE_OPT_SGD || (p2E && p2W), "AdaGrad needs p2E/p2W");
+  else SKGE_REQUIRE(ge && eidx && gw && pidx, "null output");
+  Arena ar(ws, ws_bytes);
+  float *G = ar.take<float>((size_t)n * 2 * d);
+  float *fsv = ar.take<float>(n);
+  int64_t uw = n < M ? n : M;
+  if (update) {
+    gw = ar.take<float>((size_t)uw * d * d);
+    pidx = ar.take<int32_t>(uw);
+  }
+  if (!ar.ok()) {
+    set_error("workspace too small");
+    return SKGE_EWORKSPACE;
+  }
+  SKGE_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
+  if (loss) SKGE_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
+  int threads = block_threads(d);
+  if (threads * 4 < d) threads = 256;
+  SKGE_REQUIRE(threads * 4 >= d, "d too large");
+  size_t smem = (3 * (size_t)d + 40) * sizeof(float);
+  int64_t blocks = n > kNumSMs * 16 ? kNumSMs * 16 : n;
+  rescal_logistic_kernel<<<(int)blocks, threads, smem, st>>>(E, W, s, o, p, y, n, d, G, fsv, loss, loss_accum);
+  SKGE_LAUNCH_CHECK();
+  if (int rc0 = set_i32(counts, (int32_t)n, st)) return rc0;
+  // group examples by relation, then the per-relation outer-product mean (reads the OLD E)
+  RoleMap rmw;
+  rmw.idx[0] = p; rmw.is_rel[0] = 0; rmw.grow[0] = 0; rmw.gsign[0] = 1.f; rmw.nroles = 1;
+  SegLists sl;
+  int rc = seg_build(rmw, nullptr, n, M, 0, ar, st, &sl);
+  if (rc) return rc;
+  int tiles = (d + 31) / 32;
+  dim3 grid(tiles, tiles, (unsigned)(uw > 65535 ? 65535 : uw));
+  rescal_gw_kernel<<<grid, 256, 0, st>>>(E, W, s, o, fsv, sl, d, rparam, gw, pidx, counts);
+  SKGE_LAUNCH_CHECK();
+  // entity rows: keys ss+os get (fs*WE, fs*EW): rescal.py:72-74
+  RoleMap rm;
+  const int32_t *idx[2] = {s, o};
+  for (int r = 0; r < 2; ++r) { rm.idx[r] = idx[r]; rm.is_rel[r] = 0; rm.grow[r] = r; rm.gsign[r] = 1.f; }
+  rm.nroles = 2;
+  ParamDesc pd[2];
+  pd[0] = ParamDesc{E, p2E, postE, rparam, ucE, ge, eidx};
+  pd[1] = ParamDesc{nullptr, nullptr, SKGE_POST_NONE, 0.f, nullptr, nullptr, nullptr};
+  int32_t *counts_e = counts;  // seg_run writes counts[1] (U_E) and counts[2] (0 rows of table 1)
+  // keep counts[2] = U_W: run the entity pass first into a scratch pair, then restore
+  int32_t *scratch = ar.take<int32_t>(4);
+  if (!ar.ok()) {
+    set_error("workspace too small");
+    return SKGE_EWORKSPACE;
+  }
+  rc = seg_run(rm, nullptr, n, N, 1, d, G, 2, pd, update, opt, lr, scratch, ar, st);
+  if (rc) return rc;
+  SKGE_CUDA(cudaMemcpyAsync(counts_e + 1, scratch + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (update) {
+    int64_t rowlen = (int64_t)d * d;
+    int bx = (int)((rowlen + 255) / 256);
+    if (bx > 64) bx = 64;
+    dim3 g2(bx, (unsigned)(uw > 65535 ? 65535 : uw));
+    rescal_w_update_kernel<<<g2, 256, 0, st>>>(W, p2W, gw, pidx, counts, rowlen, opt, lr, ucW);
+    SKGE_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace skge
+
+using namespace skge;
+
+extern "C" {
+
+size_t skge_logistic_workspace_bytes(int model, int64_t n, int d, int64_t N, int64_t M) {
+  (void)N;
+  return logistic_ws_bytes(model, n, d, M);
+}
+
+int skge_hole_logistic_grads(const float *E, const float *R, const int32_t *s, const int32_t *o,
+                             const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
+                             int d, float rparam, float *ge, int32_t *eidx, float *gr,
+                             int32_t *ridx, int32_t *counts, double *loss, void *ws,
+                             size_t ws_bytes, skge_stream_t stream) {
+  return hole_logistic_run(const_cast<float *>(E), const_cast<float *>(R), nullptr, nullptr, s, o, p, y, n, N,
+                           M, d, rparam, false, SKGE_OPT_SGD, 0.f, SKGE_POST_NONE, SKGE_POST_NONE, ge, eidx,
+                           gr, ridx, counts, loss, nullptr, nullptr, nullptr, ws, ws_bytes, as_stream(stream));
+}
+
+int skge_hole_logistic_step(float *E, float *R, float *p2E, float *p2R, const int32_t *s,
+                            const int32_t *o, const int32_t *p, const float *y, int64_t n,
+                            int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                            int postE, int postR, int32_t *counts, double *loss_accum,
+                            int32_t *upd_counts_E, int32_t *upd_counts_R, void *ws,
+                            size_t ws_bytes, skge_stream_t stream) {
+  return hole_logistic_run(E, R, p2E, p2R, s, o, p, y, n, N, M, d, rparam, true, opt, lr, postE, postR,
+                           nullptr, nullptr, nullptr, nullptr, counts, nullptr, loss_accum, upd_counts_E,
+                           upd_counts_R, ws, ws_bytes, as_stream(stream));
+}
+
+int skge_rescal_logistic_grads(const float *E, const float *W, const int32_t *s, const int32_t *o,
+                               const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
+                               int d, float rparam, float *ge, int32_t *eidx, float *gw,
+                               int32_t *pidx, int32_t *counts, double *loss, void *ws,
+                               size_t ws_bytes, skge_stream_t stream) {
+  return rescal_logistic_run(const_cast<float *>(E), const_cast<float *>(W), nullptr, nullptr, s, o, p, y, n,
+                             N, M, d, rparam, false, SKGE_OPT_SGD, 0.f, SKGE_POST_NONE, SKGE_POST_NONE, ge,
+                             eidx, gw, pidx, counts, loss, nullptr, nullptr, nullptr, ws, ws_bytes,
+                             as_stream(stream));
+}
+
+int skge_rescal_logistic_step(float *E, float *W, float *p2E, float *p2W, const int32_t *s,
+                              const int32_t *o, const int32_t *p, const float *y, int64_t n,
+                              int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                              int postE, int postW, int32_t *counts, double *loss_accum,
+                              int32_t *upd_counts_E, int32_t *upd_counts_W, void *ws,
+                              size_t ws_bytes, skge_stream_t stream) {
+  return rescal_logistic_run(E, W, p2E, p2W, s, o, p, y, n, N, M, d, rparam, true, opt, lr, postE, postW,
+                             nullptr, nullptr, nullptr, nullptr, counts, nullptr, loss_accum, upd_counts_E,
+                             upd_counts_W, ws, ws_bytes, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,415 @@
+// Filtered ranking: query construction, fp32 coarse sweep with an undecided
+// band, fp64 settlement of band candidates and filter entries.
+//   FilteredRankingEval.positions : skge/base.py:913-1031
+//   TransEEval                    : skge/run_transe.py:13-29 (always L1)
+//   HolEEval                      : skge/run_hole.py:10-19
+//   RESCAL (no reference evaluator): from skge/rescal.py:31-35
+#include "common.cuh"
+
+namespace skge {
+
+// Exact (fp64) score of one entity row against one query vector; all 32 lanes
+// call it and all get the result.  Used for target scores, band candidates and
+// filter entries alike, so equal inputs give bit-equal scores on every GPU.
+__device__ __forceinline__ double score64_warp(int op, const double *__restrict__ q,
+                                               const float *__restrict__ e, int d, int lane) {
+  double acc = 0.0;
+  if (op == SKGE_RANK_L1) {
+    for (int c = lane; c < d; c += 32) acc += fabs((double)__ldg(e + c) - q[c]);
+    return -warp_sum(acc);
+  }
+  for (int c = lane; c < d; c += 32) acc = fma((double)__ldg(e + c), q[c], acc);
+  return warp_sum(acc);
+}
+
+// ---------------------------------------------------------------------------
+// query vectors
+// ---------------------------------------------------------------------------
+// One CTA per query.  q64 is exact up to fp64 rounding:
+//   TransE tail: E[s]+R[p]           head: E[o]-R[p]                (run_transe.py:15-29)
+//   HolE   tail: cconv(R[p],E[s])    head: ccorr(R[p],E[o])         (run_hole.py:12-19)
+//   RESCAL tail: W[p]^T E[s]         head: W[p] E[o]                (rescal.py:31-35)
+__global__ void make_queries_kernel(int model, const float *__restrict__ E, const float *__restrict__ RW,
+                                    const uint8_t *__restrict__ kind, const int32_t *__restrict__ given,
+                                    const int32_t *__restrict__ rel, const int32_t *__restrict__ target,
+                                    int64_t Q, int d, float enorm_max, float coarse_rel,
+                                    double *__restrict__ q64, float *__restrict__ q32,
+                                    double *__restrict__ tscore, float *__restrict__ eps,
+                                    float *__restrict__ qnorm) {
+  extern __shared__ double smd[];
+  double *gv = smd;       // given entity row
+  double *rv = smd + d;   // relation row (TransE / HolE)
+  __shared__ double red[34];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int op = model == SKGE_MODEL_TRANSE ? SKGE_RANK_L1 : SKGE_RANK_DOT;
+  for (int64_t qi = blockIdx.x; qi < Q; qi += gridDim.x) {
+    __syncthreads();
+    const int head = kind[qi];
+    const float *eg = E + (int64_t)given[qi] * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) gv[i] = (double)__ldg(eg + i);
+    if (model != SKGE_MODEL_RESCAL) {
+      const float *rp = RW + (int64_t)rel[qi] * d;
+      for (int i = threadIdx.x; i < d; i += blockDim.x) rv[i] = (double)__ldg(rp + i);
+    }
+    __syncthreads();
+    double *qo = q64 + qi * d;
+    double l1 = 0.0, l2 = 0.0;
+    if (model == SKGE_MODEL_TRANSE) {
+      for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        double v = head ? gv[k] - rv[k] : gv[k] + rv[k];
+        qo[k] = v;
+        q32[qi * d + k] = (float)v;
+        l1 += fabs(v);
+        l2 += v * v;
+      }
+    } else if (model == SKGE_MODEL_HOLE) {
+      for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        double acc = 0.0;
+        if (head) {  // ccorr(r, o)_k = sum_i r_i o_{(i+k) mod d}
+          int j = k;
+          for (int i = 0; i < d; ++i) {
+            acc = fma(rv[i], gv[j], acc);
+            if (++j == d) j = 0;
+          }
+        } else {     // cconv(r, s)_k = sum_i r_i s_{(k-i) mod d}
+          int j = k;
+          for (int i = 0; i < d; ++i) {
+            acc = fma(rv[i], gv[j], acc);
+            if (--j < 0) j = d - 1;
+          }
+        }
+        qo[k] = acc;
+        q32[qi * d + k] = (float)acc;
+        l1 += fabs(acc);
+        l2 += acc * acc;
+      }
+    } else {
+      const float *w = RW + (int64_t)rel[qi] * d * d;
+      if (head) {  // q_i = sum_j W_ij o_j : warp per row, lanes over j
+        for (int r = wid; r < d; r += nw) {
+          double acc = 0.0;
+          for (int j = lane; j < d; j += 32) acc = fma((double)__ldg(w + (int64_t)r * d + j), gv[j], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) {
+            qo[r] = acc;
+            q32[qi * d + r] = (float)acc;
+            l1 += fabs(acc);
+            l2 += acc * acc;
+          }
+        }
+      } else {     // q_j = sum_i W_ij s_i : thread per column j
+        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+          double acc = 0.0;
+          for (int i = 0; i < d; ++i) acc = fma((double)__ldg(w + (int64_t)i * d + j), gv[i], acc);
+          qo[j] = acc;
+          q32[qi * d + j] = (float)acc;
+          l1 += fabs(acc);
+          l2 += acc * acc;
+        }
+      }
+    }
+    l1 = warp_sum(l1);
+    l2 = warp_sum(l2);
+    if (lane == 0) { red[wid] = l1; red[17 + wid] = l2; }
+    __syncthreads();  // also publishes qo[] to warp 0
+    if (wid == 0) {
+      double a = lane < nw ? red[lane] : 0.0, b = lane < nw ? red[17 + lane] : 0.0;
+      a = warp_sum(a);
+      b = warp_sum(b);
+      double t = score64_warp(op, qo, E + (int64_t)target[qi] * d, d, lane);
+      if (lane == 0) {
+        tscore[qi] = t;
+        float n2 = (float)sqrt(b);
+        qnorm[qi] = n2;
+        eps[qi] = op == SKGE_RANK_L1 ? coarse_rel * (float)(fabs(t) + a / (double)(d + 2))
+                                     : coarse_rel * n2 * enorm_max;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// coarse sweep on the FP32 pipes
+// ---------------------------------------------------------------------------
+// 128 queries x 128 entities per CTA step, k staged in chunks of KC through
+// double-buffered shared memory (cp.async), 8x8 accumulators per thread.  Rows
+// are stored with a stride of KC+4 floats so that the 128-bit reads of eight
+// consecutive rows hit disjoint banks.
+static constexpr int BQ = 128, BE = 128, KC = 16, KS = KC + 4;
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+  int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Stage rows [row0, row0+128) x k in [k0, k0+KC) of a row-major [nrows][d] table.
+template <bool VEC4>
+__device__ __forceinline__ void stage_tile(float *dst, const float *__restrict__ src, int64_t row0,
+                                           int64_t nrows, int d, int k0) {
+  if (VEC4) {
+    // 128 rows x 4 float4
+    for (int t = threadIdx.x; t < 128 * (KC / 4); t += blockDim.x) {
+      int r = t >> 2, c = (t & 3) * 4;
+      int64_t row = row0 + r;
+      bool ok = row < nrows && k0 + c < d;  // d % 4 == 0: a float4 is all-in or all-out
+      const float *g = src + (ok ? row * d + k0 + c : 0);
+      cp_async16(dst + r * KS + c, g, ok);
+    }
+  } else {
+    for (int t = threadIdx.x; t < 128 * KC; t += blockDim.x) {
+      int r = t / KC, c = t % KC;
+      int64_t row = row0 + r;
+      bool ok = row < nrows && k0 + c < d;
+      const float *g = src + (ok ? row * d + k0 + c : 0);
+      cp_async4(dst + r * KS + c, g, ok);
+    }
+  }
+}
+
+template <int OP, bool VEC4>
+__global__ void __launch_bounds__(256) rank_sweep_kernel(const float *__restrict__ Eshard, int64_t n_shard,
+                                                         int64_t shard_base, int d,
+                                                         const float *__restrict__ q32,
+                                                         const double *__restrict__ tscore,
+                                                         const float *__restrict__ eps, int64_t Q,
+                                                         int32_t *__restrict__ cnt_gt,
+                                                         int32_t *__restrict__ cand_q,
+                                                         int32_t *__restrict__ cand_e, int64_t cand_cap,
+                                                         unsigned long long *__restrict__ cand_count,
+                                                         int etiles_per_cta) {
+  __shared__ __align__(16) float sq[2][BQ * KS];
+  __shared__ __align__(16) float se[2][BE * KS];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t q0 = (int64_t)blockIdx.x * BQ;
+  const int64_t ntiles_e = (n_shard + BE - 1) / BE;
+  const int64_t et_beg = (int64_t)blockIdx.y * etiles_per_cta;
+  int64_t et_end = et_beg + etiles_per_cta;
+  if (et_end > ntiles_e) et_end = ntiles_e;
+  const int nk = (d + KC - 1) / KC;
+
+  float thi[8], tlo[8];
+  int cnt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t q = q0 + ty + 16 * i;
+    cnt[i] = 0;
+    if (q < Q) {
+      double t = tscore[q], e = (double)eps[q];
+      thi[i] = __double2float_ru(t + e);
+      tlo[i] = __double2float_rd(t - e);
+    } else {
+      thi[i] = INFINITY;   // never counted, never in band
+      tlo[i] = INFINITY;
+    }
+  }
+
+  for (int64_t et = et_beg; et < et_end; ++et) {
+    const int64_t e0 = et * BE;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    __syncthreads();
+    stage_tile<VEC4>(sq[0], q32, q0, Q, d, 0);
+    stage_tile<VEC4>(se[0], Eshard, e0, n_shard, d, 0);
+    cp_async_commit();
+    for (int kc = 0; kc < nk; ++kc) {
+      int cur = kc & 1;
+      if (kc + 1 < nk) {
+        stage_tile<VEC4>(sq[cur ^ 1], q32, q0, Q, d, (kc + 1) * KC);
+        stage_tile<VEC4>(se[cur ^ 1], Eshard, e0, n_shard, d, (kc + 1) * KC);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const float *pq = sq[cur], *pe = se[cur];
+#pragma unroll
+      for (int k4 = 0; k4 < KC; k4 += 4) {
+        float4 qv[8], ev[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qv[i] = *reinterpret_cast<const float4 *>(pq + (ty + 16 * i) * KS + k4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = *reinterpret_cast<const float4 *>(pe + (tx + 16 * j) * KS + k4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (OP == SKGE_RANK_L1) {
+              acc[i][j] += fabsf(qv[i].x - ev[j].x);
+              acc[i][j] += fabsf(qv[i].y - ev[j].y);
+              acc[i][j] += fabsf(qv[i].z - ev[j].z);
+              acc[i][j] += fabsf(qv[i].w - ev[j].w);
+            } else {
+              acc[i][j] = fmaf(qv[i].x, ev[j].x, acc[i][j]);
+              acc[i][j] = fmaf(qv[i].y, ev[j].y, acc[i][j]);
+              acc[i][j] = fmaf(qv[i].z, ev[j].z, acc[i][j]);
+              acc[i][j] = fmaf(qv[i].w, ev[j].w, acc[i][j]);
+            }
+          }
+      }
+      __syncthreads();
+    }
+    // epilogue: compare against the per-query thresholds; never store a score
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int64_t e = e0 + tx + 16 * j;
+      if (e >= n_shard) continue;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s = OP == SKGE_RANK_L1 ? -acc[i][j] : acc[i][j];
+        if (s > thi[i]) {
+          ++cnt[i];
+        } else if (s >= tlo[i]) {
+          unsigned long long slot = atomicAdd(cand_count, 1ull);
+          if ((int64_t)slot < cand_cap) {
+            cand_q[slot] = (int32_t)(q0 + ty + 16 * i);
+            cand_e[slot] = (int32_t)(shard_base + e);
+          }
+        }
+      }
+    }
+  }
+  // the 16 threads sharing ty sit in one half-warp: reduce, then one atomic per query
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = cnt[i];
+    c += __shfl_xor_sync(kFull, c, 8);
+    c += __shfl_xor_sync(kFull, c, 4);
+    c += __shfl_xor_sync(kFull, c, 2);
+    c += __shfl_xor_sync(kFull, c, 1);
+    int64_t q = q0 + ty + 16 * i;
+    if (tx == 0 && q < Q && c) atomicAdd(cnt_gt + q, c);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fp64 settlement
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rank_rescore_kernel(int op, const float *__restrict__ E, int d,
+                                                           const double *__restrict__ q64,
+                                                           const double *__restrict__ tscore,
+                                                           const int32_t *__restrict__ pair_q,
+                                                           const int32_t *__restrict__ pair_e, int64_t npairs,
+                                                           const unsigned long long *__restrict__ npairs_dev,
+                                                           const int32_t *__restrict__ target,
+                                                           int32_t *__restrict__ cnt) {
+  if (npairs_dev) {
+    unsigned long long n = *npairs_dev;
+    if ((int64_t)n < npairs) npairs = (int64_t)n;
+  }
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp; i < npairs; i += nwarps) {
+    int q = pair_q[i], e = pair_e[i];
+    if (target && target[q] == e) continue;
+    double s = score64_warp(op, q64 + (int64_t)q * d, E + (int64_t)e * d, d, lane);
+    if (lane == 0 && s > tscore[q]) atomicAdd(cnt + q, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) rank_scores_one_kernel(int op, const float *__restrict__ E, int64_t N,
+                                                              int d, const double *__restrict__ q64,
+                                                              double *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = warp; e < N; e += nwarps) {
+    double s = score64_warp(op, q64, E + e * d, d, lane);
+    if (lane == 0) out[e] = s;
+  }
+}
+
+}  // namespace skge
+
+using namespace skge;
+
+extern "C" {
+
+int skge_rank_make_queries(int model, const float *E, const float *RW, const uint8_t *kind,
+                           const int32_t *given, const int32_t *rel, const int32_t *target,
+                           int64_t Q, int d, float enorm_max, float coarse_rel, double *q64,
+                           float *q32, double *tscore, float *eps, float *qnorm,
+                           skge_stream_t stream) {
+  SKGE_REQUIRE(E && RW && kind && given && rel && target && q64 && q32 && tscore && eps && qnorm,
+               "null argument");
+  SKGE_REQUIRE(model >= SKGE_MODEL_TRANSE && model <= SKGE_MODEL_RESCAL && d > 0 && d <= 2048 && Q >= 0,
+               "bad sizes");
+  if (Q == 0) return 0;
+  int threads = (d + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
+  int64_t blocks = Q > kNumSMs * 16 ? kNumSMs * 16 : Q;
+  size_t smem = 2 * (size_t)d * sizeof(double);
+  make_queries_kernel<<<(int)blocks, threads, smem, as_stream(stream)>>>(
+      model, E, RW, kind, given, rel, target, Q, d, enorm_max, coarse_rel, q64, q32, tscore, eps, qnorm);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+int skge_rank_sweep(int op, const float *Eshard, int64_t n_shard, int64_t shard_base, int d,
+                    const float *q32, const double *tscore, const float *eps, int64_t Q,
+                    int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
+                    unsigned long long *cand_count, skge_stream_t stream) {
+  SKGE_REQUIRE(Eshard && q32 && tscore && eps && cnt_gt && cand_q && cand_e && cand_count, "null argument");
+  SKGE_REQUIRE((op == SKGE_RANK_L1 || op == SKGE_RANK_DOT) && d > 0 && n_shard >= 0 && Q >= 0, "bad sizes");
+  if (Q == 0 || n_shard == 0) return 0;
+  int64_t qtiles = (Q + BQ - 1) / BQ, etiles = (n_shard + BE - 1) / BE;
+  // split the entity range when there are too few query tiles to fill the GPU
+  int64_t want = 2 * kNumSMs;
+  int64_t ysplit = qtiles >= want ? 1 : (want + qtiles - 1) / qtiles;
+  if (ysplit > etiles) ysplit = etiles;
+  if (ysplit > 65535) ysplit = 65535;
+  int per = (int)((etiles + ysplit - 1) / ysplit);
+  ysplit = (etiles + per - 1) / per;
+  dim3 grid((unsigned)qtiles, (unsigned)ysplit);
+  cudaStream_t st = as_stream(stream);
+  bool v4 = d % 4 == 0;
+#define SKGE_SWEEP(OP, V)                                                                              \
+  rank_sweep_kernel<OP, V><<<grid, 256, 0, st>>>(Eshard, n_shard, shard_base, d, q32, tscore, eps, Q, \
+                                                 cnt_gt, cand_q, cand_e, cand_cap, cand_count, per)
+  if (op == SKGE_RANK_L1) { if (v4) SKGE_SWEEP(SKGE_RANK_L1, true); else SKGE_SWEEP(SKGE_RANK_L1, false); }
+  else { if (v4) SKGE_SWEEP(SKGE_RANK_DOT, true); else SKGE_SWEEP(SKGE_RANK_DOT, false); }
+#undef SKGE_SWEEP
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+int skge_rank_rescore(int op, const float *Efull, int d, const double *q64, const double *tscore,
+                      const int32_t *pair_q, const int32_t *pair_e, int64_t npairs,
+                      const unsigned long long *npairs_dev, const int32_t *target, int32_t *cnt,
+                      skge_stream_t stream) {
+  SKGE_REQUIRE(Efull && q64 && tscore && pair_q && pair_e && cnt, "null argument");
+  SKGE_REQUIRE((op == SKGE_RANK_L1 || op == SKGE_RANK_DOT) && d > 0 && npairs >= 0, "bad sizes");
+  if (npairs == 0) return 0;
+  int64_t blocks = (npairs + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  rank_rescore_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(op, Efull, d, q64, tscore, pair_q, pair_e,
+                                                                 npairs, npairs_dev, target, cnt);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+int skge_rank_scores_one(int op, const float *E, int64_t N, int d, const double *q64, double *out,
+                         skge_stream_t stream) {
+  SKGE_REQUIRE(E && q64 && out && N >= 0 && d > 0, "bad arguments");
+  if (N == 0) return 0;
+  int64_t blocks = (N + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  rank_scores_one_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(op, E, N, d, q64, out);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,467 @@
+// Segment build (radix sort of row ids), segmented mean of gradient rows and the
+// fused sparse SGD/AdaGrad update with row post-hooks.
+//   grad_sum_matrix + Sm.dot(G)/n : skge/util.py:53-101, skge/transe.py:128-160,
+//                                   skge/hole.py:31-40,69-97
+//   SGD / AdaGrad / normalize / normless1 : skge/param.py:108-174
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "segment.cuh"
+
+namespace skge {
+
+// ---------------------------------------------------------------------------
+// keys -> sorted segments
+// ---------------------------------------------------------------------------
+
+__global__ void build_keys_kernel(RoleMap rm, const uint8_t *__restrict__ flags, int64_t P, int N,
+                                  int sentinel, int32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+  int64_t L = (int64_t)rm.nroles * P;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < L; t += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(t / P);
+    int64_t i = t - (int64_t)r * P;
+    bool ok = flags ? flags[i] != 0 : true;
+    keys[t] = ok ? rm.idx[r][i] + (rm.is_rel[r] ? N : 0) : sentinel;
+    vals[t] = (int32_t)(i * 8 + r);
+  }
+}
+
+__global__ void mark_heads_kernel(const int32_t *__restrict__ keys, int64_t L, int sentinel,
+                                  int32_t *__restrict__ head) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x)
+    head[i] = (keys[i] != sentinel) && (i == 0 || keys[i] != keys[i - 1]);
+}
+
+// meta: [0] nseg, [1] segments of table 0 (keys < N), [3] number of valid keys. Pre-zeroed.
+__global__ void scatter_heads_kernel(const int32_t *__restrict__ keys, const int32_t *__restrict__ head,
+                                     const int32_t *__restrict__ pos, int64_t L, int N, int sentinel,
+                                     int32_t *__restrict__ seg_start, int32_t *__restrict__ seg_key,
+                                     int32_t *__restrict__ meta) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = keys[i];
+    if (k == sentinel) continue;
+    int h = head[i], ps = pos[i];
+    if (h) {
+      seg_start[ps] = (int32_t)i;
+      seg_key[ps] = k;
+      if (k >= N && (i == 0 || keys[i - 1] < N)) meta[1] = ps;  // first segment of table 1
+    }
+    if (i == L - 1 || keys[i + 1] == sentinel) {  // last valid key
+      int nseg = ps + h;
+      meta[0] = nseg;
+      meta[3] = (int32_t)(i + 1);
+      seg_start[nseg] = (int32_t)(i + 1);
+      if (k < N) meta[1] = nseg;  // no table-1 segments at all
+    }
+  }
+}
+
+__global__ void set_i32_kernel(int32_t *p, int32_t v) { *p = v; }
+int set_i32(int32_t *p, int32_t v, cudaStream_t st) {
+  set_i32_kernel<<<1, 1, 0, st>>>(p, v);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+static int key_bits(int64_t maxkey) {
+  int b = 1;
+  while (((int64_t)1 << b) <= maxkey) ++b;
+  return b;
+}
+
+static size_t cub_sort_bytes(int64_t L) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
+                                  (const int32_t *)nullptr, (int32_t *)nullptr, (int)L, 0, 32);
+  return bytes;
+}
+static size_t cub_scan_bytes(int64_t L) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (int)L);
+  return bytes;
+}
+
+size_t seg_workspace_bytes(int64_t L) {
+  if (L < 1) L = 1;
+  size_t b = 0;
+  b += 4 * align_up((size_t)L * 4);        // keys in/out, vals in/out
+  b += 2 * align_up((size_t)L * 4);        // head, pos
+  b += 2 * align_up((size_t)(L + 1) * 4);  // seg_start, seg_key
+  b += align_up(16);                       // meta
+  size_t c1 = cub_sort_bytes(L), c2 = cub_scan_bytes(L);
+  b += align_up(c1 > c2 ? c1 : c2);
+  return b + 1024;
+}
+
+int seg_build(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64_t M, Arena &ar,
+              cudaStream_t st, SegLists *out) {
+  int64_t L = (int64_t)rm.nroles * P;
+  SKGE_REQUIRE(L > 0 && L < ((int64_t)1 << 31) && P < ((int64_t)1 << 28), "minibatch too large");
+  SKGE_REQUIRE(N + M < ((int64_t)1 << 31) - 1, "too many rows");
+  int32_t *keys_in = ar.take<int32_t>(L), *keys_out = ar.take<int32_t>(L);
+  int32_t *vals_in = ar.take<int32_t>(L), *vals_out = ar.take<int32_t>(L);
+  int32_t *head = ar.take<int32_t>(L), *pos = ar.take<int32_t>(L);
+  int32_t *seg_start = ar.take<int32_t>(L + 1), *seg_key = ar.take<int32_t>(L + 1);
+  int32_t *meta = ar.take<int32_t>(4);
+  size_t c1 = cub_sort_bytes(L), c2 = cub_scan_bytes(L);
+  size_t cub_bytes = c1 > c2 ? c1 : c2;
+  void *cub_tmp = ar.take<char>(cub_bytes);
+  if (!ar.ok()) {
+    set_error("workspace too small: need %zu bytes, have %zu", ar.off, ar.cap);
+    return SKGE_EWORKSPACE;
+  }
+  int sentinel = (int)(N + M);
+  int threads = 256;
+  int blocks = (int)((L + threads - 1) / threads);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  SKGE_CUDA(cudaMemsetAsync(meta, 0, 16, st));
+  build_keys_kernel<<<blocks, threads, 0, st>>>(rm, flags, P, (int)N, sentinel, keys_in, vals_in);
+  SKGE_LAUNCH_CHECK();
+  size_t tb = cub_bytes;
+  SKGE_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys_in, keys_out, vals_in, vals_out, (int)L, 0,
+                                            key_bits(sentinel), st));
+  mark_heads_kernel<<<blocks, threads, 0, st>>>(keys_out, L, sentinel, head);
+  SKGE_LAUNCH_CHECK();
+  tb = cub_bytes;
+  SKGE_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, head, pos, (int)L, st));
+  scatter_heads_kernel<<<blocks, threads, 0, st>>>(keys_out, head, pos, L, (int)N, sentinel, seg_start,
+                                                   seg_key, meta);
+  SKGE_LAUNCH_CHECK();
+  out->vals = vals_out;
+  out->seg_start = seg_start;
+  out->seg_key = seg_key;
+  out->meta = meta;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// row update (shared by the fused segment kernel and skge_sparse_update)
+// ---------------------------------------------------------------------------
+
+// One warp owns one row of d floats, held as g[MAXC][VEC] per lane
+// (column = (c*32 + lane)*VEC + v).  Applies rparam, the optimiser step and the
+// post-hook and writes the row (and p2) exactly once.
+template <int VEC, int MAXC>
+__device__ __forceinline__ void row_update(float *xrow, float *p2row, float (&g)[MAXC][VEC], int d,
+                                           int lane, int opt, float lr, int post, float rparam) {
+  float x[MAXC][VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    int col = (c * 32 + lane) * VEC;
+    if (col < d) {
+      ld_vec_rw<VEC>(xrow + col, x[c]);
+      if (opt == SKGE_OPT_ADAGRAD) {
+        float p2[VEC];
+        ld_vec_rw<VEC>(p2row + col, p2);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float gg = g[c][v] + rparam * x[c][v];
+          p2[v] += gg * gg;                                   // skge/param.py:147
+          float H = fmaxf(sqrtf(p2[v]), 1e-7f);               // skge/param.py:152
+          x[c][v] -= lr * gg / H;                             // skge/param.py:155
+        }
+        st_vec<VEC>(p2row + col, p2);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[c][v] -= lr * (g[c][v] + rparam * x[c][v]);  // skge/param.py:130
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) ss += x[c][v] * x[c][v];
+    }
+  }
+  float scale = 1.f;
+  if (post != SKGE_POST_NONE) {
+    ss = warp_sum(ss);
+    if (post == SKGE_POST_NORMALIZE) scale = 1.0f / sqrtf(ss);           // skge/param.py:165-166
+    else scale = 1.0f / (ss < 1.0f ? 1.0f : ss);                        // skge/param.py:171-173 (squared norm)
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    int col = (c * 32 + lane) * VEC;
+    if (col < d) {
+      if (post != SKGE_POST_NONE) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[c][v] *= scale;
+      }
+      st_vec<VEC>(xrow + col, x[c]);
+    }
+  }
+}
+
+struct SegArgs {
+  const int32_t *seg_start, *seg_key, *vals, *meta;
+  const float *G;
+  int rows_per_unit, d, N;
+  int grow[8];
+  float gsign[8];
+  ParamDesc pd[2];
+  int opt;
+  float lr;
+  int32_t *counts;
+};
+
+template <int VEC, int MAXC, bool UPDATE>
+__global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int nseg = a.meta[0];
+  const int U0 = a.meta[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.counts) {
+    a.counts[1] = U0;
+    a.counts[2] = nseg - U0;
+  }
+  int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int d = a.d;
+  for (int seg = warp; seg < nseg; seg += nwarps) {
+    int key = a.seg_key[seg];
+    int beg = a.seg_start[seg], end = a.seg_start[seg + 1];
+    int which = key >= a.N;
+    int64_t row = which ? key - a.N : key;
+    float acc[MAXC][VEC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
+#pragma unroll 2
+    for (int j = beg; j < end; ++j) {
+      int val = a.vals[j];
+      int r = val & 7;
+      const float *g = a.G + ((int64_t)(val >> 3) * a.rows_per_unit + a.grow[r]) * d;
+      float sgn = a.gsign[r];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        int col = (c * 32 + lane) * VEC;
+        if (col < d) {
+          float t[VEC];
+          ld_vec<VEC>(g + col, t);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(sgn, t[v], acc[c][v]);
+        }
+      }
+    }
+    float n = (float)(end - beg);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[c][v] /= n;  // the mean: skge/util.py:97-101
+    const ParamDesc &pd = a.pd[which];
+    if (UPDATE) {
+      row_update<VEC, MAXC>(pd.param + row * d, pd.p2 ? pd.p2 + row * d : nullptr, acc, d, lane, a.opt,
+                            a.lr, pd.post, pd.rparam);
+      if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
+    } else {
+      int64_t u = which ? seg - U0 : seg;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        int col = (c * 32 + lane) * VEC;
+        if (col < d) {
+          if (pd.rparam != 0.f) {
+            float x[VEC];
+            ld_vec<VEC>(pd.param + row * d + col, x);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[c][v] += pd.rparam * x[v];
+          }
+          st_vec<VEC>(pd.out_g + u * d + col, acc[c]);
+        }
+      }
+      if (lane == 0) pd.out_idx[u] = (int32_t)row;
+    }
+  }
+}
+
+template <int VEC, int MAXC>
+static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
+  if (update) seg_reduce_kernel<VEC, MAXC, true><<<blocks, 256, 0, st>>>(a);
+  else seg_reduce_kernel<VEC, MAXC, false><<<blocks, 256, 0, st>>>(a);
+}
+
+template <int VEC>
+static int dispatch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
+  int chunks = (a.d + 32 * VEC - 1) / (32 * VEC);
+  if (chunks <= 1) launch_seg_reduce<VEC, 1>(a, update, blocks, st);
+  else if (chunks <= 2) launch_seg_reduce<VEC, 2>(a, update, blocks, st);
+  else if (chunks <= 4) launch_seg_reduce<VEC, 4>(a, update, blocks, st);
+  else if (chunks <= 8) launch_seg_reduce<VEC, 8>(a, update, blocks, st);
+  else {
+    set_error("row length %d not supported by the warp-per-row update (max %d)", a.d, 256 * VEC);
+    return SKGE_EINVAL;
+  }
+  return 0;
+}
+
+int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64_t M, int d,
+            const float *G, int rows_per_unit, const ParamDesc pd[2], bool update, int opt, float lr,
+            int32_t *counts, Arena &ar, cudaStream_t st) {
+  SegLists sl;
+  int rc = seg_build(rm, flags, P, N, M, ar, st, &sl);
+  if (rc) return rc;
+  SegArgs a;
+  a.seg_start = sl.seg_start;
+  a.seg_key = sl.seg_key;
+  a.vals = sl.vals;
+  a.meta = sl.meta;
+  a.G = G;
+  a.rows_per_unit = rows_per_unit;
+  a.d = d;
+  a.N = (int)N;
+  for (int r = 0; r < 8; ++r) {
+    a.grow[r] = r < rm.nroles ? rm.grow[r] : 0;
+    a.gsign[r] = r < rm.nroles ? rm.gsign[r] : 0.f;
+  }
+  a.pd[0] = pd[0];
+  a.pd[1] = pd[1];
+  a.opt = opt;
+  a.lr = lr;
+  a.counts = counts;
+  int64_t L = (int64_t)rm.nroles * P;
+  int64_t maxseg = L < N + M ? L : N + M;
+  int64_t blocks = (maxseg + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (blocks < 1) blocks = 1;
+  switch (pick_vec(d)) {
+    case 4: rc = dispatch_seg_reduce<4>(a, update, (int)blocks, st); break;
+    case 2: rc = dispatch_seg_reduce<2>(a, update, (int)blocks, st); break;
+    default: rc = dispatch_seg_reduce<1>(a, update, (int)blocks, st); break;
+  }
+  if (rc) return rc;
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// standalone ParameterUpdate.__call__(g, idx) and post-hooks
+// ---------------------------------------------------------------------------
+
+template <int VEC, int MAXC>
+__global__ void __launch_bounds__(256) sparse_update_warp_kernel(float *param, float *p2,
+                                                                 const float *__restrict__ g,
+                                                                 const int32_t *__restrict__ idx, int64_t U,
+                                                                 int d, int opt, float lr, int post,
+                                                                 int32_t *upd_counts) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t u = warp; u < U; u += nwarps) {
+    int64_t row = idx ? idx[u] : u;
+    float gr[MAXC][VEC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      int col = (c * 32 + lane) * VEC;
+      if (col < d) {
+        if (g) ld_vec<VEC>(g + u * d + col, gr[c]);
+        else
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) gr[c][v] = 0.f;
+      }
+    }
+    row_update<VEC, MAXC>(param + row * d, p2 ? p2 + row * d : nullptr, gr, d, lane, opt, lr, post, 0.f);
+    if (upd_counts && lane == 0) upd_counts[row] += 1;
+  }
+}
+
+// Long rows (RESCAL's W: d*d floats): one CTA per row, two passes when a post-hook is set.
+__global__ void __launch_bounds__(256) sparse_update_block_kernel(float *param, float *p2,
+                                                                  const float *__restrict__ g,
+                                                                  const int32_t *__restrict__ idx, int64_t U,
+                                                                  int64_t rowlen, int opt, float lr, int post,
+                                                                  int32_t *upd_counts) {
+  __shared__ float red[40];
+  for (int64_t u = blockIdx.x; u < U; u += gridDim.x) {
+    int64_t row = idx ? idx[u] : u;
+    float *x = param + row * rowlen;
+    float *a2 = p2 ? p2 + row * rowlen : nullptr;
+    const float *gu = g ? g + u * rowlen : nullptr;
+    float ss = 0.f;
+    for (int64_t c = threadIdx.x; c < rowlen; c += blockDim.x) {
+      float xv = x[c];
+      float gg = gu ? __ldg(gu + c) : 0.f;
+      if (opt == SKGE_OPT_ADAGRAD) {
+        float a = a2[c] + gg * gg;
+        a2[c] = a;
+        xv -= lr * gg / fmaxf(sqrtf(a), 1e-7f);
+      } else {
+        xv -= lr * gg;
+      }
+      x[c] = xv;
+      ss += xv * xv;
+    }
+    if (post != SKGE_POST_NONE) {
+      __syncthreads();
+      // block_sum inline (red is static here)
+      ss = warp_sum(ss);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) red[32] = t;
+      }
+      __syncthreads();
+      float tot = red[32];
+      float scale = post == SKGE_POST_NORMALIZE ? 1.0f / sqrtf(tot) : 1.0f / (tot < 1.0f ? 1.0f : tot);
+      for (int64_t c = threadIdx.x; c < rowlen; c += blockDim.x) x[c] *= scale;
+      __syncthreads();
+    }
+    if (upd_counts && threadIdx.x == 0) upd_counts[row] += 1;
+  }
+}
+
+template <int VEC>
+static bool launch_sparse_warp(float *param, float *p2, const float *g, const int32_t *idx, int64_t U, int d,
+                               int opt, float lr, int post, int32_t *uc, cudaStream_t st) {
+  int chunks = (d + 32 * VEC - 1) / (32 * VEC);
+  int64_t blocks = (U + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (chunks <= 1) sparse_update_warp_kernel<VEC, 1><<<(int)blocks, 256, 0, st>>>(param, p2, g, idx, U, d, opt, lr, post, uc);
+  else if (chunks <= 2) sparse_update_warp_kernel<VEC, 2><<<(int)blocks, 256, 0, st>>>(param, p2, g, idx, U, d, opt, lr, post, uc);
+  else if (chunks <= 4) sparse_update_warp_kernel<VEC, 4><<<(int)blocks, 256, 0, st>>>(param, p2, g, idx, U, d, opt, lr, post, uc);
+  else if (chunks <= 8) sparse_update_warp_kernel<VEC, 8><<<(int)blocks, 256, 0, st>>>(param, p2, g, idx, U, d, opt, lr, post, uc);
+  else return false;
+  return true;
+}
+
+static int sparse_update_impl(float *param, float *p2, const float *g, const int32_t *idx, int64_t U,
+                              int64_t rowlen, int opt, float lr, int post, int32_t *uc, cudaStream_t st) {
+  bool done = false;
+  if (rowlen <= 1024) {
+    int d = (int)rowlen;
+    switch (pick_vec(rowlen)) {
+      case 4: done = launch_sparse_warp<4>(param, p2, g, idx, U, d, opt, lr, post, uc, st); break;
+      case 2: done = launch_sparse_warp<2>(param, p2, g, idx, U, d, opt, lr, post, uc, st); break;
+      default: done = launch_sparse_warp<1>(param, p2, g, idx, U, d, opt, lr, post, uc, st); break;
+    }
+  }
+  if (!done) {
+    int64_t blocks = U > kNumSMs * 8 ? kNumSMs * 8 : U;
+    sparse_update_block_kernel<<<(int)blocks, 256, 0, st>>>(param, p2, g, idx, U, rowlen, opt, lr, post, uc);
+  }
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace skge
+
+using namespace skge;
+
+extern "C" {
+
+int skge_sparse_update(float *param, float *p2, const float *g, const int32_t *idx, int64_t U,
+                       int64_t rowlen, int opt, float lr, int post, int32_t *upd_counts,
+                       skge_stream_t stream) {
+  SKGE_REQUIRE(param && g && rowlen > 0 && U >= 0, "bad arguments");
+  SKGE_REQUIRE(opt == SKGE_OPT_SGD || (opt == SKGE_OPT_ADAGRAD && p2), "AdaGrad needs p2");
+  if (U == 0) return 0;
+  return sparse_update_impl(param, p2, g, idx, U, rowlen, opt, lr, post, upd_counts, as_stream(stream));
+}
+
+int skge_rows_post(float *param, const int32_t *idx, int64_t U, int64_t rowlen, int post,
+                   skge_stream_t stream) {
+  SKGE_REQUIRE(param && rowlen > 0 && U >= 0, "bad arguments");
+  if (U == 0 || post == SKGE_POST_NONE) return 0;
+  // SGD with a null gradient leaves the row unchanged and then applies the post-hook
+  return sparse_update_impl(param, nullptr, nullptr, idx, U, rowlen, SKGE_OPT_SGD, 0.f, post, nullptr,
+                            as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// Sorted-index segmented reduction + sparse row update (shared by every
+// training path).  Replaces grad_sum_matrix + Sm.dot(G)/n (skge/util.py:53-101)
+// and ParameterUpdate.__call__ (skge/param.py:108-174).
+#pragma once
+#include "common.cuh"
+
+namespace skge {
+
+static constexpr int kMaxRoles = 6;
+
+// How the occurrences of rows in a minibatch map to per-unit gradient rows.
+// Unit i (a pair or an example) owns `rows_per_unit` rows in G; role r says
+// "row idx[r][i] of table is_rel[r] receives gsign[r] * G[i][grow[r]]".
+struct RoleMap {
+  const int32_t *idx[kMaxRoles];
+  int is_rel[kMaxRoles];
+  int grow[kMaxRoles];
+  float gsign[kMaxRoles];
+  int nroles;
+};
+
+// One parameter table (E, or the relation table R).
+struct ParamDesc {
+  float *param;        // table, row-major [rows][d]
+  float *p2;           // AdaGrad accumulator (UPDATE + ADAGRAD only)
+  int post;            // SKGE_POST_*
+  float rparam;        // g += rparam * row  (skge/hole.py:33,40,83)
+  int32_t *upd_counts; // nullable
+  float *out_g;        // emit mode: [U][d]
+  int32_t *out_idx;    // emit mode: [U]
+};
+
+size_t seg_workspace_bytes(int64_t L);
+
+// Builds keys from `rm` (masked by flags, nullable), sorts, finds segments and
+// either emits (mean gradient, row id) per unique row (update == false) or
+// applies the optimiser step in place (update == true).  counts[1], counts[2]
+// receive the number of unique rows of table 0 / table 1.
+int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64_t M, int d,
+            const float *G, int rows_per_unit, const ParamDesc pd[2], bool update, int opt, float lr,
+            int32_t *counts, Arena &ar, cudaStream_t st);
+
+// *p = v on the stream (keeps the step capturable in a CUDA graph)
+int set_i32(int32_t *p, int32_t v, cudaStream_t st);
+
+// Sort-only service for callers with their own reduction (RESCAL's W gradient):
+// sorted unit ids grouped by key, with segment starts/keys and meta[0] = nseg.
+struct SegLists {
+  const int32_t *vals;       // sorted payload (unit * 8 + role)
+  const int32_t *seg_start;  // [nseg + 1]
+  const int32_t *seg_key;    // [nseg]
+  const int32_t *meta;       // [0] = nseg, [1] = segments of table 0
+};
+int seg_build(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64_t M, Arena &ar,
+              cudaStream_t st, SegLists *out);
+
+}  // namespace skge

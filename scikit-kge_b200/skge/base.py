@@ -1,0 +1,387 @@
+"""Model base class and the stochastic trainers (reference: skge/base.py:1140-1427).
+
+Same constructor keywords, attributes and callback protocol as the reference.
+Two execution paths:
+
+* fused (default whenever the model, the updater class and the sampler are the
+  built-in ones): the training triples are marshalled ONCE into int32 SoA device
+  arrays at ``fit`` time and every minibatch is sample -> score -> mask ->
+  segmented mean -> sparse update on the stream, with one host read
+  (``nviolations`` / ``loss``) per epoch;
+* hook path (custom ``_gradients`` / ``param_update`` / ``samplef``): the
+  reference's control flow verbatim, calling the same kernels through the
+  model's ``_gradients`` / ``_pairwise_gradients`` and the updaters.
+"""
+import pickle
+import timeit
+
+import numpy as np
+import torch
+
+from . import _ext, kernels
+from .param import Parameter, AdaGrad, SGD, post_code
+
+_DEF_NBATCHES = 100
+_DEF_POST_EPOCH = []
+_DEF_LEARNING_RATE = 0.1
+_DEF_SAMPLE_FUN = None
+_DEF_MAX_EPOCHS = 1000
+_DEF_MARGIN = 1.0
+# Deviation from the reference (skge/base.py:35-36, 1336-1346): a bare
+# PairwiseStochasticTrainer(model) does NOT open gradients.txt / embeddings.txt
+# in the working directory; pass file_grad= / file_embed= to get the dumps.
+_FILE_GRADIENTS = None
+_FILE_EMBEDDINGS = None
+
+
+class Model(object):
+    """Base class of the knowledge-graph models (skge/base.py:1140-1192).
+
+    Subclasses implement ``_scores(ss, ps, os)``, ``_gradients(xys)`` and / or
+    ``_pairwise_gradients(pxs, nxs)``.
+    """
+
+    track_counters = True   # per-entity instrumentation counters of the fork (cheap device atomics)
+
+    def __init__(self, *args, **kwargs):
+        self.params = {}
+        self.hyperparams = {}
+        self.add_hyperparam('init', kwargs.pop('init', 'nunif'))
+
+    def add_param(self, param_id, shape, post=None, value=None):
+        if value is None:
+            value = Parameter(shape, self.init, name=param_id, post=post)
+        setattr(self, param_id, value)
+        self.params[param_id] = value
+
+    def add_hyperparam(self, param_id, value):
+        setattr(self, param_id, value)
+        self.hyperparams[param_id] = value
+
+    def __getstate__(self):
+        return {'hyperparams': self.hyperparams, 'params': self.params}
+
+    def __setstate__(self, st):
+        self.params = {}
+        self.hyperparams = {}
+        for pid, p in st['params'].items():
+            self.add_param(pid, None, None, value=p)
+        for pid, p in st['hyperparams'].items():
+            self.add_hyperparam(pid, p)
+
+    def save(self, fname, protocol=pickle.HIGHEST_PROTOCOL):
+        with open(fname, 'wb') as fout:
+            pickle.dump(self, fout, protocol=protocol)
+
+    @staticmethod
+    def load(fname):
+        with open(fname, 'rb') as fin:
+            return pickle.load(fin)
+
+
+def _triples_to_device(xs):
+    """list / array of (s, o, p) -> three int32 CUDA tensors (SoA)."""
+    if isinstance(xs, torch.Tensor):
+        a = xs.to(_ext.device())
+        return tuple(a[:, i].to(torch.int32).contiguous() for i in range(3))
+    a = np.asarray(xs, dtype=np.int64).reshape(-1, 3)
+    t = torch.from_numpy(np.ascontiguousarray(a.T, dtype=np.int32)).to(_ext.device())
+    return t[0].contiguous(), t[1].contiguous(), t[2].contiguous()
+
+
+def _opt_code(pu):
+    """SKGE_OPT_* when the updater CLASS is exactly the built-in SGD / AdaGrad."""
+    if pu is SGD:
+        return _ext.OPT_SGD
+    if pu is AdaGrad:
+        return _ext.OPT_ADAGRAD
+    return None
+
+
+class StochasticTrainer(object):
+    """Stochastic gradient descent trainer with scalar (logistic) loss
+    (skge/base.py:1195-1316).  Models implement ``_gradients(xys)``."""
+
+    def __init__(self, *args, **kwargs):
+        self.model = args[0]
+        self.hyperparams = {}
+        self.add_hyperparam('max_epochs', kwargs.pop('max_epochs', _DEF_MAX_EPOCHS))
+        self.add_hyperparam('nbatches', kwargs.pop('nbatches', _DEF_NBATCHES))
+        self.add_hyperparam('learning_rate', kwargs.pop('learning_rate', _DEF_LEARNING_RATE))
+        self.post_epoch = kwargs.pop('post_epoch', _DEF_POST_EPOCH)
+        self.samplef = kwargs.pop('samplef', _DEF_SAMPLE_FUN)
+        pu = kwargs.pop('param_update', AdaGrad)
+        self._param_update = pu
+        self._updaters = {key: pu(param, self.learning_rate) for key, param in self.model.params.items()}
+        self.seed = kwargs.pop('seed', 42)       # the reference seeds numpy with 42 at import
+        self.fused = kwargs.pop('fused', True)   # set False to force the reference's hook path
+        self._gen = None
+
+    def set_max_epochs(self, epoch):
+        self.max_epochs = epoch
+
+    def __getstate__(self):
+        return self.hyperparams
+
+    def __setstate__(self, st):
+        self.hyperparams = {}
+        for pid, p in st.items():
+            self.add_hyperparam(pid, p)
+
+    def add_hyperparam(self, param_id, value):
+        setattr(self, param_id, value)
+        self.hyperparams[param_id] = value
+
+    # -- shared machinery ---------------------------------------------------------
+    def _device_sampler(self):
+        """The built-in sampler object behind ``samplef`` (None if user code)."""
+        from .sample import Sampler
+        owner = getattr(self.samplef, '__self__', None)
+        if isinstance(owner, Sampler) and getattr(self.samplef, '__func__', None) is Sampler.sample \
+                and owner.device_ready():
+            return owner
+        return None
+
+    def _can_fuse(self, fused_attr):
+        if not self.fused or _opt_code(self._param_update) is None:
+            return False
+        if not hasattr(self.model, fused_attr) or hasattr(self.model, '_prepare_batch_step'):
+            return False
+        if any(post_code(p.post) is None for p in self.model.params.values()):
+            return False
+        return self.samplef is None or self._device_sampler() is not None
+
+    def _randperm(self, n):
+        if self._gen is None:
+            self._gen = torch.Generator(device=_ext.device())
+            self._gen.manual_seed(int(self.seed))
+        return torch.randperm(n, device=_ext.device(), generator=self._gen, dtype=torch.int64)
+
+    def _batch_bounds(self, n):
+        """nbatches slices of n // nbatches plus a remainder slice when
+        n % nbatches != 0 (skge/base.py:1246-1252, 1268)."""
+        self.batch_size = n // self.nbatches
+        cuts = list(range(self.batch_size, n, self.batch_size))
+        return list(zip([0] + cuts, cuts + [n]))
+
+    def _run_epochs(self, n, step):
+        """The epoch loop of ``_optim`` (skge/base.py:1254-1291); ``step(batch)``
+        gets an int32 CUDA tensor of example indices."""
+        bounds = self._batch_bounds(n)
+        for self.epoch in range(1, self.max_epochs + 1):
+            self._pre_epoch()
+            perm = self._randperm(n).to(torch.int32)
+            self.epoch_start = timeit.default_timer()
+            for lo, hi in bounds:
+                step(perm[lo:hi])
+            self._end_epoch()
+            for f in self.post_epoch:
+                if not f(self):
+                    break   # as in the reference, this only leaves the callback loop
+
+    # -- reference API ----------------------------------------------------------------
+    def fit(self, xs, ys):
+        if self._can_fuse('_fused_logistic_step'):
+            self._fit_fused(xs, ys)
+        else:
+            self._optim(list(zip(xs, ys)))
+
+    def _pre_epoch(self):
+        self.loss = 0
+        if getattr(self, '_loss_dev', None) is not None:
+            self._loss_dev.zero_()
+
+    def _end_epoch(self):
+        if getattr(self, '_loss_dev', None) is not None:
+            self.loss = float(self._loss_dev.item())
+
+    def _fit_fused(self, xs, ys):
+        dev = _ext.device()
+        s, o, p = _triples_to_device(xs)
+        y = _ext.as_f32(np.asarray(ys, dtype=np.float32))
+        n = s.numel()
+        self._loss_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        sampler = self._device_sampler() if self.samplef is not None else None
+        state = {'calls': 0}
+
+        def step(batch):
+            bl = batch.long()
+            bs, bo, bp, by = s[bl], o[bl], p[bl], y[bl]
+            if sampler is not None:
+                _, neg, valid = sampler.device_sample(None, batch.numel(), state['calls'], src=(bs, bo, bp))
+                state['calls'] += 1
+                keep = valid.bool()
+                bs = torch.cat([bs, neg[0][keep]])
+                bo = torch.cat([bo, neg[1][keep]])
+                bp = torch.cat([bp, neg[2][keep]])
+                by = torch.cat([by, torch.full((int(keep.sum()),), -1.0, device=dev)])
+            self.model._fused_logistic_step(self._updaters, bs.contiguous(), bo.contiguous(), bp.contiguous(),
+                                            by.contiguous(), self._counts, self._loss_dev)
+
+        self._run_epochs(n, step)
+
+    def _optim(self, xys):
+        """Hook path: the reference's loop on host lists (skge/base.py:1242-1291)."""
+        idx = np.arange(len(xys))
+        self.batch_size = len(xys) // self.nbatches
+        batch_idx = np.arange(self.batch_size, len(xys), self.batch_size)
+        rng = np.random.RandomState(self.seed)
+        for self.epoch in range(1, self.max_epochs + 1):
+            self._pre_epoch()
+            rng.shuffle(idx)
+            self.epoch_start = timeit.default_timer()
+            for batch in np.split(idx, batch_idx):
+                bxys = [xys[z] for z in batch]
+                self._process_batch(bxys)
+            for f in self.post_epoch:
+                if not f(self):
+                    break
+
+    def _process_batch(self, xys):
+        if self.samplef is not None:
+            xys += self.samplef(xys)
+        if hasattr(self.model, '_prepare_batch_step'):
+            self.model._prepare_batch_step(xys)
+        grads = self.model._gradients(xys)
+        self.loss += self.model.loss
+        self._batch_step(grads)
+
+    def _batch_step(self, grads):
+        for paramID in self._updaters.keys():
+            self._updaters[paramID](*grads[paramID])
+
+
+class PairwiseStochasticTrainer(StochasticTrainer):
+    """Stochastic gradient descent trainer with pairwise ranking loss
+    (skge/base.py:1320-1427).  Models implement ``_pairwise_gradients(pxs, nxs)``."""
+
+    def __init__(self, *args, **kwargs):
+        margin = kwargs.pop('margin', _DEF_MARGIN)
+        fg = kwargs.pop('file_grad', _FILE_GRADIENTS)
+        fe = kwargs.pop('file_embed', _FILE_EMBEDDINGS)
+        super(PairwiseStochasticTrainer, self).__init__(*args, **kwargs)
+        self.model.add_hyperparam('margin', margin)   # stored on the MODEL (skge/base.py:1335)
+        self.file_gradients = open(fg, 'w') if fg is not None else None
+        self.file_embeddings = open(fe, 'w') if fe is not None else None
+        self.pickle_file_embeddings = open(fe + '.pkl', 'wb') if fe is not None else None
+        self._nviol_dev = None
+
+    def fit(self, xs, ys):
+        fused = self._can_fuse('_fused_pair_step')
+        if self.samplef is None:
+            # supplied-negatives mode (skge/base.py:1350-1357)
+            ysa = np.asarray(ys)
+            pidx = np.where(ysa == 1)[0]
+            nidx = np.where(ysa != 1)[0]
+            pxs = [xs[i] for i in pidx]
+            self.nxs = [xs[i] for i in nidx]
+            self.pxs = int(len(self.nxs) / len(pxs)) * pxs
+            n = min(len(pxs), len(self.nxs))
+            if fused:
+                self._fit_fused_supplied(n)
+            else:
+                self._optim(list(range(n)))
+            return
+        if fused:
+            self._fit_fused_sampled(xs)
+        else:
+            self._optim(list(zip(xs, ys)))
+        self._post_fit(xs)
+
+    # -- fused paths ---------------------------------------------------------------
+    def _setup_fused(self):
+        dev = _ext.device()
+        self._nviol_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._counts = torch.zeros(4, dtype=torch.int32, device=dev)
+
+    def _fit_fused_sampled(self, xs):
+        self._setup_fused()
+        sampler = self._device_sampler()
+        sampler.ensure_device(xs)
+        n = sampler.train_size()
+        state = {'calls': 0}
+
+        def step(batch):
+            pos, neg, valid = sampler.device_sample(batch, batch.numel(), state['calls'])
+            state['calls'] += 1
+            self.model._fused_pair_step(self._updaters, pos, neg, valid, self._counts, self._nviol_dev)
+
+        self._run_epochs(n, step)
+
+    def _fit_fused_supplied(self, n):
+        self._setup_fused()
+        P = torch.stack(_triples_to_device(self.pxs), 1)
+        Nn = torch.stack(_triples_to_device(self.nxs), 1)
+        self._sup = [P, Nn]
+
+        def step(batch):
+            bl = batch.long()
+            pp, nn = self._sup[0][bl], self._sup[1][bl]
+            pos = tuple(pp[:, i].contiguous() for i in range(3))
+            neg = tuple(nn[:, i].contiguous() for i in range(3))
+            self.model._fused_pair_step(self._updaters, pos, neg, None, self._counts, self._nviol_dev)
+
+        self._run_epochs(n, step)
+
+    def _pre_epoch(self):
+        self.nviolations = 0
+        if self._nviol_dev is not None:
+            self._nviol_dev.zero_()
+        if self.samplef is None:
+            if getattr(self, '_sup', None) is not None:
+                # independent shuffles of positives and negatives (skge/base.py:1390-1392)
+                self._sup = [t[self._randperm(t.shape[0])] for t in self._sup]
+            else:
+                rng = np.random.RandomState(self.seed + getattr(self, 'epoch', 0))
+                rng.shuffle(self.pxs)
+                rng.shuffle(self.nxs)
+
+    def _end_epoch(self):
+        if self._nviol_dev is not None:
+            self.nviolations = int(self._nviol_dev.item())
+
+    # -- hook path ---------------------------------------------------------------------
+    def _process_batch(self, xys):
+        pxs, nxs = [], []
+        for xy in xys:
+            if self.samplef is not None:
+                for nx in self.samplef([xy]):
+                    pxs.append(xy)
+                    nxs.append(nx)
+            else:
+                pxs.append((self.pxs[xy], 1))
+                nxs.append((self.nxs[xy], 1))
+        if hasattr(self.model, '_prepare_batch_step'):
+            self.model._prepare_batch_step(pxs, nxs)
+        grads = self.model._pairwise_gradients(pxs, nxs)
+        if grads is not None:
+            self.nviolations += self.model.nviolations
+            self._batch_step(grads)
+
+    # -- end-of-fit instrumentation (skge/base.py:1364-1386) ------------------------------
+    def _post_fit(self, xs):
+        E = self.model.params.get('E')
+        if E is None:
+            return
+        s, o, _ = _triples_to_device(xs)
+        n = E.shape[0]
+        E._neighbours += (torch.bincount(s.long(), minlength=n) + torch.bincount(o.long(), minlength=n)).int()
+        if self.file_gradients is not None:
+            self.file_gradients.write('Entity,Degree,#(violations),#(updates)\n')
+            for i, (en, ev, ec) in enumerate(zip(E.neighbours, E.violations, E.updateCounts)):
+                self.file_gradients.write('%d,%d,%d,%d\n' % (i, en, ev, ec))
+            self.file_gradients.flush()
+        if self.file_embeddings is not None or self.pickle_file_embeddings is not None:
+            emb = np.asarray(E, dtype=np.float64)
+            if self.file_embeddings is not None:
+                for i, e in enumerate(emb):
+                    self.file_embeddings.write('%d,%s\n' % (i, str(e)))
+                self.file_embeddings.flush()
+            if self.pickle_file_embeddings is not None:
+                pickle.dump(list(emb), self.pickle_file_embeddings, protocol=2)
+                self.pickle_file_embeddings.flush()
+
+
+# the evaluator and metric helpers live in skge/base.py in the reference
+from .ranking import (FilteredRankingEval, ranking_scores, compute_scores, _print_pos)  # noqa: E402,F401

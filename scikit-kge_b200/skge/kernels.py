@@ -1,0 +1,193 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point family).
+
+Everything here takes and returns CUDA tensors; nothing computes on the host.
+"""
+import numpy as np
+import torch
+
+from . import _ext
+from ._ext import check, lib, ptr, stream
+
+_ws = _ext.Workspace()
+
+TRANSE, HOLE, RESCAL = _ext.MODEL_TRANSE, _ext.MODEL_HOLE, _ext.MODEL_RESCAL
+
+
+def _i32(n, dev=None):
+    return torch.empty(n, dtype=torch.int32, device=dev or _ext.device())
+
+
+def _f32(*shape):
+    return torch.empty(*shape, dtype=torch.float32, device=_ext.device())
+
+
+def scores(model, E, R, s, p, o, l1=True):
+    """Model._scores: s, p, o are int32 CUDA tensors; returns fp32 [n]."""
+    n, d = s.numel(), E.shape[1]
+    out = _f32(n)
+    if model == TRANSE:
+        check(lib().skge_scores_transe(ptr(E), ptr(R), ptr(s), ptr(p), ptr(o), n, d, int(bool(l1)), ptr(out),
+                                       stream()))
+    elif model == HOLE:
+        check(lib().skge_scores_hole(ptr(E), ptr(R), ptr(s), ptr(p), ptr(o), n, d, ptr(out), stream()))
+    else:
+        check(lib().skge_scores_rescal(ptr(E), ptr(R), ptr(s), ptr(p), ptr(o), n, d, ptr(out), stream()))
+    return out
+
+
+def pair_workspace(P, d, rows, N, M):
+    return _ws.get(lib().skge_pair_workspace_bytes(P, d, rows, N, M))
+
+
+def pair_grads(model, E, R, pos, neg, valid, margin, l1_or_af, rparam=0.0, ent_viol=None):
+    """Un-fused pairwise gradients.  pos/neg are (s, o, p) triples of int32 CUDA
+    tensors.  Returns dict(nviol, ge, eidx, gr, ridx, pscores, nscores)."""
+    (sp, op, pp), (sn, on, pn) = pos, neg
+    P, (N, d), M = sp.numel(), E.shape, R.shape[0]
+    ue, ur = min(4 * P, N), min(2 * P, M)
+    ge, eidx, gr, ridx = _f32(ue, d), _i32(ue), _f32(ur, d), _i32(ur)
+    ps, ns, counts = _f32(P), _f32(P), _i32(4)
+    rows = 2 if model == TRANSE else 6
+    ws = pair_workspace(P, d, rows, N, M)
+    if model == TRANSE:
+        check(lib().skge_transe_pair_grads(ptr(E), ptr(R), ptr(sp), ptr(op), ptr(pp), ptr(sn), ptr(on), ptr(pn),
+                                           ptr(valid), P, N, M, d, int(l1_or_af), float(margin), ptr(ps), ptr(ns),
+                                           ptr(ge), ptr(eidx), ptr(gr), ptr(ridx), ptr(counts), ptr(ent_viol),
+                                           ptr(ws), ws.numel(), stream()))
+    else:
+        check(lib().skge_hole_pair_grads(ptr(E), ptr(R), ptr(sp), ptr(op), ptr(pp), ptr(sn), ptr(on), ptr(pn),
+                                         ptr(valid), P, N, M, d, int(l1_or_af), float(margin), float(rparam),
+                                         ptr(ps), ptr(ns), ptr(ge), ptr(eidx), ptr(gr), ptr(ridx), ptr(counts),
+                                         ptr(ws), ws.numel(), stream()))
+    nviol, U_E, U_R, _ = counts.tolist()
+    return dict(nviol=nviol, ge=ge[:U_E], eidx=eidx[:U_E], gr=gr[:U_R], ridx=ridx[:U_R], pscores=ps, nscores=ns)
+
+
+def pair_step(model, E, R, p2E, p2R, pos, neg, valid, margin, l1_or_af, rparam, opt, lr, postE, postR,
+              counts, nviol_accum, ent_viol=None, ucE=None, ucR=None):
+    """Fused minibatch step (gradient + update), asynchronous on the stream."""
+    (sp, op, pp), (sn, on, pn) = pos, neg
+    P, (N, d), M = sp.numel(), E.shape, R.shape[0]
+    rows = 2 if model == TRANSE else 6
+    ws = pair_workspace(P, d, rows, N, M)
+    if model == TRANSE:
+        check(lib().skge_transe_pair_step(ptr(E), ptr(R), ptr(p2E), ptr(p2R), ptr(sp), ptr(op), ptr(pp), ptr(sn),
+                                          ptr(on), ptr(pn), ptr(valid), P, N, M, d, int(l1_or_af), float(margin),
+                                          opt, float(lr), postE, postR, ptr(counts), ptr(nviol_accum),
+                                          ptr(ent_viol), ptr(ucE), ptr(ucR), ptr(ws), ws.numel(), stream()))
+    else:
+        check(lib().skge_hole_pair_step(ptr(E), ptr(R), ptr(p2E), ptr(p2R), ptr(sp), ptr(op), ptr(pp), ptr(sn),
+                                        ptr(on), ptr(pn), ptr(valid), P, N, M, d, int(l1_or_af), float(margin),
+                                        float(rparam), opt, float(lr), postE, postR, ptr(counts),
+                                        ptr(nviol_accum), ptr(ucE), ptr(ucR), ptr(ws), ws.numel(), stream()))
+
+
+def logistic_grads(model, E, R2, s, o, p, y, rparam):
+    """Un-fused logistic gradients.  R2 is R (HolE) or W (RESCAL).
+    Returns dict(loss, ge, eidx, g2, idx2)."""
+    n, (N, d), M = s.numel(), E.shape, R2.shape[0]
+    ue, u2 = min(2 * n, N), min(n, M)
+    ge, eidx, idx2, counts = _f32(ue, d), _i32(ue), _i32(u2), _i32(4)
+    loss = torch.zeros(1, dtype=torch.float64, device=_ext.device())
+    ws = _ws.get(lib().skge_logistic_workspace_bytes(model, n, d, N, M))
+    if model == HOLE:
+        g2 = _f32(u2, d)
+        check(lib().skge_hole_logistic_grads(ptr(E), ptr(R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d,
+                                             float(rparam), ptr(ge), ptr(eidx), ptr(g2), ptr(idx2), ptr(counts),
+                                             ptr(loss), ptr(ws), ws.numel(), stream()))
+    else:
+        g2 = _f32(u2, d, d)
+        check(lib().skge_rescal_logistic_grads(ptr(E), ptr(R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d,
+                                               float(rparam), ptr(ge), ptr(eidx), ptr(g2), ptr(idx2), ptr(counts),
+                                               ptr(loss), ptr(ws), ws.numel(), stream()))
+    _, U_E, U_2, _ = counts.tolist()
+    return dict(loss=float(loss.item()), ge=ge[:U_E], eidx=eidx[:U_E], g2=g2[:U_2], idx2=idx2[:U_2])
+
+
+def logistic_step(model, E, R2, p2E, p2R2, s, o, p, y, rparam, opt, lr, postE, post2, counts, loss_accum,
+                  ucE=None, uc2=None):
+    n, (N, d), M = s.numel(), E.shape, R2.shape[0]
+    ws = _ws.get(lib().skge_logistic_workspace_bytes(model, n, d, N, M))
+    fn = lib().skge_hole_logistic_step if model == HOLE else lib().skge_rescal_logistic_step
+    check(fn(ptr(E), ptr(R2), ptr(p2E), ptr(p2R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d, float(rparam), opt,
+             float(lr), postE, post2, ptr(counts), ptr(loss_accum), ptr(ucE), ptr(uc2), ptr(ws), ws.numel(),
+             stream()))
+
+
+class TripleSet(object):
+    """Device hash set of training triples + corrupted-triple sampler
+    (RandomModeSampler / LCWASampler of skge/sample.py)."""
+
+    def __init__(self, s, o, p, N, M, lcwa=False):
+        if N >= (1 << 24) - 1 or M > (1 << 16):
+            raise ValueError('device sampler packs keys as 24/24/16 bits: need N < 2^24-1 and M <= 2^16')
+        self.s, self.o, self.p, self.N, self.M = s, o, p, int(N), int(M)
+        T = s.numel()
+        nbytes = lib().skge_tripleset_bytes(T)
+        self.table = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
+        check(lib().skge_tripleset_build(ptr(self.table), nbytes, ptr(s), ptr(o), ptr(p), T, 0, stream()))
+        self.sp_table = None
+        if lcwa:
+            self.sp_table = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
+            check(lib().skge_tripleset_build(ptr(self.sp_table), nbytes, ptr(s), ptr(o), ptr(p), T, 1, stream()))
+
+    def contains(self, s, o, p):
+        out = torch.empty(s.numel(), dtype=torch.uint8, device=_ext.device())
+        check(lib().skge_tripleset_contains(ptr(self.table), self.table.numel(), ptr(s), ptr(o), ptr(p), s.numel(),
+                                            ptr(out), stream()))
+        return out
+
+    def sample(self, batch_idx, B, n_per, modes_mask, ntries, seed, offset, src=None):
+        """Returns (pos, neg, valid): pos/neg are (s, o, p) int32 tensors of
+        B * n_per * nmodes pairs.  ``src`` overrides the (s, o, p) arrays the
+        positives are read from (default: the training arrays)."""
+        s, o, p = src if src is not None else (self.s, self.o, self.p)
+        nm = bin(modes_mask & 7).count('1')
+        n = B * n_per * nm
+        outs = [_i32(n) for _ in range(6)]
+        valid = torch.empty(n, dtype=torch.uint8, device=_ext.device())
+        check(lib().skge_sample_corrupt(ptr(self.table), self.table.numel(), ptr(self.sp_table),
+                                        self.sp_table.numel() if self.sp_table is not None else 0, ptr(s), ptr(o),
+                                        ptr(p), ptr(batch_idx), B, n_per, modes_mask, self.N, self.M, ntries,
+                                        seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), *[ptr(t) for t in outs],
+                                        ptr(valid), stream()))
+        return tuple(outs[:3]), tuple(outs[3:]), valid
+
+
+# ---------------------------------------------------------------------------
+# ranking
+# ---------------------------------------------------------------------------
+
+def rank_op(model):
+    return _ext.RANK_L1 if model == TRANSE else _ext.RANK_DOT
+
+
+def make_queries(model, E, RW, kind, given, rel, target, enorm_max, coarse_rel):
+    Q, d = given.numel(), E.shape[1]
+    dev = _ext.device()
+    q64 = torch.empty(Q, d, dtype=torch.float64, device=dev)
+    q32 = torch.empty(Q, d, dtype=torch.float32, device=dev)
+    tscore = torch.empty(Q, dtype=torch.float64, device=dev)
+    eps, qnorm = _f32(Q), _f32(Q)
+    check(lib().skge_rank_make_queries(model, ptr(E), ptr(RW), ptr(kind), ptr(given), ptr(rel), ptr(target), Q, d,
+                                       float(enorm_max), float(coarse_rel), ptr(q64), ptr(q32), ptr(tscore),
+                                       ptr(eps), ptr(qnorm), stream()))
+    return dict(q64=q64, q32=q32, tscore=tscore, eps=eps, qnorm=qnorm)
+
+
+def rank_sweep(op, Eshard, shard_base, q, cnt_gt, cand_q, cand_e, cand_count):
+    n_shard, d = Eshard.shape
+    check(lib().skge_rank_sweep(op, ptr(Eshard), n_shard, shard_base, d, ptr(q['q32']), ptr(q['tscore']),
+                                ptr(q['eps']), q['q32'].shape[0], ptr(cnt_gt), ptr(cand_q), ptr(cand_e),
+                                cand_q.numel(), ptr(cand_count), stream()))
+
+
+def rank_rescore(op, Efull, q, pair_q, pair_e, npairs, npairs_dev, target, cnt):
+    check(lib().skge_rank_rescore(op, ptr(Efull), Efull.shape[1], ptr(q['q64']), ptr(q['tscore']), ptr(pair_q),
+                                  ptr(pair_e), npairs, ptr(npairs_dev), ptr(target), ptr(cnt), stream()))
+
+
+def rank_scores_one(op, E, q64_row):
+    out = torch.empty(E.shape[0], dtype=torch.float64, device=_ext.device())
+    check(lib().skge_rank_scores_one(op, ptr(E), E.shape[0], E.shape[1], ptr(q64_row), ptr(out), stream()))
+    return out

@@ -1,0 +1,353 @@
+"""Filtered link-prediction ranking on the device.
+
+Reference: FilteredRankingEval (skge/base.py:739-759, 913-1031), the per-model
+scorers TransEEval (skge/run_transe.py:13-29) and HolEEval
+(skge/run_hole.py:10-19), ranking_scores / compute_scores
+(skge/base.py:1050-1103).
+
+The reference scores one query at a time against all N entities and argsorts
+four times per test triple.  Here every query of the test set is one row of a
+query matrix; a coarse sweep over the (sharded) entity table counts, per query,
+the entities that beat the target by more than an error bound and lists the
+undecided ones; those and the filter entries are settled in fp64 from the fp32
+master table.  rank = 1 + #{score > target score}, which equals the reference's
+argsort position whenever the target's score is not tied.
+
+With torch.distributed initialised (one process per GPU) the entity table is
+row-partitioned across ranks, each rank counts over its own shard and one
+all-reduce of 2Q int32 counts combines them; results are identical on every
+rank and for every world size.
+"""
+import logging
+import math
+
+import numpy as np
+import torch
+
+from . import _ext, kernels
+
+log = logging.getLogger('EX-KG')
+
+
+# ---------------------------------------------------------------------------
+# host-side logic shared by all world sizes (pure functions: CPU-testable)
+# ---------------------------------------------------------------------------
+
+def shard_range(N, rank, world):
+    """Row range [lo, hi) of the entity table owned by ``rank``: contiguous
+    blocks of ceil(N / world) rows."""
+    per = (N + world - 1) // world
+    lo = min(N, rank * per)
+    return lo, min(N, lo + per)
+
+
+def flatten_queries(test):
+    """(Te, 3) test triples (s, o, p) -> query arrays of length 2*Te:
+    first the Te tail queries (s, p, ?) -> o, then the Te head queries (?, p, o) -> s.
+    Returns kind (uint8), given, rel, target (int64 numpy)."""
+    t = np.asarray(test, dtype=np.int64).reshape(-1, 3)
+    te = t.shape[0]
+    kind = np.concatenate([np.zeros(te, np.uint8), np.ones(te, np.uint8)])
+    given = np.concatenate([t[:, 0], t[:, 1]])
+    rel = np.concatenate([t[:, 2], t[:, 2]])
+    target = np.concatenate([t[:, 1], t[:, 0]])
+    return kind, given, rel, target
+
+
+def build_filter_pairs(true_triples, kind, given, rel, target, device=None):
+    """All (query, entity) filter entries: for a tail query (s, p, ?) the known
+    objects of (s, p) other than the target, for a head query the known subjects
+    of (p, o) (skge/base.py:744-752, 970-977, 1012-1014).  Duplicates collapse
+    (the reference writes -inf twice).  Returns int32 tensors (pair_q ascending,
+    pair_e) on ``device``; torch ops only, so it runs on CPU or GPU."""
+    dev = device if device is not None else torch.device('cpu')
+    tt = torch.as_tensor(np.asarray(true_triples, dtype=np.int64).reshape(-1, 3), device=dev)
+    kind_t = torch.as_tensor(kind.astype(np.int64), device=dev)
+    given_t = torch.as_tensor(given, device=dev)
+    rel_t = torch.as_tensor(rel, device=dev)
+    target_t = torch.as_tensor(target, device=dev)
+    nmax = int(max(tt[:, :2].max().item() if tt.numel() else 0, given_t.max().item(), target_t.max().item())) + 1
+    out_q, out_e = [], []
+    for k, (gcol, vcol) in enumerate(((0, 1), (1, 0))):   # tail: key (p, s) -> o ; head: key (p, o) -> s
+        qsel = torch.nonzero(kind_t == k).flatten()
+        if qsel.numel() == 0 or tt.numel() == 0:
+            continue
+        keys = tt[:, 2] * nmax + tt[:, gcol]
+        packed = torch.unique(keys * nmax + tt[:, vcol])     # sorted, duplicates collapsed
+        ukeys, uvals = packed // nmax, packed % nmax
+        qkey = rel_t[qsel] * nmax + given_t[qsel]
+        lo = torch.searchsorted(ukeys, qkey, right=False)
+        hi = torch.searchsorted(ukeys, qkey, right=True)
+        lens = hi - lo
+        total = int(lens.sum().item())
+        if total == 0:
+            continue
+        owner = torch.repeat_interleave(torch.arange(qsel.numel(), device=dev), lens)
+        start = torch.cumsum(lens, 0) - lens
+        pos = lo[owner] + (torch.arange(total, device=dev) - start[owner])
+        e = uvals[pos]
+        q = qsel[owner]
+        keep = e != target_t[q]
+        out_q.append(q[keep])
+        out_e.append(e[keep])
+    if not out_q:
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return z, z.clone()
+    q = torch.cat(out_q)
+    e = torch.cat(out_e)
+    order = torch.argsort(q, stable=True)
+    return q[order].to(torch.int32), e[order].to(torch.int32)
+
+
+def allreduce_counts(cnt):
+    """Sum the per-shard counts over ranks (no-op without a process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    return cnt
+
+
+def ranks_from_counts(cnt):
+    """cnt: int32 [2, Q] = (#entities beating the target, #filter entities
+    beating the target) -> (raw ranks, filtered ranks)."""
+    raw = 1 + cnt[0]
+    return raw, raw - cnt[1]
+
+
+def regroup(test, raw, filt):
+    """Flat rank arrays (tail queries then head queries) -> the reference's
+    ``pos`` / ``fpos`` dicts ``{p: {'head': [...], 'tail': [...]}}`` with
+    relations and triples in insertion order (skge/base.py:743, 921, 1027-1028)."""
+    t = np.asarray(test, dtype=np.int64).reshape(-1, 3)
+    te = t.shape[0]
+    raw, filt = np.asarray(raw), np.asarray(filt)
+    pos, fpos = {}, {}
+    rels, first = np.unique(t[:, 2], return_index=True)
+    for p in rels[np.argsort(first)]:
+        sel = np.nonzero(t[:, 2] == p)[0]
+        pos[int(p)] = {'head': [int(x) for x in raw[te + sel]], 'tail': [int(x) for x in raw[sel]]}
+        fpos[int(p)] = {'head': [int(x) for x in filt[te + sel]], 'tail': [int(x) for x in filt[sel]]}
+    return pos, fpos
+
+
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ---------------------------------------------------------------------------
+# evaluators
+# ---------------------------------------------------------------------------
+
+class FilteredRankingEval(object):
+    """FilteredRankingEval(xs, true_triples, neval=-1).positions(mdl) -> (pos, fpos).
+
+    Subclasses name the model family (``model_code``); the reference's
+    per-query hooks ``prepare`` / ``scores_o`` / ``scores_s`` are still offered
+    (computed on the device in fp64) for callers that want raw score vectors.
+    """
+
+    model_code = None
+    chunk_queries = 32768       # queries per device pass (bounds q64/q32 scratch)
+    use_tensor_cores = True     # DOT models: tcgen05 coarse pass when the shapes allow
+
+    def __init__(self, xs, true_triples, neval=-1):
+        self.test = np.asarray(xs, dtype=np.int64).reshape(-1, 3)
+        self._true = true_triples
+        self.sz = len(self.test)
+        self.neval = neval
+        self.kind, self.given, self.rel, self.target = flatten_queries(self.test)
+        self._dev = None
+        self.last_stats = {}
+
+    # the reference's python indices, built on demand (small graphs only)
+    @property
+    def idx(self):
+        d = {}
+        for s, o, p in self.test.tolist():
+            d.setdefault(p, []).append((s, o))
+        return d
+
+    @property
+    def tt(self):
+        d = {}
+        for s, o, p in np.asarray(self._true, dtype=np.int64).reshape(-1, 3).tolist():
+            e = d.setdefault(p, {'ss': {}, 'os': {}})
+            e['os'].setdefault(s, []).append(o)
+            e['ss'].setdefault(o, []).append(s)
+        return d
+
+    # -- device state, built once ------------------------------------------------
+    def _device_state(self):
+        if self._dev is None:
+            dev = _ext.device()
+            pq, pe = build_filter_pairs(self._true, self.kind, self.given, self.rel, self.target, device=dev)
+            self._dev = dict(
+                kind=torch.from_numpy(self.kind).to(dev),
+                given=torch.from_numpy(self.given.astype(np.int32)).to(dev),
+                rel=torch.from_numpy(self.rel.astype(np.int32)).to(dev),
+                target=torch.from_numpy(self.target.astype(np.int32)).to(dev),
+                pair_q=pq.contiguous(), pair_e=pe.contiguous())
+        return self._dev
+
+    def _second(self, mdl):
+        return mdl.W.data if self.model_code == _ext.MODEL_RESCAL else mdl.R.data
+
+    # -- the ranking pass ------------------------------------------------------------
+    def positions(self, mdl, plot=False, pagerankMap=None):
+        if self.model_code is None:
+            raise NotImplementedError('derive from TransEEval / HolEEval / RESCALEval: the device ranking '
+                                      'pass needs to know the model family (there is no host fallback)')
+        cnt = self.count_pass(mdl)
+        raw, filt = ranks_from_counts(cnt)
+        return regroup(self.test, raw.cpu().numpy(), filt.cpu().numpy())
+
+    def count_pass(self, mdl, E=None, world=None):
+        """int32 [2, Q] counts, already summed over ranks.  ``world`` = (rank,
+        world_size) overrides the process group and skips the reduction (used to
+        emulate several shards on one GPU)."""
+        st = self._device_state()
+        dev = _ext.device()
+        E = mdl.E.data if E is None else E
+        RW = self._second(mdl)
+        N, d = E.shape
+        Q = st['given'].numel()
+        emulated = world is not None
+        rank, world = world if emulated else _world()
+        lo, hi = shard_range(N, rank, world)
+        op = kernels.rank_op(self.model_code)
+        cnt = torch.zeros(2, Q, dtype=torch.int32, device=dev)
+        enorm = float(torch.linalg.vector_norm(E, dim=1).max().item()) if op == _ext.RANK_DOT else 1.0
+        # filter entries are settled by the rank that owns the entity
+        pq, pe = st['pair_q'], st['pair_e']
+        if world > 1:
+            own = (pe >= lo) & (pe < hi)
+            pq, pe = pq[own].contiguous(), pe[own].contiguous()
+        engine = self._coarse_engine(E, lo, hi, enorm)
+        pair_bounds = torch.searchsorted(pq.to(torch.int64),
+                                         torch.arange(0, Q + self.chunk_queries, self.chunk_queries, device=dev)
+                                         ).tolist()
+        ncand = 0
+        for ci, q0 in enumerate(range(0, Q, self.chunk_queries)):
+            q1 = min(Q, q0 + self.chunk_queries)
+            sl = slice(q0, q1)
+            q = kernels.make_queries(self.model_code, E, RW, st['kind'][sl], st['given'][sl], st['rel'][sl],
+                                     st['target'][sl], enorm, engine.coarse_rel(d))
+            ncand += engine.run(op, q, cnt[0, sl])
+            a, b = pair_bounds[ci], pair_bounds[ci + 1]
+            if b > a:
+                kernels.rank_rescore(op, E, q, (pq[a:b] - q0).contiguous(), pe[a:b], b - a, None, None,
+                                     cnt[1, sl])
+        self.last_stats = dict(candidates=ncand, filter_pairs=int(pq.numel()), shard=(lo, hi), world=world,
+                               engine=engine.name)
+        return cnt if emulated else allreduce_counts(cnt)
+
+    def _coarse_engine(self, E, lo, hi, enorm):
+        return _SweepEngine(E, lo, hi)
+
+    # -- reference-style hooks (fp64 score vectors from the device) ---------------------
+    def prepare(self, mdl, p):
+        self._hook_p = p
+
+    def _scores_one(self, mdl, given, p, kind):
+        dev = _ext.device()
+        one = lambda v, dt: torch.tensor([v], dtype=dt, device=dev)  # noqa: E731
+        q = kernels.make_queries(self.model_code, mdl.E.data, self._second(mdl), one(kind, torch.uint8),
+                                 one(given, torch.int32), one(p, torch.int32), one(0, torch.int32), 1.0, 0.0)
+        return kernels.rank_scores_one(kernels.rank_op(self.model_code), mdl.E.data, q['q64'][0]).cpu().numpy()
+
+    def scores_o(self, mdl, s, p):
+        return self._scores_one(mdl, s, p, 0)
+
+    def scores_s(self, mdl, o, p):
+        return self._scores_one(mdl, o, p, 1)
+
+
+class _SweepEngine(object):
+    """fp32 coarse sweep on the CUDA cores (any model, any d) + fp64 settlement."""
+    name = 'fp32-sweep'
+
+    def __init__(self, E, lo, hi):
+        self.E = E
+        self.lo, self.hi = lo, hi
+        self.shard = E[lo:hi]
+        self.cap = 1 << 22
+        dev = E.device
+        self.cand_q = torch.empty(self.cap, dtype=torch.int32, device=dev)
+        self.cand_e = torch.empty(self.cap, dtype=torch.int32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def coarse_rel(self, d):
+        return 2.0 * (d + 2) * 2.0 ** -24
+
+    def _coarse(self, op, q, cnt_gt):
+        kernels.rank_sweep(op, self.shard, self.lo, q, cnt_gt, self.cand_q, self.cand_e, self.count)
+
+    def run(self, op, q, cnt_gt):
+        """Adds this shard's counts for the query chunk into cnt_gt; returns the
+        number of band candidates that had to be settled in fp64."""
+        if self.hi <= self.lo:
+            return 0
+        base = cnt_gt.clone()
+        while True:
+            self.count.zero_()
+            self._coarse(op, q, cnt_gt)
+            n = int(self.count.item())
+            if n <= self.cap:
+                break
+            # candidate list overflowed: grow it and redo the chunk from the saved counts
+            cnt_gt.copy_(base)
+            self.cap = 1 << int(math.ceil(math.log2(n + 1)))
+            self.cand_q = torch.empty(self.cap, dtype=torch.int32, device=self.E.device)
+            self.cand_e = torch.empty(self.cap, dtype=torch.int32, device=self.E.device)
+        if n:
+            kernels.rank_rescore(op, self.E, q, self.cand_q, self.cand_e, n, None, None, cnt_gt)
+        return n
+
+
+class TransEEval(FilteredRankingEval):
+    """skge/run_transe.py:13-29 -- evaluation is L1 whatever ``mdl.l1`` says."""
+    model_code = _ext.MODEL_TRANSE
+
+
+class HolEEval(FilteredRankingEval):
+    """skge/run_hole.py:10-19."""
+    model_code = _ext.MODEL_HOLE
+
+
+class RESCALEval(FilteredRankingEval):
+    """No evaluator exists in the reference; scores follow skge/rescal.py:31-35."""
+    model_code = _ext.MODEL_RESCAL
+
+
+# ---------------------------------------------------------------------------
+# metrics (skge/base.py:1050-1103)
+# ---------------------------------------------------------------------------
+
+def compute_scores(pos, hits=10):
+    pos = np.asarray(pos)
+    mrr = np.mean(1.0 / pos)
+    mean_pos = np.mean(pos)
+    ans_hits = np.mean(pos <= hits).sum() * 100
+    return mrr, mean_pos, ans_hits
+
+
+def _print_pos(fresult, pos, fpos, epoch, txt):
+    mrr, mean_pos, hits = compute_scores(pos)
+    fmrr, fmean_pos, fhits = compute_scores(fpos)
+    line = "[%3d] %s: MRR = %.2f/%.2f, Mean Rank = %.2f/%.2f, Hits@10 = %.2f/%.2f" % (
+        epoch, txt, mrr, fmrr, mean_pos, fmean_pos, hits, fhits)
+    log.info(line)
+    if fresult is not None:
+        fresult.write(line + "\n")
+    return fmrr
+
+
+def ranking_scores(fresult, pos, fpos, epoch, txt):
+    hpos = [p for k in pos.keys() for p in pos[k]['head']]
+    tpos = [p for k in pos.keys() for p in pos[k]['tail']]
+    fhpos = [p for k in fpos.keys() for p in fpos[k]['head']]
+    ftpos = [p for k in fpos.keys() for p in fpos[k]['tail']]
+    return _print_pos(fresult, np.array(hpos + tpos), np.array(fhpos + ftpos), epoch, txt)

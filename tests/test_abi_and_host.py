@@ -1,0 +1,199 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol that
+include/skge_b200.h declares, the ctypes prototypes agree with the header, and
+the host-side ranking logic (query flattening, filter lists, sharding, count
+combination, regrouping) matches the oracle -- including a world_size-2 gloo run.
+No compute call is made (there is no GPU here)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'skge_b200.h')
+
+CTYPE = {'int': 'c_int', 'int64_t': 'c_long', 'float': 'c_float', 'size_t': 'c_ulong', 'uint64_t': 'c_ulong'}
+
+
+def header_prototypes():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'SKGE_API\s+([\w\s\*]+?)\s*\b(skge_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        kinds = []
+        if args and args != 'void':
+            for a in args.split(','):
+                a = ' '.join(a.split())
+                if '*' in a or a.startswith('skge_stream_t'):
+                    kinds.append('ptr')
+                else:
+                    kinds.append(CTYPE[a.replace('const ', '').split(' ')[0]])
+        protos[name] = (ret, kinds)
+    return protos
+
+
+def test_library_exports_every_declared_symbol():
+    from skge import _ext
+    lib = _ext.load_library()
+    protos = header_prototypes()
+    assert len(protos) >= 29
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert set(protos) == set(_ext.SIGNATURES), set(protos) ^ set(_ext.SIGNATURES)
+    assert lib.skge_version() == 100
+
+
+def test_ctypes_prototypes_match_header():
+    import ctypes as C
+    from skge import _ext
+    protos = header_prototypes()
+    for name, (ret, kinds) in protos.items():
+        res, args = _ext.SIGNATURES[name]
+        assert len(args) == len(kinds), name
+        for i, (a, k) in enumerate(zip(args, kinds)):
+            if k == 'ptr':
+                assert a is C.c_void_p, (name, i)
+            else:
+                assert a.__name__ == k, (name, i, a.__name__, k)
+
+
+def test_compute_without_gpu_fails_loudly():
+    from skge import _ext
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        _ext.lib()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'scikit-kge_b200', 'skge')
+    for f in os.listdir(pkg):
+        if f.endswith('.py'):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+
+
+def _toy(seed=0, N=40, M=3, ntrue=160, ntest=24):
+    rng = np.random.default_rng(seed)
+    true = np.unique(np.stack([rng.integers(N, size=ntrue), rng.integers(N, size=ntrue),
+                               rng.integers(M, size=ntrue)], 1), axis=0)
+    test = true[rng.choice(len(true), ntest, replace=False)]
+    return N, M, true, test
+
+
+def _oracle_counts(kind_name, E, R, test, true, lo, hi):
+    """Per-shard counts computed with the oracle's scorers (numpy)."""
+    from skge.ranking import flatten_queries
+    kind, given, rel, target = flatten_queries(test)
+    prepare, scores_o, scores_s = orc._eval_hooks(kind_name, E, R)
+    idx, tt = orc.build_filter_index(test, true)
+    cnt = np.zeros((2, len(kind)), dtype=np.int32)
+    for j in range(len(kind)):
+        prepare(int(rel[j]))
+        sc = (scores_o if kind[j] == 0 else scores_s)(int(given[j]), int(rel[j])).flatten()
+        t = sc[target[j]]
+        cnt[0, j] = np.sum(sc[lo:hi] > t)
+        known = tt[int(rel[j])]['os' if kind[j] == 0 else 'ss'][int(given[j])]
+        known = {e for e in known if e != target[j] and lo <= e < hi}
+        cnt[1, j] = sum(1 for e in known if sc[e] > t)
+    return cnt
+
+
+def test_filter_pairs_match_oracle_index():
+    from skge.ranking import flatten_queries, build_filter_pairs
+    N, M, true, test = _toy()
+    kind, given, rel, target = flatten_queries(test)
+    pq, pe = build_filter_pairs(true, kind, given, rel, target)
+    got = {}
+    for q, e in zip(pq.tolist(), pe.tolist()):
+        got.setdefault(q, set()).add(e)
+    idx, tt = orc.build_filter_index(test, true)
+    for j in range(len(kind)):
+        known = tt[int(rel[j])]['os' if kind[j] == 0 else 'ss'][int(given[j])]
+        want = {e for e in known if e != target[j]}
+        assert got.get(j, set()) == want
+    assert (np.diff(pq.numpy()) >= 0).all()
+
+
+@pytest.mark.parametrize('kind_name', ['transe', 'hole'])
+@pytest.mark.parametrize('world', [1, 2, 3, 8])
+def test_sharded_counts_recombine_to_reference_ranks(kind_name, world):
+    from skge.ranking import shard_range, ranks_from_counts, regroup
+    N, M, true, test = _toy(seed=3)
+    rng = np.random.default_rng(1)
+    E, R = rng.normal(size=(N, 8)), rng.normal(size=(M, 8))
+    total = np.zeros((2, 2 * len(test)), dtype=np.int32)
+    covered = 0
+    for r in range(world):
+        lo, hi = shard_range(N, r, world)
+        covered += hi - lo
+        total += _oracle_counts(kind_name, E, R, test, true, lo, hi)
+    assert covered == N
+    raw, filt = ranks_from_counts(torch.from_numpy(total))
+    pos, fpos = regroup(test, raw.numpy(), filt.numpy())
+    rpos, rfpos = orc.rank_positions(kind_name, E, R, test, true, tie='argsort')
+    assert pos == rpos and fpos == rfpos
+    assert list(pos.keys()) == list(rpos.keys())
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path[:0] = [%(root)r, os.path.join(%(root)r, 'scikit-kge_b200'), os.path.join(%(root)r, 'tests')]
+import numpy as np, torch, torch.distributed as dist
+from test_abi_and_host import _toy, _oracle_counts
+from skge.ranking import shard_range, allreduce_counts, ranks_from_counts, regroup
+from oracle import cpu_oracle as orc
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%(port)d', rank=int(sys.argv[1]), world_size=2)
+N, M, true, test = _toy(seed=5)
+rng = np.random.default_rng(2)
+E, R = rng.normal(size=(N, 8)), rng.normal(size=(M, 8))
+lo, hi = shard_range(N, dist.get_rank(), 2)
+cnt = torch.from_numpy(_oracle_counts('hole', E, R, test, true, lo, hi))
+cnt = allreduce_counts(cnt)
+raw, filt = ranks_from_counts(cnt)
+pos, fpos = regroup(test, raw.numpy(), filt.numpy())
+rpos, rfpos = orc.rank_positions('hole', E, R, test, true, tie='argsort')
+assert pos == rpos and fpos == rfpos, 'rank %%d mismatch' %% dist.get_rank()
+dist.barrier()
+dist.destroy_process_group()
+print('ok')
+'''
+
+
+def test_two_rank_gloo_count_reduction(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_WORKER % dict(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and 'ok' in o, o
+
+
+def test_trainer_batch_bounds_and_api_surface():
+    import skge
+    from skge.base import StochasticTrainer
+    assert set(['HolE', 'RESCAL', 'TransE', 'StochasticTrainer', 'PairwiseStochasticTrainer',
+                'activation_functions']) <= set(dir(skge))
+    assert set(skge.activation_functions) == {'linear', 'sigmoid', 'tanh', 'relu', 'softplus'}
+    t = StochasticTrainer.__new__(StochasticTrainer)
+    t.nbatches = 100
+    b = t._batch_bounds(141442)        # WN18: 100 x 1414 + remainder 42 (skge/base.py:1264)
+    assert len(b) == 101 and b[0] == (0, 1414) and b[-1] == (141400, 141442) and t.batch_size == 1414
+    assert len(t._batch_bounds(1000)) == 100
+    from skge.param import SGD, AdaGrad, normalize, normless1  # noqa: F401  (README.md:95)
+    from skge.util import ccorr, cconv, grad_sum_matrix, unzip_triples
+    ss, ps, os_ = unzip_triples([((1, 2, 3), 1.0), ((4, 5, 6), -1.0)])
+    assert ss.tolist() == [1, 4] and ps.tolist() == [3, 6] and os_.tolist() == [2, 5]
+    u, Sm, n = grad_sum_matrix([1, 2, 6, 4, 2, 3, 2])
+    assert u.tolist() == [1, 2, 3, 4, 6] and n.flatten().tolist() == [1, 3, 1, 1, 1]
+    a = np.arange(6.0).reshape(2, 3)
+    np.testing.assert_allclose(ccorr(a, a[::-1]), orc.ccorr_direct(a, a[::-1]))
+    np.testing.assert_allclose(cconv(a, a[::-1]), orc.cconv_direct(a, a[::-1]))
