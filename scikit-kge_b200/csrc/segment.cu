@@ -449,9 +449,9 @@ extern "C" {
 int skge_sparse_update(float *param, float *p2, const float *g, const int32_t *idx, int64_t U,
                        int64_t rowlen, int opt, float lr, int post, int32_t *upd_counts,
                        skge_stream_t stream) {
-  SKGE_REQUIRE(param && g && rowlen > 0 && U >= 0, "bad arguments");
-  SKGE_REQUIRE(opt == SKGE_OPT_SGD || (opt == SKGE_OPT_ADAGRAD && p2), "AdaGrad needs p2");
   if (U == 0) return 0;
+  SKGE_REQUIRE(param && g && rowlen > 0 && U > 0, "bad arguments");
+  SKGE_REQUIRE(opt == SKGE_OPT_SGD || (opt == SKGE_OPT_ADAGRAD && p2), "AdaGrad needs p2");
   return sparse_update_impl(param, p2, g, idx, U, rowlen, opt, lr, post, upd_counts, as_stream(stream));
 }
 

@@ -321,6 +321,8 @@ class ParameterUpdate(object):
         else:
             it = _as_tensor(idx, torch.int32)
             U = it.numel()
+        if U == 0:
+            return
         st = self._state()
         counts = p._update_counts if self.opt_code == _ext.OPT_ADAGRAD else None
         _ext.check(_ext.lib().skge_sparse_update(_ext.ptr(p.data), _ext.ptr(st), _ext.ptr(gt), _ext.ptr(it),

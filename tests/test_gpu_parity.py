@@ -254,7 +254,15 @@ def test_wn18_shaped_minibatch_against_oracle(kind, d, margin, l1):
     post = 'normalize' if kind == 'transe' else 'normless1'
     orc.adagrad_update(E, np.zeros_like(E), ograds['E'][0], ograds['E'][1], 0.1, post)
     orc.adagrad_update(R, np.zeros_like(R), ograds['R'][0], ograds['R'][1], 0.1, None)
-    np.testing.assert_allclose(np.asarray(m.E), E, **PARAM_TOL)
+    # AdaGrad's first step is x -= lr * g / max(|g|, 1e-7) (skge/param.py:147-155): for |g| below
+    # ~1e-6 the step is a discontinuous function of g (sign flip / clamp region), so fp32 and
+    # float64 legitimately disagree there.  Such components are excluded -- and must be rare.
+    # The row post-hook spreads such a component's difference over its whole row, so the rows
+    # that contain one are excluded.
+    gotE, ok = np.asarray(m.E, dtype=np.float64), np.ones(E.shape[0], dtype=bool)
+    ok[ograds['E'][1]] = ((np.abs(ograds['E'][0]) > 1e-6) | (ograds['E'][0] == 0)).all(axis=1)
+    assert (~ok).mean() < 2e-3
+    np.testing.assert_allclose(gotE[ok], E[ok], **PARAM_TOL)
     np.testing.assert_allclose(np.asarray(m.R), R, **PARAM_TOL)
 
 
