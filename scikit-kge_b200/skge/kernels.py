@@ -10,6 +10,16 @@ from ._ext import check, lib, ptr, stream
 
 _ws = _ext.Workspace()
 
+# Number of libskge_b200 kernels launched so far (CUB sort/scan passes and memsets
+# are not counted): bench.py reports the delta over its timed region.
+LAUNCHES = {'n': 0}
+_OWN_KERNELS = {'scores': 1, 'pair': 5, 'logistic_hole': 5, 'logistic_rescal': 11, 'sample': 1, 'set': 1,
+                'make_queries': 1, 'sweep': 1, 'rescore': 1, 'scores_one': 1, 'pack': 1, 'gemm': 1}
+
+
+def _count(what, times=1):
+    LAUNCHES['n'] += _OWN_KERNELS[what] * times
+
 TRANSE, HOLE, RESCAL = _ext.MODEL_TRANSE, _ext.MODEL_HOLE, _ext.MODEL_RESCAL
 
 
@@ -25,6 +35,7 @@ def scores(model, E, R, s, p, o, l1=True):
     """Model._scores: s, p, o are int32 CUDA tensors; returns fp32 [n]."""
     n, d = s.numel(), E.shape[1]
     out = _f32(n)
+    _count('scores')
     if model == TRANSE:
         check(lib().skge_scores_transe(ptr(E), ptr(R), ptr(s), ptr(p), ptr(o), n, d, int(bool(l1)), ptr(out),
                                        stream()))
@@ -49,6 +60,7 @@ def pair_grads(model, E, R, pos, neg, valid, margin, l1_or_af, rparam=0.0, ent_v
     ps, ns, counts = _f32(P), _f32(P), _i32(4)
     rows = 2 if model == TRANSE else 6
     ws = pair_workspace(P, d, rows, N, M)
+    _count('pair')
     if model == TRANSE:
         check(lib().skge_transe_pair_grads(ptr(E), ptr(R), ptr(sp), ptr(op), ptr(pp), ptr(sn), ptr(on), ptr(pn),
                                            ptr(valid), P, N, M, d, int(l1_or_af), float(margin), ptr(ps), ptr(ns),
@@ -70,6 +82,7 @@ def pair_step(model, E, R, p2E, p2R, pos, neg, valid, margin, l1_or_af, rparam, 
     P, (N, d), M = sp.numel(), E.shape, R.shape[0]
     rows = 2 if model == TRANSE else 6
     ws = pair_workspace(P, d, rows, N, M)
+    _count('pair')
     if model == TRANSE:
         check(lib().skge_transe_pair_step(ptr(E), ptr(R), ptr(p2E), ptr(p2R), ptr(sp), ptr(op), ptr(pp), ptr(sn),
                                           ptr(on), ptr(pn), ptr(valid), P, N, M, d, int(l1_or_af), float(margin),
@@ -90,6 +103,7 @@ def logistic_grads(model, E, R2, s, o, p, y, rparam):
     ge, eidx, idx2, counts = _f32(ue, d), _i32(ue), _i32(u2), _i32(4)
     loss = torch.zeros(1, dtype=torch.float64, device=_ext.device())
     ws = _ws.get(lib().skge_logistic_workspace_bytes(model, n, d, N, M))
+    _count('logistic_hole' if model == HOLE else 'logistic_rescal')
     if model == HOLE:
         g2 = _f32(u2, d)
         check(lib().skge_hole_logistic_grads(ptr(E), ptr(R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d,
@@ -109,6 +123,7 @@ def logistic_step(model, E, R2, p2E, p2R2, s, o, p, y, rparam, opt, lr, postE, p
     n, (N, d), M = s.numel(), E.shape, R2.shape[0]
     ws = _ws.get(lib().skge_logistic_workspace_bytes(model, n, d, N, M))
     fn = lib().skge_hole_logistic_step if model == HOLE else lib().skge_rescal_logistic_step
+    _count('logistic_hole' if model == HOLE else 'logistic_rescal')
     check(fn(ptr(E), ptr(R2), ptr(p2E), ptr(p2R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d, float(rparam), opt,
              float(lr), postE, post2, ptr(counts), ptr(loss_accum), ptr(ucE), ptr(uc2), ptr(ws), ws.numel(),
              stream()))
@@ -146,6 +161,7 @@ class TripleSet(object):
         n = B * n_per * nm
         outs = [_i32(n) for _ in range(6)]
         valid = torch.empty(n, dtype=torch.uint8, device=_ext.device())
+        _count('sample')
         check(lib().skge_sample_corrupt(ptr(self.table), self.table.numel(), ptr(self.sp_table),
                                         self.sp_table.numel() if self.sp_table is not None else 0, ptr(s), ptr(o),
                                         ptr(p), ptr(batch_idx), B, n_per, modes_mask, self.N, self.M, ntries,
@@ -169,6 +185,7 @@ def make_queries(model, E, RW, kind, given, rel, target, enorm_max, coarse_rel):
     q32 = torch.empty(Q, d, dtype=torch.float32, device=dev)
     tscore = torch.empty(Q, dtype=torch.float64, device=dev)
     eps, qnorm = _f32(Q), _f32(Q)
+    _count('make_queries')
     check(lib().skge_rank_make_queries(model, ptr(E), ptr(RW), ptr(kind), ptr(given), ptr(rel), ptr(target), Q, d,
                                        float(enorm_max), float(coarse_rel), ptr(q64), ptr(q32), ptr(tscore),
                                        ptr(eps), ptr(qnorm), stream()))
@@ -177,12 +194,14 @@ def make_queries(model, E, RW, kind, given, rel, target, enorm_max, coarse_rel):
 
 def rank_sweep(op, Eshard, shard_base, q, cnt_gt, cand_q, cand_e, cand_count):
     n_shard, d = Eshard.shape
+    _count('sweep')
     check(lib().skge_rank_sweep(op, ptr(Eshard), n_shard, shard_base, d, ptr(q['q32']), ptr(q['tscore']),
                                 ptr(q['eps']), q['q32'].shape[0], ptr(cnt_gt), ptr(cand_q), ptr(cand_e),
                                 cand_q.numel(), ptr(cand_count), stream()))
 
 
 def rank_rescore(op, Efull, q, pair_q, pair_e, npairs, npairs_dev, target, cnt):
+    _count('rescore')
     check(lib().skge_rank_rescore(op, ptr(Efull), Efull.shape[1], ptr(q['q64']), ptr(q['tscore']), ptr(pair_q),
                                   ptr(pair_e), npairs, ptr(npairs_dev), ptr(target), ptr(cnt), stream()))
 

@@ -61,7 +61,10 @@ def build_filter_pairs(true_triples, kind, given, rel, target, device=None):
     (the reference writes -inf twice).  Returns int32 tensors (pair_q ascending,
     pair_e) on ``device``; torch ops only, so it runs on CPU or GPU."""
     dev = device if device is not None else torch.device('cpu')
-    tt = torch.as_tensor(np.asarray(true_triples, dtype=np.int64).reshape(-1, 3), device=dev)
+    if isinstance(true_triples, torch.Tensor):
+        tt = true_triples.to(device=dev, dtype=torch.int64).reshape(-1, 3)
+    else:
+        tt = torch.as_tensor(np.asarray(true_triples, dtype=np.int64).reshape(-1, 3), device=dev)
     kind_t = torch.as_tensor(kind.astype(np.int64), device=dev)
     given_t = torch.as_tensor(given, device=dev)
     rel_t = torch.as_tensor(rel, device=dev)
@@ -122,11 +125,17 @@ def regroup(test, raw, filt):
     te = t.shape[0]
     raw, filt = np.asarray(raw), np.asarray(filt)
     pos, fpos = {}, {}
-    rels, first = np.unique(t[:, 2], return_index=True)
-    for p in rels[np.argsort(first)]:
-        sel = np.nonzero(t[:, 2] == p)[0]
-        pos[int(p)] = {'head': [int(x) for x in raw[te + sel]], 'tail': [int(x) for x in raw[sel]]}
-        fpos[int(p)] = {'head': [int(x) for x in filt[te + sel]], 'tail': [int(x) for x in filt[sel]]}
+    if te == 0:
+        return pos, fpos
+    order = np.argsort(t[:, 2], kind='stable')          # triples of one relation stay in test order
+    ps = t[order, 2]
+    cuts = np.nonzero(np.diff(ps))[0] + 1
+    groups = np.split(order, cuts)
+    groups.sort(key=lambda g: g[0])                     # relations in order of first appearance
+    for sel in groups:
+        p = int(t[sel[0], 2])
+        pos[p] = {'head': raw[te + sel].tolist(), 'tail': raw[sel].tolist()}
+        fpos[p] = {'head': filt[te + sel].tolist(), 'tail': filt[sel].tolist()}
     return pos, fpos
 
 
@@ -154,6 +163,8 @@ class FilteredRankingEval(object):
     use_tensor_cores = True     # DOT models: tcgen05 coarse pass when the shapes allow
 
     def __init__(self, xs, true_triples, neval=-1):
+        if isinstance(xs, torch.Tensor):
+            xs = xs.cpu().numpy()
         self.test = np.asarray(xs, dtype=np.int64).reshape(-1, 3)
         self._true = true_triples
         self.sz = len(self.test)
@@ -181,16 +192,23 @@ class FilteredRankingEval(object):
 
     # -- device state, built once ------------------------------------------------
     def _device_state(self):
+        """The filter index (built once, on the device) plus this call's upload
+        of the query descriptors from pinned host memory."""
+        dev = _ext.device()
         if self._dev is None:
-            dev = _ext.device()
             pq, pe = build_filter_pairs(self._true, self.kind, self.given, self.rel, self.target, device=dev)
-            self._dev = dict(
-                kind=torch.from_numpy(self.kind).to(dev),
-                given=torch.from_numpy(self.given.astype(np.int32)).to(dev),
-                rel=torch.from_numpy(self.rel.astype(np.int32)).to(dev),
-                target=torch.from_numpy(self.target.astype(np.int32)).to(dev),
-                pair_q=pq.contiguous(), pair_e=pe.contiguous())
+            host = dict(kind=torch.from_numpy(self.kind),
+                        given=torch.from_numpy(self.given.astype(np.int32)),
+                        rel=torch.from_numpy(self.rel.astype(np.int32)),
+                        target=torch.from_numpy(self.target.astype(np.int32)))
+            self._host = {k: v.pin_memory() for k, v in host.items()}
+            self._dev = dict(pair_q=pq.contiguous(), pair_e=pe.contiguous())
+        for k, v in self._host.items():
+            self._dev[k] = v.to(dev, non_blocking=True)
         return self._dev
+
+    def h2d_bytes(self):
+        return int(sum(v.numel() * v.element_size() for v in self._host.values())) if self._dev else 0
 
     def _second(self, mdl):
         return mdl.W.data if self.model_code == _ext.MODEL_RESCAL else mdl.R.data
@@ -265,6 +283,9 @@ class FilteredRankingEval(object):
         return self._scores_one(mdl, o, p, 1)
 
 
+TIMINGS = []   # (start event, end event, algorithmic flops/ops) per coarse launch when timing is on
+
+
 class _SweepEngine(object):
     """fp32 coarse sweep on the CUDA cores (any model, any d) + fp64 settlement."""
     name = 'fp32-sweep'
@@ -282,8 +303,22 @@ class _SweepEngine(object):
     def coarse_rel(self, d):
         return 2.0 * (d + 2) * 2.0 ** -24
 
+    # CUDA-event timing of the coarse kernel alone (bench.py's roofline leg)
+    timing = False
+
+    def _timed(self, fn, work):
+        if not self.timing:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        TIMINGS.append((a, b, work))
+
     def _coarse(self, op, q, cnt_gt):
-        kernels.rank_sweep(op, self.shard, self.lo, q, cnt_gt, self.cand_q, self.cand_e, self.count)
+        work = 2.0 * (self.hi - self.lo) * self.E.shape[1] * q['q32'].shape[0]
+        self._timed(lambda: kernels.rank_sweep(op, self.shard, self.lo, q, cnt_gt, self.cand_q, self.cand_e,
+                                               self.count), work)
 
     def run(self, op, q, cnt_gt):
         """Adds this shard's counts for the query chunk into cnt_gt; returns the
