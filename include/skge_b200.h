@@ -242,6 +242,11 @@ SKGE_API int skge_rank_scores_one(int op, const float *E, int64_t N, int d, cons
 SKGE_API size_t skge_rank_packed_bytes(int64_t rows, int d); /* bytes of ONE (hi or lo) packed array */
 SKGE_API int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_scale,
                        float scalar_scale, void *hi, void *lo, skge_stream_t stream);
+/* Per-query power-of-two scale (max|q| * qscale in [2^11, 2^12)) and the scaled
+ * thresholds thr = (tscore -+ eps) * qscale * escale, rounded outwards. */
+SKGE_API int skge_rank_query_scale(const float *q32, const double *tscore, const float *eps, int64_t Q, int d,
+                          float escale, float *qscale, float *thr_lo, float *thr_hi,
+                          skge_stream_t stream);
 SKGE_API int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
                          const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
                          const float *thr_lo, const float *thr_hi, int32_t *cnt_gt,

@@ -1,7 +1,471 @@
-// placeholder: replaced by the tcgen05 kernel
+// HolE / RESCAL filtered ranking on the 5th-generation tensor cores (tcgen05).
+//
+//   scores[q][e] = sum_k Q[q][k] * E[e][k]      (skge/run_hole.py:15-19 as one GEMM)
+//
+// is never materialised: a persistent, warp-specialised kernel streams the
+// entity shard through shared memory with bulk-TMA copies, contracts it against
+// a resident tile of 128 queries with tcgen05.mma (fp32 accumulators in TMEM) and
+// the epilogue warps compare each accumulator, straight out of TMEM, with the
+// query's two thresholds: above thr_hi -> counted, inside [thr_lo, thr_hi] ->
+// appended to the candidate list that skge_rank_rescore settles in fp64.
+//
+// Precision: operands are fp16 hi/lo splits (x*scale = hi + lo + O(2^-22 |x|));
+// with nsplit = 3 the three products hi*hi + hi*lo + lo*hi are accumulated into
+// the same TMEM tile, which reproduces the fp32 inputs to ~2^-21 relative.  The
+// thresholds already contain the (power-of-two) scales.
+//
+// Memory layout (produced by skge_rank_pack_f16): rows are grouped in tiles of
+// 128, k in chunks of 64; one (tile, chunk) block is 16 KB laid out as UMMA
+// K-major, no-swizzle core matrices:  [kcore 8][rowgroup 16][row 8][8 halfs],
+// i.e. leading-dimension byte offset (between the two k core matrices of one
+// MMA) 2048 B and stride byte offset (between 8-row groups) 128 B.  A block is
+// contiguous in global memory, so a stage is filled by plain 1-D bulk copies
+// (no tensor map, nothing to keep in sync with a swizzle mode).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
-extern "C" {
-size_t skge_rank_packed_bytes(int64_t rows, int d) { (void)rows; (void)d; return 0; }
-int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_scale, float scalar_scale, void *hi, void *lo, skge_stream_t stream) { skge::set_error("not built"); return SKGE_EINVAL; }
-int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base, const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit, const float *thr_lo, const float *thr_hi, int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap, unsigned long long *cand_count, skge_stream_t stream) { skge::set_error("not built"); return SKGE_EINVAL; }
+
+namespace skge {
+
+static constexpr int TILE = 128;                       // rows per tile (queries: UMMA M, entities: UMMA N)
+static constexpr int KCHUNK = 64;                      // k per block
+static constexpr int BLOCK_HALFS = TILE * KCHUNK;      // 8192 halfs = 16 KB
+static constexpr int BLOCK_BYTES = BLOCK_HALFS * 2;
+static constexpr int MAX_KCH = 4;                      // d <= 256
+static constexpr int B_STAGES = 3;
+static constexpr int ACC_STAGES = 4;                   // 4 x 128 TMEM columns
+static constexpr int STAGING = 192;                    // candidate staging entries in smem
+static constexpr uint32_t LBO_BYTES = 2048, SBO_BYTES = 128;
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(LBO_BYTES >> 4) << 16) |
+         ((uint64_t)(SBO_BYTES >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = F32 (bit 4), A = B = F16 (0), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29).
+static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- shared-memory plan ----------------------------------------------------------
+struct __align__(8) Ctrl {
+  uint64_t a_full, a_empty;
+  uint64_t b_full[B_STAGES], b_empty[B_STAGES];
+  uint64_t acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
+  uint32_t tmem_base;
+  int stage_count;
+  unsigned long long base_slot;
+  int stage_q[STAGING], stage_e[STAGING];
+};
+
+struct GemmArgs {
+  const __half *Ehi, *Elo, *Qhi, *Qlo;
+  int64_t n_shard, shard_base, Q;
+  int kch, nsplit;
+  const float *thr_lo, *thr_hi;
+  int32_t *cnt_gt, *cand_q, *cand_e;
+  int64_t cand_cap;
+  unsigned long long *cand_count;
+  int qtiles, etiles;
+};
+
+// Work schedule shared by all roles: CTA c sweeps query tiles c, c + grid, c + 2 grid, ...
+// over ALL entity tiles, so the CTAs move through the entity shard together and every
+// entity block is fetched from HBM once and then served from L2 to the other CTAs.
+
+__device__ __forceinline__ void flush_staging(Ctrl *ctrl, const GemmArgs &a, int tid128) {
+  // called by the 128 epilogue threads together
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  int n = ctrl->stage_count;
+  if (n > STAGING) n = STAGING;
+  if (tid128 == 0 && n > 0) ctrl->base_slot = atomicAdd(a.cand_count, (unsigned long long)n);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int i = tid128; i < n; i += 128) {
+    unsigned long long slot = ctrl->base_slot + i;
+    if ((int64_t)slot < a.cand_cap) {
+      a.cand_q[slot] = ctrl->stage_q[i];
+      a.cand_e[slot] = ctrl->stage_e[i];
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (tid128 == 0) ctrl->stage_count = 0;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+__device__ __forceinline__ void push_candidate(Ctrl *ctrl, const GemmArgs &a, int q, int e) {
+  int pos = atomicAdd(&ctrl->stage_count, 1);
+  if (pos < STAGING) {
+    ctrl->stage_q[pos] = q;
+    ctrl->stage_e[pos] = e;
+  } else {  // staging full: straight to the global list (rare)
+    unsigned long long slot = atomicAdd(a.cand_count, 1ull);
+    if ((int64_t)slot < a.cand_cap) {
+      a.cand_q[slot] = q;
+      a.cand_e[slot] = e;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) rank_gemm_kernel(GemmArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // carve: A (kch blocks hi, kch blocks lo), B stages (hi, lo), control.  No-swizzle
+  // descriptors and bulk copies only need 16-byte alignment.
+  uint8_t *sA_hi = smem_raw;
+  uint8_t *sA_lo = sA_hi + a.kch * BLOCK_BYTES;
+  uint8_t *sB = sA_lo + a.kch * BLOCK_BYTES;  // stage s: hi at s*2*BLOCK, lo right after
+  Ctrl *ctrl = reinterpret_cast<Ctrl *>(sB + B_STAGES * 2 * BLOCK_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kch = a.kch;
+  const int nprod = a.nsplit == 1 ? 1 : 3;
+  const bool use_lo = nprod == 3;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&ctrl->a_full, 1);
+    mbar_init(&ctrl->a_empty, 1);
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ctrl->b_full[s], 1); mbar_init(&ctrl->b_empty[s], 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&ctrl->acc_full[s], 1); mbar_init(&ctrl->acc_empty[s], 4); }
+    ctrl->stage_count = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctrl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer: bulk copies global -> shared =====================
+    if (lane == 0) {
+      uint32_t bstage = 0, bphase = 0, aphase = 0;
+      const uint32_t a_bytes = (uint32_t)kch * BLOCK_BYTES * (use_lo ? 2 : 1);
+      const uint32_t b_bytes = (uint32_t)BLOCK_BYTES * (use_lo ? 2 : 1);
+      for (int qt = blockIdx.x; qt < a.qtiles; qt += gridDim.x) {
+        mbar_wait(&ctrl->a_empty, aphase ^ 1);  // previous sweep's MMAs retired
+        mbar_expect_tx(&ctrl->a_full, a_bytes);
+        const __half *qh = a.Qhi + (int64_t)qt * kch * BLOCK_HALFS;
+        const __half *ql = a.Qlo + (int64_t)qt * kch * BLOCK_HALFS;
+        for (int c = 0; c < kch; ++c) {
+          bulk_g2s(sA_hi + c * BLOCK_BYTES, qh + (int64_t)c * BLOCK_HALFS, BLOCK_BYTES, &ctrl->a_full);
+          if (use_lo) bulk_g2s(sA_lo + c * BLOCK_BYTES, ql + (int64_t)c * BLOCK_HALFS, BLOCK_BYTES, &ctrl->a_full);
+        }
+        aphase ^= 1;
+        for (int et = 0; et < a.etiles; ++et) {
+          for (int c = 0; c < kch; ++c) {
+            mbar_wait(&ctrl->b_empty[bstage], bphase ^ 1);
+            mbar_expect_tx(&ctrl->b_full[bstage], b_bytes);
+            uint8_t *dst = sB + bstage * 2 * BLOCK_BYTES;
+            int64_t off = ((int64_t)et * kch + c) * BLOCK_HALFS;
+            bulk_g2s(dst, a.Ehi + off, BLOCK_BYTES, &ctrl->b_full[bstage]);
+            if (use_lo) bulk_g2s(dst + BLOCK_BYTES, a.Elo + off, BLOCK_BYTES, &ctrl->b_full[bstage]);
+            if (++bstage == B_STAGES) { bstage = 0; bphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected lane) =====================
+    if (lane == 0) {
+      uint32_t bstage = 0, bphase = 0, aphase = 0, accs = 0, accphase = 0;
+      for (int qt = blockIdx.x; qt < a.qtiles; qt += gridDim.x) {
+        mbar_wait(&ctrl->a_full, aphase);
+        aphase ^= 1;
+        for (int et = 0; et < a.etiles; ++et) {
+          mbar_wait(&ctrl->acc_empty[accs], accphase ^ 1);  // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + accs * TILE;
+          uint32_t acc_on = 0;
+          for (int c = 0; c < kch; ++c) {
+            mbar_wait(&ctrl->b_full[bstage], bphase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(sA_hi + c * BLOCK_BYTES), a_lo = smem_u32(sA_lo + c * BLOCK_BYTES);
+            const uint32_t b_hi = smem_u32(sB + bstage * 2 * BLOCK_BYTES), b_lo = b_hi + BLOCK_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < KCHUNK / 16; ++ks) {
+              const uint32_t koff = ks * 2 * LBO_BYTES;  // one MMA consumes two k core matrices
+              umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), IDESC, acc_on);
+              acc_on = 1;
+              if (use_lo) {
+                umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), IDESC, 1);
+                umma_f16(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), IDESC, 1);
+              }
+            }
+            tc_commit(&ctrl->b_empty[bstage]);  // frees the stage once these MMAs have read it
+            if (++bstage == B_STAGES) { bstage = 0; bphase ^= 1; }
+          }
+          tc_commit(&ctrl->acc_full[accs]);  // accumulator complete -> epilogue
+          if (++accs == ACC_STAGES) { accs = 0; accphase ^= 1; }
+        }
+        tc_commit(&ctrl->a_empty);  // all MMAs of this sweep retired -> A may be overwritten
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> compare -> count / candidates =====================
+    const int ew = warp - 4;              // == warp % 4: the TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;       // query row inside the tile
+    const int tid128 = threadIdx.x - 128;
+    uint32_t accs = 0, accphase = 0;
+    for (int qt = blockIdx.x; qt < a.qtiles; qt += gridDim.x) {
+      const int64_t q = (int64_t)qt * TILE + row;
+      float thi = INFINITY, tlo = INFINITY;
+      if (q < a.Q) { thi = a.thr_hi[q]; tlo = a.thr_lo[q]; }
+      int cnt = 0;
+      for (int et = 0; et < a.etiles; ++et) {
+        mbar_wait(&ctrl->acc_full[accs], accphase);
+        tc_fence_after();
+        const int64_t e0 = (int64_t)et * TILE;
+        const int nvalid = (int)min((int64_t)TILE, a.n_shard - e0);
+        const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + accs * TILE;
+#pragma unroll 1
+        for (int c4 = 0; c4 < TILE / 32; ++c4) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c4 * 32, r);
+          tmem_ld_wait();
+          int chi = 0, clo = 0;
+          if (c4 * 32 + 32 <= nvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]);
+              chi += v > thi;
+              clo += v >= tlo;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]);
+              bool ok = c4 * 32 + j < nvalid;
+              chi += ok && v > thi;
+              clo += ok && v >= tlo;
+            }
+          }
+          cnt += chi;
+          if (clo != chi) {  // someone sits inside [tlo, thi]: list them
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]);
+              if (c4 * 32 + j < nvalid && v >= tlo && !(v > thi))
+                push_candidate(ctrl, a, (int)q, (int)(a.shard_base + e0 + c4 * 32 + j));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->acc_empty[accs]);
+        if (++accs == ACC_STAGES) { accs = 0; accphase ^= 1; }
+        // the flush decision must be uniform across the 128 epilogue threads: take it at fixed points
+        if ((et & 15) == 15 || et == a.etiles - 1) flush_staging(ctrl, a, tid128);
+      }
+      if (q < a.Q && cnt) atomicAdd(a.cnt_gt + q, cnt);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---- operand packing ------------------------------------------------------------------
+// X[rows][d] fp32 -> hi/lo fp16 blocks (see the layout at the top).  One thread per
+// (row, group of 8 k): two 16-byte stores.
+__global__ void __launch_bounds__(256) pack_f16_kernel(const float *__restrict__ X, int64_t rows, int d,
+                                                       const float *__restrict__ row_scale, float scalar_scale,
+                                                       __half *__restrict__ hi, __half *__restrict__ lo, int kch,
+                                                       int64_t rows_padded) {
+  const int groups = kch * (KCHUNK / 8);
+  int64_t total = rows_padded * groups;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t / groups;
+    int g = (int)(t - r * groups);
+    int c = g / (KCHUNK / 8), kcore = g % (KCHUNK / 8);
+    int k0 = c * KCHUNK + kcore * 8;
+    float sc = scalar_scale * ((row_scale && r < rows) ? row_scale[r] : 1.0f);
+    __align__(16) __half h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = (r < rows && k0 + i < d) ? __ldg(X + r * d + k0 + i) * sc : 0.f;
+      __half hh = __float2half_rn(v);
+      h[i] = hh;
+      l[i] = __float2half_rn(v - __half2float(hh));
+    }
+    int64_t tile = r / TILE;
+    int rr = (int)(r % TILE);
+    int64_t off = (tile * kch + c) * (int64_t)BLOCK_HALFS + (int64_t)kcore * (16 * 64) + (rr >> 3) * 64 + (rr & 7) * 8;
+    *reinterpret_cast<uint4 *>(hi + off) = *reinterpret_cast<const uint4 *>(h);
+    *reinterpret_cast<uint4 *>(lo + off) = *reinterpret_cast<const uint4 *>(l);
+  }
+}
+
+// Per-query power-of-two scale and the scaled thresholds.
+//   qscale = 2^(12 - ceil(log2 max|q|));  thr = (tscore -+ eps) * qscale * escale (rounded outwards)
+__global__ void __launch_bounds__(256) query_scale_kernel(const float *__restrict__ q32,
+                                                          const double *__restrict__ tscore,
+                                                          const float *__restrict__ eps, int64_t Q, int d,
+                                                          float escale, float *__restrict__ qscale,
+                                                          float *__restrict__ thr_lo, float *__restrict__ thr_hi) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t q = warp; q < Q; q += nwarps) {
+    float m = 0.f;
+    for (int c = lane; c < d; c += 32) m = fmaxf(m, fabsf(__ldg(q32 + q * d + c)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if (lane == 0) {
+      int ex = 0;
+      if (m > 0.f) frexpf(m, &ex);          // m = f * 2^ex, f in [0.5, 1)
+      float s = ldexpf(1.0f, 12 - ex);       // m * s in [2^11, 2^12)
+      qscale[q] = s;
+      double f = (double)s * (double)escale, t = tscore[q], e = (double)eps[q];
+      thr_hi[q] = __double2float_ru((t + e) * f);
+      thr_lo[q] = __double2float_rd((t - e) * f);
+    }
+  }
+}
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace skge
+
+using namespace skge;
+
+extern "C" {
+
+size_t skge_rank_packed_bytes(int64_t rows, int d) {
+  int kch = (d + KCHUNK - 1) / KCHUNK;
+  return (size_t)(round_up(rows > 0 ? rows : 1, TILE) / TILE) * kch * BLOCK_BYTES;
+}
+
+int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_scale, float scalar_scale,
+                       void *hi, void *lo, skge_stream_t stream) {
+  SKGE_REQUIRE(X && hi && lo && rows > 0 && d > 0, "bad arguments");
+  int kch = (d + KCHUNK - 1) / KCHUNK;
+  int64_t rp = round_up(rows, TILE);
+  int64_t total = rp * kch * (KCHUNK / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  pack_f16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(X, rows, d, row_scale, scalar_scale,
+                                                             static_cast<__half *>(hi), static_cast<__half *>(lo),
+                                                             kch, rp);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+int skge_rank_query_scale(const float *q32, const double *tscore, const float *eps, int64_t Q, int d,
+                          float escale, float *qscale, float *thr_lo, float *thr_hi, skge_stream_t stream) {
+  SKGE_REQUIRE(q32 && tscore && eps && qscale && thr_lo && thr_hi && Q >= 0 && d > 0, "bad arguments");
+  if (Q == 0) return 0;
+  int64_t blocks = (Q + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  query_scale_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(q32, tscore, eps, Q, d, escale, qscale, thr_lo,
+                                                                thr_hi);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
+                         const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
+                         const float *thr_lo, const float *thr_hi, int32_t *cnt_gt,
+                         int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
+                         unsigned long long *cand_count, skge_stream_t stream) {
+  SKGE_REQUIRE(Ehi && Elo && Qhi && Qlo && thr_lo && thr_hi && cnt_gt && cand_q && cand_e && cand_count,
+               "null argument");
+  SKGE_REQUIRE(d > 0 && d <= MAX_KCH * KCHUNK, "the tcgen05 ranking kernel supports d <= 256");
+  SKGE_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
+  SKGE_REQUIRE(n_shard >= 0 && Q >= 0, "bad sizes");
+  if (Q == 0 || n_shard == 0) return 0;
+  GemmArgs a;
+  a.Ehi = static_cast<const __half *>(Ehi);
+  a.Elo = static_cast<const __half *>(Elo);
+  a.Qhi = static_cast<const __half *>(Qhi);
+  a.Qlo = static_cast<const __half *>(Qlo);
+  a.n_shard = n_shard;
+  a.shard_base = shard_base;
+  a.Q = Q;
+  a.kch = (d + KCHUNK - 1) / KCHUNK;
+  a.nsplit = nsplit;
+  a.thr_lo = thr_lo;
+  a.thr_hi = thr_hi;
+  a.cnt_gt = cnt_gt;
+  a.cand_q = cand_q;
+  a.cand_e = cand_e;
+  a.cand_cap = cand_cap;
+  a.cand_count = cand_count;
+  a.qtiles = (int)((Q + TILE - 1) / TILE);
+  a.etiles = (int)((n_shard + TILE - 1) / TILE);
+  size_t smem = (size_t)2 * a.kch * BLOCK_BYTES + (size_t)B_STAGES * 2 * BLOCK_BYTES + sizeof(Ctrl);
+  SKGE_CUDA(cudaFuncSetAttribute(rank_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = a.qtiles < kNumSMs ? a.qtiles : kNumSMs;
+  rank_gemm_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

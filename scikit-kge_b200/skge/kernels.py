@@ -210,3 +210,32 @@ def rank_scores_one(op, E, q64_row):
     out = torch.empty(E.shape[0], dtype=torch.float64, device=_ext.device())
     check(lib().skge_rank_scores_one(op, ptr(E), E.shape[0], E.shape[1], ptr(q64_row), ptr(out), stream()))
     return out
+
+
+def pack_f16(X, row_scale, scalar_scale):
+    """fp32 [rows, d] -> (hi, lo) fp16 UMMA blocks (uint8 tensors)."""
+    rows, d = X.shape
+    nbytes = lib().skge_rank_packed_bytes(rows, d)
+    hi = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
+    lo = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
+    _count('pack')
+    check(lib().skge_rank_pack_f16(ptr(X), rows, d, ptr(row_scale), float(scalar_scale), ptr(hi), ptr(lo),
+                                   stream()))
+    return hi, lo
+
+
+def query_scale(q, escale):
+    Q, d = q['q32'].shape
+    qscale, tlo, thi = _f32(Q), _f32(Q), _f32(Q)
+    _count('pack')
+    check(lib().skge_rank_query_scale(ptr(q['q32']), ptr(q['tscore']), ptr(q['eps']), Q, d, float(escale),
+                                      ptr(qscale), ptr(tlo), ptr(thi), stream()))
+    return qscale, tlo, thi
+
+
+def rank_gemm_count(Ehi, Elo, n_shard, shard_base, Qhi, Qlo, Q, d, nsplit, tlo, thi, cnt_gt, cand_q, cand_e,
+                    cand_count):
+    _count('gemm')
+    check(lib().skge_rank_gemm_count(ptr(Ehi), ptr(Elo), n_shard, shard_base, ptr(Qhi), ptr(Qlo), Q, d, nsplit,
+                                     ptr(tlo), ptr(thi), ptr(cnt_gt), ptr(cand_q), ptr(cand_e), cand_q.numel(),
+                                     ptr(cand_count), stream()))

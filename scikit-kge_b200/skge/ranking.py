@@ -262,7 +262,18 @@ class FilteredRankingEval(object):
                                engine=engine.name)
         return cnt if emulated else allreduce_counts(cnt)
 
+    engine = 'auto'             # 'auto' | 'sweep' (fp32 CUDA cores) | 'umma' (tcgen05, DOT models, d <= 256)
+    nsplit = 3                  # fp16 hi/lo products accumulated by the tcgen05 engine (1 or 3)
+
     def _coarse_engine(self, E, lo, hi, enorm):
+        dot = kernels.rank_op(self.model_code) == _ext.RANK_DOT
+        want = self.engine
+        if want == 'auto':
+            want = 'umma' if (dot and self.use_tensor_cores and E.shape[1] <= 256) else 'sweep'
+        if want == 'umma':
+            if not dot or E.shape[1] > 256:
+                raise ValueError('the tcgen05 engine needs a dot-product model with d <= 256')
+            return _UmmaEngine(E, lo, hi, self.nsplit)
         return _SweepEngine(E, lo, hi)
 
     # -- reference-style hooks (fp64 score vectors from the device) ---------------------
@@ -340,6 +351,37 @@ class _SweepEngine(object):
         if n:
             kernels.rank_rescore(op, self.E, q, self.cand_q, self.cand_e, n, None, None, cnt_gt)
         return n
+
+
+class _UmmaEngine(_SweepEngine):
+    """tcgen05 coarse pass: fp16 hi/lo split operands, fp32 accumulation in TMEM,
+    count / band epilogue straight out of TMEM (csrc/rank_umma.cu).  The fp16
+    shadow of the entity shard is rebuilt once per ranking pass."""
+    name = 'tcgen05-f16x3'
+
+    def __init__(self, E, lo, hi, nsplit=3):
+        super(_UmmaEngine, self).__init__(E, lo, hi)
+        self.nsplit = nsplit
+        self.name = 'tcgen05-f16x%d' % nsplit
+        if hi > lo:
+            emax = float(self.shard.abs().max().item())
+            self.escale = 2.0 ** (12 - math.ceil(math.log2(emax))) if emax > 0 else 1.0
+            self.Ehi, self.Elo = kernels.pack_f16(self.shard, None, self.escale)
+
+    def coarse_rel(self, d):
+        # split residual 3*2^-22 + fp32 rounding of q 2^-24 + <= 2^-22 per tcgen05.mma over the
+        # 3*d/16 accumulation steps, all relative to sum|q_i e_i| <= |q||e|: < 1.3e-5 at d = 256.
+        # 2^-15 leaves a 2.5x margin.  nsplit = 1 keeps only hi*hi: 2^-10 (fp16 rounding of both operands).
+        return 2.0 ** -15 if self.nsplit == 3 else 2.0 ** -9
+
+    def _coarse(self, op, q, cnt_gt):
+        Q, d = q['q32'].shape
+        qscale, tlo, thi = kernels.query_scale(q, self.escale)
+        Qhi, Qlo = kernels.pack_f16(q['q32'], qscale, 1.0)
+        work = 2.0 * (self.hi - self.lo) * d * Q
+        self._timed(lambda: kernels.rank_gemm_count(self.Ehi, self.Elo, self.hi - self.lo, self.lo, Qhi, Qlo, Q, d,
+                                                    self.nsplit, tlo, thi, cnt_gt, self.cand_q, self.cand_e,
+                                                    self.count), work)
 
 
 class TransEEval(FilteredRankingEval):

@@ -74,10 +74,12 @@ def _graph(seed, N, M, ntrue, ntest):
     return rng, true, test
 
 
-@pytest.mark.parametrize('kind,N,d', [('transe', 1500, 50), ('transe', 700, 200), ('hole', 1500, 150),
-                                      ('hole', 900, 256), ('rescal', 800, 100), ('hole', 333, 37),
-                                      ('transe', 257, 7)])
-def test_positions_match_oracle_on_random_graphs(kind, N, d):
+@pytest.mark.parametrize('kind,N,d,engine', [
+    ('transe', 1500, 50, 'sweep'), ('transe', 700, 200, 'sweep'), ('transe', 257, 7, 'sweep'),
+    ('hole', 1500, 150, 'sweep'), ('hole', 900, 256, 'sweep'), ('rescal', 800, 100, 'sweep'), ('hole', 333, 37, 'sweep'),
+    ('hole', 1500, 150, 'umma'), ('hole', 900, 256, 'umma'), ('rescal', 800, 100, 'umma'), ('hole', 333, 37, 'umma'),
+    ('hole', 129, 64, 'umma'), ('hole', 700, 300, 'auto')])
+def test_positions_match_oracle_on_random_graphs(kind, N, d, engine):
     M = 5
     rng, true, test = _graph(N + d, N, M, 6 * N, 150)
     E0 = (rng.normal(size=(N, d)) * 0.3).astype(np.float32).astype(np.float64)
@@ -86,7 +88,10 @@ def test_positions_match_oracle_on_random_graphs(kind, N, d):
     m = _model(kind, E0, R0)
     ev = _evaluator(kind)(test, true)
     ev.chunk_queries = 128        # several chunks, the last one ragged
+    ev.engine = engine
     pos, fpos = ev.positions(m)
+    want = {'sweep': 'fp32-sweep', 'umma': 'tcgen05-f16x3', 'auto': 'fp32-sweep' if d > 256 else 'tcgen05-f16x3'}
+    assert ev.last_stats['engine'] == want[engine]
     opos, ofpos, margins = orc.rank_positions(kind, E0, R0, test, true, tie='argsort', with_scores=True)
     assert list(pos.keys()) == list(opos.keys())
     nt = 0
@@ -99,6 +104,29 @@ def test_positions_match_oracle_on_random_graphs(kind, N, d):
                     assert fpos[p][side][i] == ofpos[p][side][i], (p, side, i)
     assert nt >= 290
     assert ev.last_stats['filter_pairs'] > 0
+
+
+@pytest.mark.parametrize('N,d,te', [(40943, 150, 700), (20000, 256, 1500), (5000, 64, 300)])
+def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te):
+    """Both coarse engines settle their undecided band in fp64, so the final counts
+    must agree exactly (config-2-sized table and a d = 256 table); the single-product
+    fp16 mode (nsplit = 1) must agree too, it only lists more candidates."""
+    M = 18
+    rng, true, test = _graph(N, N, M, 3 * N, te)
+    E0 = (rng.normal(size=(N, d)) / np.sqrt(d)).astype(np.float32)
+    R0 = (rng.normal(size=(M, d)) / np.sqrt(d)).astype(np.float32)
+    m = _model('hole', E0, R0)
+    ev = _evaluator('hole')(test, true)
+    ev.engine = 'sweep'
+    ref = ev.count_pass(m)
+    ev.engine = 'umma'
+    got = ev.count_pass(m)
+    c3 = ev.last_stats['candidates']
+    assert torch.equal(got, ref)
+    ev.nsplit = 1
+    got1 = ev.count_pass(m)
+    assert torch.equal(got1, ref)
+    assert ev.last_stats['candidates'] > c3 and ev.last_stats['engine'] == 'tcgen05-f16x1'
 
 
 @pytest.mark.parametrize('kind', ['transe', 'hole'])
