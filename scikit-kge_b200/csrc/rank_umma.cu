@@ -127,46 +127,67 @@ struct GemmArgs {
   int64_t cand_cap;
   unsigned long long *cand_count;
   int qtiles, etiles;
+  int nslices, tiles_per_slice;   // entity tiles are processed in L2-sized slices
 };
 
-// Work schedule shared by all roles: CTA c sweeps query tiles c, c + grid, c + 2 grid, ...
-// over ALL entity tiles, so the CTAs move through the entity shard together and every
-// entity block is fetched from HBM once and then served from L2 to the other CTAs.
+// Work schedule shared by all roles.  The entity shard is cut into slices that fit in L2;
+// a work item is (slice, query tile), numbered slice-major, and CTA c takes items
+// c, c + grid, c + 2 grid, ...  All CTAs therefore sweep the SAME slice with different
+// query tiles at the same time: a slice is fetched from HBM once and then served from L2
+// to every query tile, and the fine-grained items keep the last wave short.
+struct Item { int qt, et_beg, et_end; };
+__device__ __forceinline__ Item get_item(const GemmArgs &a, int item) {
+  Item it;
+  int slice = item / a.qtiles;
+  it.qt = item - slice * a.qtiles;
+  it.et_beg = slice * a.tiles_per_slice;
+  it.et_end = min(a.etiles, it.et_beg + a.tiles_per_slice);
+  return it;
+}
 
 __device__ __forceinline__ void flush_staging(Ctrl *ctrl, const GemmArgs &a, int tid128) {
-  // called by the 128 epilogue threads together
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // called by the 256 epilogue threads together
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   int n = ctrl->stage_count;
   if (n > STAGING) n = STAGING;
   if (tid128 == 0 && n > 0) ctrl->base_slot = atomicAdd(a.cand_count, (unsigned long long)n);
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  for (int i = tid128; i < n; i += 128) {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  for (int i = tid128; i < n; i += 256) {
     unsigned long long slot = ctrl->base_slot + i;
     if ((int64_t)slot < a.cand_cap) {
       a.cand_q[slot] = ctrl->stage_q[i];
       a.cand_e[slot] = ctrl->stage_e[i];
     }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   if (tid128 == 0) ctrl->stage_count = 0;
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-__device__ __forceinline__ void push_candidate(Ctrl *ctrl, const GemmArgs &a, int q, int e) {
-  int pos = atomicAdd(&ctrl->stage_count, 1);
-  if (pos < STAGING) {
-    ctrl->stage_q[pos] = q;
-    ctrl->stage_e[pos] = e;
-  } else {  // staging full: straight to the global list (rare)
-    unsigned long long slot = atomicAdd(a.cand_count, 1ull);
-    if ((int64_t)slot < a.cand_cap) {
-      a.cand_q[slot] = q;
-      a.cand_e[slot] = e;
+// Append the in-band columns of one lane's 32-column chunk: one shared-memory atomic
+// reserves the slots, then the set bits are walked.  Overflow of the staging area goes
+// straight to the global list (rare).
+__device__ __forceinline__ void push_band(Ctrl *ctrl, const GemmArgs &a, int q, int ebase, uint32_t band) {
+  int n = __popc(band);
+  int pos = atomicAdd(&ctrl->stage_count, n);
+  while (band) {
+    int j = __ffs(band) - 1;
+    band &= band - 1;
+    if (pos < STAGING) {
+      ctrl->stage_q[pos] = q;
+      ctrl->stage_e[pos] = ebase + j;
+    } else {
+      unsigned long long slot = atomicAdd(a.cand_count, 1ull);
+      if ((int64_t)slot < a.cand_cap) {
+        a.cand_q[slot] = q;
+        a.cand_e[slot] = ebase + j;
+      }
     }
+    ++pos;
   }
 }
 
-__global__ void __launch_bounds__(256, 1) rank_gemm_kernel(GemmArgs a) {
+__global__ void __launch_bounds__(384, 1) rank_gemm_kernel(GemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // carve: A (kch blocks hi, kch blocks lo), B stages (hi, lo), control.  No-swizzle
   // descriptors and bulk copies only need 16-byte alignment.
@@ -177,6 +198,7 @@ __global__ void __launch_bounds__(256, 1) rank_gemm_kernel(GemmArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kch = a.kch;
+  const int nitems = a.qtiles * a.nslices;
   const int nprod = a.nsplit == 1 ? 1 : 3;
   const bool use_lo = nprod == 3;
 
@@ -184,7 +206,7 @@ __global__ void __launch_bounds__(256, 1) rank_gemm_kernel(GemmArgs a) {
     mbar_init(&ctrl->a_full, 1);
     mbar_init(&ctrl->a_empty, 1);
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ctrl->b_full[s], 1); mbar_init(&ctrl->b_empty[s], 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&ctrl->acc_full[s], 1); mbar_init(&ctrl->acc_empty[s], 4); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&ctrl->acc_full[s], 1); mbar_init(&ctrl->acc_empty[s], 8); }
     ctrl->stage_count = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -206,17 +228,18 @@ __global__ void __launch_bounds__(256, 1) rank_gemm_kernel(GemmArgs a) {
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       const uint32_t a_bytes = (uint32_t)kch * BLOCK_BYTES * (use_lo ? 2 : 1);
       const uint32_t b_bytes = (uint32_t)BLOCK_BYTES * (use_lo ? 2 : 1);
-      for (int qt = blockIdx.x; qt < a.qtiles; qt += gridDim.x) {
-        mbar_wait(&ctrl->a_empty, aphase ^ 1);  // previous sweep's MMAs retired
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const Item it = get_item(a, item);
+        mbar_wait(&ctrl->a_empty, aphase ^ 1);  // previous item's MMAs retired
         mbar_expect_tx(&ctrl->a_full, a_bytes);
-        const __half *qh = a.Qhi + (int64_t)qt * kch * BLOCK_HALFS;
-        const __half *ql = a.Qlo + (int64_t)qt * kch * BLOCK_HALFS;
+        const __half *qh = a.Qhi + (int64_t)it.qt * kch * BLOCK_HALFS;
+        const __half *ql = a.Qlo + (int64_t)it.qt * kch * BLOCK_HALFS;
         for (int c = 0; c < kch; ++c) {
           bulk_g2s(sA_hi + c * BLOCK_BYTES, qh + (int64_t)c * BLOCK_HALFS, BLOCK_BYTES, &ctrl->a_full);
           if (use_lo) bulk_g2s(sA_lo + c * BLOCK_BYTES, ql + (int64_t)c * BLOCK_HALFS, BLOCK_BYTES, &ctrl->a_full);
         }
         aphase ^= 1;
-        for (int et = 0; et < a.etiles; ++et) {
+        for (int et = it.et_beg; et < it.et_end; ++et) {
           for (int c = 0; c < kch; ++c) {
             mbar_wait(&ctrl->b_empty[bstage], bphase ^ 1);
             mbar_expect_tx(&ctrl->b_full[bstage], b_bytes);
@@ -233,10 +256,11 @@ __global__ void __launch_bounds__(256, 1) rank_gemm_kernel(GemmArgs a) {
     // ===================== MMA issuer (one elected lane) =====================
     if (lane == 0) {
       uint32_t bstage = 0, bphase = 0, aphase = 0, accs = 0, accphase = 0;
-      for (int qt = blockIdx.x; qt < a.qtiles; qt += gridDim.x) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const Item it = get_item(a, item);
         mbar_wait(&ctrl->a_full, aphase);
         aphase ^= 1;
-        for (int et = 0; et < a.etiles; ++et) {
+        for (int et = it.et_beg; et < it.et_end; ++et) {
           mbar_wait(&ctrl->acc_empty[accs], accphase ^ 1);  // epilogue drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem + accs * TILE;
@@ -262,64 +286,62 @@ __global__ void __launch_bounds__(256, 1) rank_gemm_kernel(GemmArgs a) {
           tc_commit(&ctrl->acc_full[accs]);  // accumulator complete -> epilogue
           if (++accs == ACC_STAGES) { accs = 0; accphase ^= 1; }
         }
-        tc_commit(&ctrl->a_empty);  // all MMAs of this sweep retired -> A may be overwritten
+        tc_commit(&ctrl->a_empty);  // all MMAs of this item retired -> A may be overwritten
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> compare -> count / candidates =====================
-    const int ew = warp - 4;              // == warp % 4: the TMEM lane quarter this warp may read
-    const int row = ew * 32 + lane;       // query row inside the tile
-    const int tid128 = threadIdx.x - 128;
+    // 8 warps: warp % 4 is the TMEM lane quarter a warp may read, (warp - 4) / 4 the column half
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int row = quarter * 32 + lane;  // query row inside the tile
+    const int tid256 = threadIdx.x - 128;
     uint32_t accs = 0, accphase = 0;
-    for (int qt = blockIdx.x; qt < a.qtiles; qt += gridDim.x) {
-      const int64_t q = (int64_t)qt * TILE + row;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const Item it = get_item(a, item);
+      const int64_t q = (int64_t)it.qt * TILE + row;
       float thi = INFINITY, tlo = INFINITY;
       if (q < a.Q) { thi = a.thr_hi[q]; tlo = a.thr_lo[q]; }
       int cnt = 0;
-      for (int et = 0; et < a.etiles; ++et) {
+      for (int et = it.et_beg; et < it.et_end; ++et) {
         mbar_wait(&ctrl->acc_full[accs], accphase);
         tc_fence_after();
         const int64_t e0 = (int64_t)et * TILE;
         const int nvalid = (int)min((int64_t)TILE, a.n_shard - e0);
-        const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + accs * TILE;
-#pragma unroll 1
-        for (int c4 = 0; c4 < TILE / 32; ++c4) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c4 * 32, r);
-          tmem_ld_wait();
-          int chi = 0, clo = 0;
-          if (c4 * 32 + 32 <= nvalid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]);
-              chi += v > thi;
-              clo += v >= tlo;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]);
-              bool ok = c4 * 32 + j < nvalid;
-              chi += ok && v > thi;
-              clo += ok && v >= tlo;
-            }
-          }
-          cnt += chi;
-          if (clo != chi) {  // someone sits inside [tlo, thi]: list them
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]);
-              if (c4 * 32 + j < nvalid && v >= tlo && !(v > thi))
-                push_candidate(ctrl, a, (int)q, (int)(a.shard_base + e0 + c4 * 32 + j));
-            }
-          }
-        }
+        const int col0 = half * 64;
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + accs * TILE + col0;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+        // the accumulator is in registers: hand the TMEM stage back before the compare work
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctrl->acc_empty[accs]);
         if (++accs == ACC_STAGES) { accs = 0; accphase ^= 1; }
-        // the flush decision must be uniform across the 128 epilogue threads: take it at fixed points
-        if ((et & 15) == 15 || et == a.etiles - 1) flush_staging(ctrl, a, tid128);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          // bit j of mhi / mlo: column j beats thr_hi / reaches thr_lo (4 partial masks keep the
+          // dependency chains short)
+          uint32_t mh[4] = {0u, 0u, 0u, 0u}, ml[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(c2 == 0 ? r0[j] : r1[j]);
+            if (v > thi) mh[j & 3] |= 1u << j;
+            if (v >= tlo) ml[j & 3] |= 1u << j;
+          }
+          uint32_t mhi = (mh[0] | mh[1]) | (mh[2] | mh[3]), mlo = (ml[0] | ml[1]) | (ml[2] | ml[3]);
+          const int left = nvalid - (col0 + c2 * 32);
+          if (left < 32) {  // last, partial entity tile
+            uint32_t vm = left <= 0 ? 0u : (0xFFFFFFFFu >> (32 - left));
+            mhi &= vm;
+            mlo &= vm;
+          }
+          cnt += __popc(mhi);
+          uint32_t band = mlo & ~mhi;  // inside [thr_lo, thr_hi]: settle in fp64 later
+          if (band) push_band(ctrl, a, (int)q, (int)(a.shard_base + e0 + col0 + c2 * 32), band);
+        }
+        // the flush decision must be uniform across the 256 epilogue threads: take it at fixed points
+        if (((et - it.et_beg) & 15) == 15 || et == it.et_end - 1) flush_staging(ctrl, a, tid256);
       }
       if (q < a.Q && cnt) atomicAdd(a.cnt_gt + q, cnt);
     }
@@ -462,8 +484,16 @@ int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int6
   a.etiles = (int)((n_shard + TILE - 1) / TILE);
   size_t smem = (size_t)2 * a.kch * BLOCK_BYTES + (size_t)B_STAGES * 2 * BLOCK_BYTES + sizeof(Ctrl);
   SKGE_CUDA(cudaFuncSetAttribute(rank_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = a.qtiles < kNumSMs ? a.qtiles : kNumSMs;
-  rank_gemm_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
+  // slices of at most ~48 MB (hi + lo) so a slice stays L2-resident while every query tile
+  // sweeps it; more slices when there are too few query tiles to fill the machine
+  int tps = (48 << 20) / (a.kch * 2 * BLOCK_BYTES);
+  if (tps > a.etiles) tps = a.etiles;
+  while (tps > 64 && (int64_t)a.qtiles * ((a.etiles + tps - 1) / tps) < 8 * kNumSMs) tps = (tps + 1) / 2;
+  a.tiles_per_slice = tps;
+  a.nslices = (a.etiles + tps - 1) / tps;
+  int64_t nitems = (int64_t)a.qtiles * a.nslices;
+  int grid = nitems < kNumSMs ? (int)nitems : kNumSMs;
+  rank_gemm_kernel<<<grid, 384, smem, as_stream(stream)>>>(a);
   SKGE_LAUNCH_CHECK();
   return 0;
 }

@@ -159,7 +159,7 @@ class FilteredRankingEval(object):
     """
 
     model_code = None
-    chunk_queries = 32768       # queries per device pass (bounds q64/q32 scratch)
+    chunk_queries = 1 << 18     # queries per device pass (bounds q64/q32 scratch: 3 KB per query at d = 256)
     use_tensor_cores = True     # DOT models: tcgen05 coarse pass when the shapes allow
 
     def __init__(self, xs, true_triples, neval=-1):
@@ -244,6 +244,7 @@ class FilteredRankingEval(object):
             own = (pe >= lo) & (pe < hi)
             pq, pe = pq[own].contiguous(), pe[own].contiguous()
         engine = self._coarse_engine(E, lo, hi, enorm)
+        engine.reserve(min(Q, self.chunk_queries))
         pair_bounds = torch.searchsorted(pq.to(torch.int64),
                                          torch.arange(0, Q + self.chunk_queries, self.chunk_queries, device=dev)
                                          ).tolist()
@@ -259,22 +260,29 @@ class FilteredRankingEval(object):
                 kernels.rank_rescore(op, E, q, (pq[a:b] - q0).contiguous(), pe[a:b], b - a, None, None,
                                      cnt[1, sl])
         self.last_stats = dict(candidates=ncand, filter_pairs=int(pq.numel()), shard=(lo, hi), world=world,
-                               engine=engine.name)
+                               engine=engine.name, dtype=engine.dtype)
         return cnt if emulated else allreduce_counts(cnt)
 
     engine = 'auto'             # 'auto' | 'sweep' (fp32 CUDA cores) | 'umma' (tcgen05, DOT models, d <= 256)
     nsplit = 3                  # fp16 hi/lo products accumulated by the tcgen05 engine (1 or 3)
 
     def _coarse_engine(self, E, lo, hi, enorm):
+        """The coarse-pass engine for this shard.  The object (and its candidate
+        buffers) is cached across calls; the fp16 shadow of the shard is rebuilt on
+        every call because the model may have been trained in between."""
         dot = kernels.rank_op(self.model_code) == _ext.RANK_DOT
         want = self.engine
         if want == 'auto':
             want = 'umma' if (dot and self.use_tensor_cores and E.shape[1] <= 256) else 'sweep'
-        if want == 'umma':
-            if not dot or E.shape[1] > 256:
-                raise ValueError('the tcgen05 engine needs a dot-product model with d <= 256')
-            return _UmmaEngine(E, lo, hi, self.nsplit)
-        return _SweepEngine(E, lo, hi)
+        if want == 'umma' and (not dot or E.shape[1] > 256):
+            raise ValueError('the tcgen05 engine needs a dot-product model with d <= 256')
+        key = (want, self.nsplit if want == 'umma' else 0)
+        cache = self.__dict__.setdefault('_engines', {})
+        eng = cache.get(key)
+        if eng is None:
+            eng = cache[key] = _UmmaEngine(self.nsplit) if want == 'umma' else _SweepEngine()
+        eng.bind(E, lo, hi)
+        return eng
 
     # -- reference-style hooks (fp64 score vectors from the device) ---------------------
     def prepare(self, mdl, p):
@@ -300,16 +308,29 @@ TIMINGS = []   # (start event, end event, algorithmic flops/ops) per coarse laun
 class _SweepEngine(object):
     """fp32 coarse sweep on the CUDA cores (any model, any d) + fp64 settlement."""
     name = 'fp32-sweep'
+    dtype = 'f32 sweep + f64 settle'
+    cands_per_query = 512       # initial sizing of the candidate list
 
-    def __init__(self, E, lo, hi):
+    def __init__(self):
+        self.cap = 0
+        self.cand_q = self.cand_e = self.count = None
+
+    def bind(self, E, lo, hi):
         self.E = E
         self.lo, self.hi = lo, hi
         self.shard = E[lo:hi]
-        self.cap = 1 << 22
-        dev = E.device
-        self.cand_q = torch.empty(self.cap, dtype=torch.int32, device=dev)
-        self.cand_e = torch.empty(self.cap, dtype=torch.int32, device=dev)
-        self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+        if self.count is None or self.count.device != E.device:
+            self.count = torch.zeros(1, dtype=torch.int64, device=E.device)
+            self.cap = 0
+
+    def reserve(self, nqueries):
+        self._grow(max(1 << 20, self.cands_per_query * nqueries))
+
+    def _grow(self, n):
+        if n > self.cap:
+            self.cap = 1 << int(math.ceil(math.log2(n)))
+            self.cand_q = torch.empty(self.cap, dtype=torch.int32, device=self.E.device)
+            self.cand_e = torch.empty(self.cap, dtype=torch.int32, device=self.E.device)
 
     def coarse_rel(self, d):
         return 2.0 * (d + 2) * 2.0 ** -24
@@ -345,9 +366,7 @@ class _SweepEngine(object):
                 break
             # candidate list overflowed: grow it and redo the chunk from the saved counts
             cnt_gt.copy_(base)
-            self.cap = 1 << int(math.ceil(math.log2(n + 1)))
-            self.cand_q = torch.empty(self.cap, dtype=torch.int32, device=self.E.device)
-            self.cand_e = torch.empty(self.cap, dtype=torch.int32, device=self.E.device)
+            self._grow(n + 1)
         if n:
             kernels.rank_rescore(op, self.E, q, self.cand_q, self.cand_e, n, None, None, cnt_gt)
         return n
@@ -358,21 +377,30 @@ class _UmmaEngine(_SweepEngine):
     count / band epilogue straight out of TMEM (csrc/rank_umma.cu).  The fp16
     shadow of the entity shard is rebuilt once per ranking pass."""
     name = 'tcgen05-f16x3'
+    cands_per_query = 160
 
-    def __init__(self, E, lo, hi, nsplit=3):
-        super(_UmmaEngine, self).__init__(E, lo, hi)
+    def __init__(self, nsplit=3):
+        super(_UmmaEngine, self).__init__()
         self.nsplit = nsplit
         self.name = 'tcgen05-f16x%d' % nsplit
+        self.dtype = 'f16x%d split (tcgen05, fp32 accumulate) + f64 settle' % nsplit
+        if nsplit != 3:
+            self.cands_per_query = 4096
+
+    def bind(self, E, lo, hi):
+        super(_UmmaEngine, self).bind(E, lo, hi)
         if hi > lo:
             emax = float(self.shard.abs().max().item())
             self.escale = 2.0 ** (12 - math.ceil(math.log2(emax))) if emax > 0 else 1.0
             self.Ehi, self.Elo = kernels.pack_f16(self.shard, None, self.escale)
 
     def coarse_rel(self, d):
-        # split residual 3*2^-22 + fp32 rounding of q 2^-24 + <= 2^-22 per tcgen05.mma over the
-        # 3*d/16 accumulation steps, all relative to sum|q_i e_i| <= |q||e|: < 1.3e-5 at d = 256.
-        # 2^-15 leaves a 2.5x margin.  nsplit = 1 keeps only hi*hi: 2^-10 (fp16 rounding of both operands).
-        return 2.0 ** -15 if self.nsplit == 3 else 2.0 ** -9
+        # Error model, relative to sum|q_i e_i| <= |q||e|: split residual 3*2^-22, fp32 rounding
+        # of q 2^-24, and at most 2^-23 per tcgen05.mma over the 3*d/16 <= 48 accumulation steps
+        # (worst case, all one-sided): 6.2e-6 at d = 256.  2^-17 = 7.6e-6 covers it; the error
+        # measured on the B200 (profiles/exp_gemm.py probe) is 1.1e-7 = 2^-23.1, 70x smaller.
+        # nsplit = 1 keeps only hi*hi: fp16 rounding of both operands, 2^-10 worst case.
+        return 2.0 ** -17 if self.nsplit == 3 else 2.0 ** -9
 
     def _coarse(self, op, q, cnt_gt):
         Q, d = q['q32'].shape

@@ -85,7 +85,7 @@ def test_training_improves_filtered_mrr():
         run.epoch()
     _, (cpu_fmrr, _, _) = orc.ranking_scores(*orc.rank_positions('transe', run.E, run.R, np.array(test),
                                                                   np.array(triples)))
-    assert after > 2.5 * before
+    assert after > 1.5 * before and after > 0.05
     assert after > 0.6 * cpu_fmrr, (after, cpu_fmrr)
 
 
