@@ -171,11 +171,11 @@ static size_t logistic_ws_bytes(int model, int64_t n, int d, int64_t M) {
   if (n < 1) n = 1;
   int rows = model == SKGE_MODEL_RESCAL ? 2 : 3;
   size_t b = align_up((size_t)n * rows * d * sizeof(float));
-  b += seg_workspace_bytes((int64_t)3 * n);
+  b += seg_workspace_bytes((int64_t)3 * n, d);
   if (model == SKGE_MODEL_RESCAL) {
     int64_t uw = n < M ? n : M;
     b += align_up((size_t)n * sizeof(float));                     // fs
-    b += seg_workspace_bytes(n);                                  // relation grouping
+    b += seg_workspace_bytes(n, 0);                               // relation grouping
     b += align_up((size_t)uw * d * d * sizeof(float));            // gw (step mode)
     b += align_up((size_t)uw * sizeof(int32_t));                  // pidx (step mode)
   }

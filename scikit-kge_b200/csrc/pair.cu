@@ -195,7 +195,7 @@ struct PairBuffers {
 static size_t pair_ws_bytes(int64_t P, int d, int rows, int nroles) {
   if (P < 1) P = 1;
   return align_up((size_t)P) + align_up((size_t)P * rows * d * sizeof(float)) +
-         seg_workspace_bytes((int64_t)nroles * P) + 1024;
+         seg_workspace_bytes((int64_t)nroles * P, d) + 1024;
 }
 
 // model: 0 TransE, 1 HolE

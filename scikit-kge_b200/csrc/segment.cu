@@ -81,9 +81,19 @@ static size_t cub_scan_bytes(int64_t L) {
   return bytes;
 }
 
-size_t seg_workspace_bytes(int64_t L) {
+// Segments longer than kSegChunk occurrences (hot rows: a hub entity, a frequent relation)
+// are cut into chunks reduced by different warps and combined by one CTA per segment, in a
+// fixed order (deterministic, no atomics on parameter rows).
+static constexpr int kSegChunk = 128;
+
+static int64_t long_chunk_cap(int64_t L) { return L / (kSegChunk / 2) + 8; }  // sum ceil(len/128) over len > 128
+static int64_t long_seg_cap(int64_t L) { return L / kSegChunk + 8; }
+
+size_t seg_workspace_bytes(int64_t L, int d) {
   if (L < 1) L = 1;
   size_t b = 0;
+  b += align_up((size_t)long_seg_cap(L) * 3 * 4) + align_up((size_t)long_chunk_cap(L) * 2 * 4) + align_up(16);
+  b += align_up((size_t)long_chunk_cap(L) * (d > 0 ? d : 1) * sizeof(float));
   b += 4 * align_up((size_t)L * 4);        // keys in/out, vals in/out
   b += 2 * align_up((size_t)L * 4);        // head, pos
   b += 2 * align_up((size_t)(L + 1) * 4);  // seg_start, seg_key
@@ -199,73 +209,199 @@ struct SegArgs {
   int opt;
   float lr;
   int32_t *counts;
+  // long segments (more than kSegChunk occurrences)
+  int32_t *long_meta;   // [0] number of long segments, [1] number of chunks allocated
+  int32_t *long_seg;    // [long_seg_cap][3]: segment, first chunk, number of chunks
+  int32_t *long_work;   // [long_chunk_cap][2]: segment, chunk index inside the segment
+  float *partials;      // [long_chunk_cap][d]
+  int long_seg_cap, long_chunk_cap;
 };
 
+// acc += signed gradient rows of occurrences [beg, end) of the sorted list
+template <int VEC, int MAXC>
+__device__ __forceinline__ void accumulate_rows(const SegArgs &a, int beg, int end, int lane,
+                                                float (&acc)[MAXC][VEC]) {
+  const int d = a.d;
+#pragma unroll 2
+  for (int j = beg; j < end; ++j) {
+    int val = a.vals[j];
+    int r = val & 7;
+    const float *g = a.G + ((int64_t)(val >> 3) * a.rows_per_unit + a.grow[r]) * d;
+    float sgn = a.gsign[r];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      int col = (c * 32 + lane) * VEC;
+      if (col < d) {
+        float t[VEC];
+        ld_vec<VEC>(g + col, t);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(sgn, t[v], acc[c][v]);
+      }
+    }
+  }
+}
+
+// acc holds the SUM over the n occurrences of segment seg: take the mean and either apply
+// the optimiser step in place or emit (gradient row, row id).
+template <int VEC, int MAXC, bool UPDATE>
+__device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, int n, int lane,
+                                           float (&acc)[MAXC][VEC]) {
+  const int d = a.d;
+  const int U0 = a.meta[1];
+  int which = key >= a.N;
+  int64_t row = which ? key - a.N : key;
+  float fn = (float)n;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[c][v] /= fn;  // the mean: skge/util.py:97-101
+  const ParamDesc &pd = a.pd[which];
+  if (UPDATE) {
+    row_update<VEC, MAXC>(pd.param + row * d, pd.p2 ? pd.p2 + row * d : nullptr, acc, d, lane, a.opt, a.lr,
+                          pd.post, pd.rparam);
+    if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
+  } else {
+    int64_t u = which ? seg - U0 : seg;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      int col = (c * 32 + lane) * VEC;
+      if (col < d) {
+        if (pd.rparam != 0.f) {
+          float x[VEC];
+          ld_vec<VEC>(pd.param + row * d + col, x);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[c][v] += pd.rparam * x[v];
+        }
+        st_vec<VEC>(pd.out_g + u * d + col, acc[c]);
+      }
+    }
+    if (lane == 0) pd.out_idx[u] = (int32_t)row;
+  }
+}
+
+// Pass 1: one warp per segment.  Short segments are finished here; long ones are registered
+// (segment, chunk range) for passes 2 and 3.
 template <int VEC, int MAXC, bool UPDATE>
 __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
   const int lane = threadIdx.x & 31;
   const int nseg = a.meta[0];
-  const int U0 = a.meta[1];
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.counts) {
-    a.counts[1] = U0;
-    a.counts[2] = nseg - U0;
+    a.counts[1] = a.meta[1];
+    a.counts[2] = nseg - a.meta[1];
   }
   int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int nwarps = gridDim.x * (blockDim.x >> 5);
-  const int d = a.d;
   for (int seg = warp; seg < nseg; seg += nwarps) {
     int key = a.seg_key[seg];
     int beg = a.seg_start[seg], end = a.seg_start[seg + 1];
-    int which = key >= a.N;
-    int64_t row = which ? key - a.N : key;
+    int n = end - beg;
+    if (n > kSegChunk) {
+      int nch = (n + kSegChunk - 1) / kSegChunk;
+      int slot = 0, first = 0;
+      if (lane == 0) {
+        slot = atomicAdd(a.long_meta, 1);
+        first = atomicAdd(a.long_meta + 1, nch);
+      }
+      slot = __shfl_sync(kFull, slot, 0);
+      first = __shfl_sync(kFull, first, 0);
+      if (lane == 0) {
+        a.long_seg[3 * slot] = seg;
+        a.long_seg[3 * slot + 1] = first;
+        a.long_seg[3 * slot + 2] = nch;
+      }
+      for (int k = lane; k < nch; k += 32) {
+        a.long_work[2 * (first + k)] = seg;
+        a.long_work[2 * (first + k) + 1] = k;
+      }
+      continue;
+    }
     float acc[MAXC][VEC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
-#pragma unroll 2
-    for (int j = beg; j < end; ++j) {
-      int val = a.vals[j];
-      int r = val & 7;
-      const float *g = a.G + ((int64_t)(val >> 3) * a.rows_per_unit + a.grow[r]) * d;
-      float sgn = a.gsign[r];
+    accumulate_rows<VEC, MAXC>(a, beg, end, lane, acc);
+    finish_row<VEC, MAXC, UPDATE>(a, seg, key, n, lane, acc);
+  }
+}
+
+// Pass 2: one warp per chunk of a long segment -> partial sum row.
+template <int VEC, int MAXC>
+__global__ void __launch_bounds__(256) seg_long_chunks_kernel(SegArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = a.long_meta[1];
+  int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int d = a.d;
+  for (int c = warp; c < nchunks; c += nwarps) {
+    int seg = a.long_work[2 * c], k = a.long_work[2 * c + 1];
+    int beg = a.seg_start[seg] + k * kSegChunk;
+    int end = min(a.seg_start[seg + 1], beg + kSegChunk);
+    float acc[MAXC][VEC];
+#pragma unroll
+    for (int cc = 0; cc < MAXC; ++cc)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[cc][v] = 0.f;
+    accumulate_rows<VEC, MAXC>(a, beg, end, lane, acc);
+    float *dst = a.partials + (int64_t)c * d;
+#pragma unroll
+    for (int cc = 0; cc < MAXC; ++cc) {
+      int col = (cc * 32 + lane) * VEC;
+      if (col < d) st_vec<VEC>(dst + col, acc[cc]);
+    }
+  }
+}
+
+// Pass 3: one CTA per long segment: warp w sums partials w, w + 8, ...; the eight warp sums are
+// combined through shared memory in warp order, then warp 0 finishes the row.
+template <int VEC, int MAXC, bool UPDATE>
+__global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
+  extern __shared__ float red[];  // [8][d]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nlong = a.long_meta[0];
+  const int d = a.d;
+  for (int s = blockIdx.x; s < nlong; s += gridDim.x) {
+    int seg = a.long_seg[3 * s], first = a.long_seg[3 * s + 1], nch = a.long_seg[3 * s + 2];
+    float acc[MAXC][VEC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
+    for (int k = w; k < nch; k += 8) {
+      const float *src = a.partials + (int64_t)(first + k) * d;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         int col = (c * 32 + lane) * VEC;
         if (col < d) {
           float t[VEC];
-          ld_vec<VEC>(g + col, t);
+          ld_vec_rw<VEC>(src + col, t);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(sgn, t[v], acc[c][v]);
+          for (int v = 0; v < VEC; ++v) acc[c][v] += t[v];
         }
       }
     }
-    float n = (float)(end - beg);
+    __syncthreads();
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[c][v] /= n;  // the mean: skge/util.py:97-101
-    const ParamDesc &pd = a.pd[which];
-    if (UPDATE) {
-      row_update<VEC, MAXC>(pd.param + row * d, pd.p2 ? pd.p2 + row * d : nullptr, acc, d, lane, a.opt,
-                            a.lr, pd.post, pd.rparam);
-      if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
-    } else {
-      int64_t u = which ? seg - U0 : seg;
+    for (int c = 0; c < MAXC; ++c) {
+      int col = (c * 32 + lane) * VEC;
+      if (col < d) st_vec<VEC>(red + w * d + col, acc[c]);
+    }
+    __syncthreads();
+    if (w == 0) {
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         int col = (c * 32 + lane) * VEC;
         if (col < d) {
-          if (pd.rparam != 0.f) {
-            float x[VEC];
-            ld_vec<VEC>(pd.param + row * d + col, x);
+          for (int ww = 1; ww < 8; ++ww) {
+            float t[VEC];
+            ld_vec_rw<VEC>(red + ww * d + col, t);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[c][v] += pd.rparam * x[v];
+            for (int v = 0; v < VEC; ++v) acc[c][v] += t[v];
           }
-          st_vec<VEC>(pd.out_g + u * d + col, acc[c]);
         }
       }
-      if (lane == 0) pd.out_idx[u] = (int32_t)row;
+      int n = a.seg_start[seg + 1] - a.seg_start[seg];
+      finish_row<VEC, MAXC, UPDATE>(a, seg, a.seg_key[seg], n, lane, acc);
     }
   }
 }
@@ -274,6 +410,13 @@ template <int VEC, int MAXC>
 static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
   if (update) seg_reduce_kernel<VEC, MAXC, true><<<blocks, 256, 0, st>>>(a);
   else seg_reduce_kernel<VEC, MAXC, false><<<blocks, 256, 0, st>>>(a);
+  int cb = (a.long_chunk_cap + 7) / 8;
+  if (cb > kNumSMs * 8) cb = kNumSMs * 8;
+  seg_long_chunks_kernel<VEC, MAXC><<<cb, 256, 0, st>>>(a);
+  int sb = a.long_seg_cap < kNumSMs * 4 ? a.long_seg_cap : kNumSMs * 4;
+  size_t smem = (size_t)8 * a.d * sizeof(float);
+  if (update) seg_long_finish_kernel<VEC, MAXC, true><<<sb, 256, smem, st>>>(a);
+  else seg_long_finish_kernel<VEC, MAXC, false><<<sb, 256, smem, st>>>(a);
 }
 
 template <int VEC>
@@ -296,7 +439,19 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
   SegLists sl;
   int rc = seg_build(rm, flags, P, N, M, ar, st, &sl);
   if (rc) return rc;
+  int64_t L = (int64_t)rm.nroles * P;
   SegArgs a;
+  a.long_seg_cap = (int)long_seg_cap(L);
+  a.long_chunk_cap = (int)long_chunk_cap(L);
+  a.long_meta = ar.take<int32_t>(4);
+  a.long_seg = ar.take<int32_t>((size_t)a.long_seg_cap * 3);
+  a.long_work = ar.take<int32_t>((size_t)a.long_chunk_cap * 2);
+  a.partials = ar.take<float>((size_t)a.long_chunk_cap * d);
+  if (!ar.ok()) {
+    set_error("workspace too small: need %zu bytes, have %zu", ar.off, ar.cap);
+    return SKGE_EWORKSPACE;
+  }
+  SKGE_CUDA(cudaMemsetAsync(a.long_meta, 0, 16, st));
   a.seg_start = sl.seg_start;
   a.seg_key = sl.seg_key;
   a.vals = sl.vals;
@@ -314,7 +469,6 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
   a.opt = opt;
   a.lr = lr;
   a.counts = counts;
-  int64_t L = (int64_t)rm.nroles * P;
   int64_t maxseg = L < N + M ? L : N + M;
   int64_t blocks = (maxseg + 7) / 8;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;

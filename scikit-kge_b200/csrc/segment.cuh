@@ -30,7 +30,7 @@ struct ParamDesc {
   int32_t *out_idx;    // emit mode: [U]
 };
 
-size_t seg_workspace_bytes(int64_t L);
+size_t seg_workspace_bytes(int64_t L, int d);
 
 // Builds keys from `rm` (masked by flags, nullable), sorts, finds segments and
 // either emits (mean gradient, row id) per unique row (update == false) or

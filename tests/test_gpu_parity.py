@@ -266,6 +266,53 @@ def test_wn18_shaped_minibatch_against_oracle(kind, d, margin, l1):
     np.testing.assert_allclose(np.asarray(m.R), R, **PARAM_TOL)
 
 
+@pytest.mark.parametrize('kind,d', [('transe', 50), ('transe', 256), ('hole', 64), ('hole', 150)])
+def test_hot_rows_use_the_chunked_segment_reduction(kind, d):
+    """Rows with thousands of occurrences in one minibatch (a hub entity, a frequent
+    relation) go through the chunked two-level reduction; the mean must still match."""
+    import skge
+    from skge.param import SGD
+    N, M, P = 40, 2, 6000
+    rng = np.random.default_rng(d + 1)
+    E0 = (rng.normal(size=(N, d)) * 0.3).astype(np.float32).astype(np.float64)
+    R0 = (rng.normal(size=(M, d)) * 0.3).astype(np.float32).astype(np.float64)
+    if kind == 'transe':
+        E0 = orc.normalize(E0).astype(np.float32).astype(np.float64)
+    pos = np.stack([rng.integers(N, size=P), rng.integers(N, size=P), rng.integers(M, size=P)], 1)
+    pos[: P // 2, 0] = 7                      # hub subject: > 3000 occurrences
+    neg = pos.copy()
+    neg[0::2, 0] = rng.integers(N, size=P // 2)
+    neg[1::2, 1] = rng.integers(N, size=P // 2)
+    margin = 2.0 if kind == 'transe' else 0.2
+    if kind == 'transe':
+        m = skge.TransE((N, N, M), d)
+        ograds, info = orc.transe_pairwise_gradients(E0, R0, pos, neg, margin, True)
+    else:
+        m = skge.HolE((N, N, M), d, rparam=0.05)
+        ograds, info = orc.hole_pairwise_gradients(E0, R0, pos, neg, margin, 'sigmoid', 0.05)
+    m.E[...] = E0
+    m.R[...] = R0
+    trn = skge.PairwiseStochasticTrainer(m, nbatches=1, margin=margin, learning_rate=0.1, param_update=SGD)
+    assert not _near_margin(info, margin, 1e-5).any()
+    assert np.bincount(np.concatenate([pos[info['ind'], 0], neg[info['ind'], 0]])).max() > 1000
+    grads = m._pairwise_gradients(as_xys(pos), as_xys(neg))
+    assert m.nviolations == info['nviolations']
+    np.testing.assert_array_equal(np.asarray(grads['E'][1]), ograds['E'][1])
+    np.testing.assert_array_equal(np.asarray(grads['R'][1]), ograds['R'][1])
+    np.testing.assert_allclose(np.asarray(grads['E'][0]), ograds['E'][0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(np.asarray(grads['R'][0]), ograds['R'][0], rtol=1e-4, atol=1e-5)
+    # and the fused step (SGD: continuous in g)
+    trn._setup_fused()
+    from skge._modelutil import idx_tensor
+    m._fused_pair_step(trn._updaters, tuple(idx_tensor(pos[:, i]) for i in range(3)),
+                       tuple(idx_tensor(neg[:, i]) for i in range(3)), None, trn._counts, trn._nviol_dev)
+    E, R = E0.copy(), R0.copy()
+    orc.sgd_update(E, ograds['E'][0], ograds['E'][1], 0.1, 'normalize' if kind == 'transe' else 'normless1')
+    orc.sgd_update(R, ograds['R'][0], ograds['R'][1], 0.1, None)
+    np.testing.assert_allclose(np.asarray(m.E), E, **PARAM_TOL)
+    np.testing.assert_allclose(np.asarray(m.R), R, **PARAM_TOL)
+
+
 def test_rescal_wn18_shaped_minibatch_against_oracle():
     """Config 3: d = 100, 1414 positives + 2828 negatives, logistic loss, SGD."""
     import skge
