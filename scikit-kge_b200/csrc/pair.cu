@@ -182,6 +182,158 @@ __global__ void hole_pair_kernel(const float *__restrict__ E, const float *__res
   }
 }
 
+// ---------------------------------------------------------------------------
+// HolE for power-of-two d: the correlations go through radix-2 Stockham FFTs in shared
+// memory (what the reference does with numpy's FFT, skge/util.py:27,50), O(d log d)
+// instead of O(d^2) per correlation.  Per pair, three complex FFTs carry the six real
+// rows (s + i o, r + i r', s' + i o'); spectra are unpacked by Hermitian symmetry, the
+// six products formed, the raw scores read off by Parseval
+//     score = sum_k r_k ccorr(s,o)_k = (1/d) Re sum_f conj(S_f) O_f conj(R_f),
+// and, for violating pairs only, three inverse FFTs return the six gradient rows
+// (two real rows per complex transform).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // conj(a) * b
+  return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+
+// NF transforms of length N = 1 << LOGD, in[f][*] -> result returned in `in` or `out`
+// (the pointer to the buffer holding the result is returned).  tw[m] = exp(-2 pi i m / N).
+template <int LOGD, int NF, bool INVERSE>
+__device__ __forceinline__ float2 *fft_batch(float2 *in, float2 *out, const float2 *tw) {
+  constexpr int N = 1 << LOGD, H = N / 2;
+#pragma unroll 1
+  for (int s = 0; s < LOGD; ++s) {
+    const int Ns = 1 << s;
+    for (int b = threadIdx.x; b < NF * H; b += blockDim.x) {
+      const int f = b / H, j = b - f * H;
+      const int k = j & (Ns - 1);
+      float2 w = tw[k << (LOGD - 1 - s)];
+      if (INVERSE) w.y = -w.y;
+      const float2 u0 = in[f * N + j];
+      const float2 u1 = cmul(in[f * N + j + H], w);
+      const int j0 = (j << 1) - k;
+      out[f * N + j0] = make_float2(u0.x + u1.x, u0.y + u1.y);
+      out[f * N + j0 + Ns] = make_float2(u0.x - u1.x, u0.y - u1.y);
+    }
+    __syncthreads();
+    float2 *t = in; in = out; out = t;
+  }
+  return in;
+}
+
+template <int LOGD>
+__global__ void __launch_bounds__(256) hole_pair_fft_kernel(const float *__restrict__ E, const float *__restrict__ R,
+                                                            PairIdx ix, int64_t P, int af, float margin,
+                                                            float *__restrict__ pscores,
+                                                            float *__restrict__ nscores,
+                                                            uint8_t *__restrict__ flags, float *__restrict__ G,
+                                                            int32_t *__restrict__ counts,
+                                                            int64_t *__restrict__ nviol_accum) {
+  constexpr int N = 1 << LOGD;
+  extern __shared__ __align__(16) float2 fsm[];
+  float2 *bufA = fsm, *bufB = fsm + 3 * N, *tw = fsm + 6 * N;
+  float *red = reinterpret_cast<float *>(tw + N / 2);
+  for (int m = threadIdx.x; m < N / 2; m += blockDim.x) {
+    float sn, cs;
+    sincospif(-2.0f * (float)m / (float)N, &sn, &cs);
+    tw[m] = make_float2(cs, sn);
+  }
+  const float inv_n = 1.0f / (float)N;
+  int nv = 0;
+  for (int64_t i = blockIdx.x; i < P; i += gridDim.x) {
+    if (ix.valid && !ix.valid[i]) {
+      if (threadIdx.x == 0) {
+        flags[i] = 0;
+        if (pscores) pscores[i] = 0.f;
+        if (nscores) nscores[i] = 0.f;
+      }
+      continue;
+    }
+    __syncthreads();
+    {
+      const float *es = E + (int64_t)ix.sp[i] * N, *eo = E + (int64_t)ix.op[i] * N;
+      const float *rp = R + (int64_t)ix.pp[i] * N, *rn = R + (int64_t)ix.pn[i] * N;
+      const float *fs = E + (int64_t)ix.sn[i] * N, *fo = E + (int64_t)ix.on[i] * N;
+      for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        bufA[t] = make_float2(__ldg(es + t), __ldg(eo + t));
+        bufA[N + t] = make_float2(__ldg(rp + t), __ldg(rn + t));
+        bufA[2 * N + t] = make_float2(__ldg(fs + t), __ldg(fo + t));
+      }
+    }
+    __syncthreads();
+    float2 *X = fft_batch<LOGD, 3, false>(bufA, bufB, tw);
+    float2 *Y = X == bufA ? bufB : bufA;
+    // unpack the spectra, form the products, accumulate the Parseval sums
+    float accp = 0.f, accn = 0.f;
+    for (int f = threadIdx.x; f < N; f += blockDim.x) {
+      const int g = (N - f) & (N - 1);
+      const float2 z0 = X[f], z0c = X[g], z1 = X[N + f], z1c = X[N + g], z2 = X[2 * N + f], z2c = X[2 * N + g];
+      // x + i y  ->  Xf = (Z_f + conj Z_g) / 2,  Yf = (Z_f - conj Z_g) / (2 i)
+      const float2 S = make_float2(0.5f * (z0.x + z0c.x), 0.5f * (z0.y - z0c.y));
+      const float2 O = make_float2(0.5f * (z0.y + z0c.y), -0.5f * (z0.x - z0c.x));
+      const float2 Rp = make_float2(0.5f * (z1.x + z1c.x), 0.5f * (z1.y - z1c.y));
+      const float2 Rn = make_float2(0.5f * (z1.y + z1c.y), -0.5f * (z1.x - z1c.x));
+      const float2 S2 = make_float2(0.5f * (z2.x + z2c.x), 0.5f * (z2.y - z2c.y));
+      const float2 O2 = make_float2(0.5f * (z2.y + z2c.y), -0.5f * (z2.x - z2c.x));
+      const float2 A1 = cmulc(S, O), B1 = cmulc(S2, O2);      // ccorr(s, o)
+      const float2 A2 = cmulc(Rp, O), B2 = cmulc(Rn, O2);     // ccorr(r, o)
+      const float2 A3 = cmul(S, Rp), B3 = cmul(S2, Rn);       // cconv(s, r)
+      accp += A1.x * Rp.x + A1.y * Rp.y;                      // Re(A1 conj(R))
+      accn += B1.x * Rn.x + B1.y * Rn.y;
+      // two real sequences per inverse transform: U + i V
+      Y[f] = make_float2(A1.x - B1.y, A1.y + B1.x);
+      Y[N + f] = make_float2(A2.x - A3.y, A2.y + A3.x);
+      Y[2 * N + f] = make_float2(B2.x - B3.y, B2.y + B3.x);
+    }
+    const float raw_p = block_sum(accp, red) * inv_n;
+    const float raw_n = block_sum(accn, red) * inv_n;
+    const float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
+    const bool viol = fn + margin > fp;  // skge/hole.py:56
+    if (threadIdx.x == 0) {
+      flags[i] = viol;
+      if (pscores) pscores[i] = raw_p;
+      if (nscores) nscores[i] = raw_n;
+    }
+    if (!viol) continue;
+    ++nv;
+    float2 *other = Y == bufA ? bufB : bufA;
+    __syncthreads();
+    const float2 *Z = fft_batch<LOGD, 3, true>(Y, other, tw);
+    const float gp = -act_g_given_f(af, fp) * inv_n, gn = act_g_given_f(af, fn) * inv_n;  // hole.py:66-67
+    float *g = G + (int64_t)i * 6 * N;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      const float2 y0 = Z[t], y1 = Z[N + t], y2 = Z[2 * N + t];
+      g[0 * N + t] = gp * y1.x;   // gp ccorr(R[pp], E[op]) -> sp
+      g[1 * N + t] = gn * y2.x;   // gn ccorr(R[pn], E[on]) -> sn
+      g[2 * N + t] = gp * y1.y;   // gp cconv(E[sp], R[pp]) -> op
+      g[3 * N + t] = gn * y2.y;   // gn cconv(E[sn], R[pn]) -> on
+      g[4 * N + t] = gp * y0.x;   // gp ccorr(E[sp], E[op]) -> pp
+      g[5 * N + t] = gn * y0.y;   // gn ccorr(E[sn], E[on]) -> pn
+    }
+  }
+  if (threadIdx.x == 0 && nv) {
+    atomicAdd(counts, nv);
+    if (nviol_accum) atomicAdd(reinterpret_cast<unsigned long long *>(nviol_accum), (unsigned long long)nv);
+  }
+}
+
+template <int LOGD>
+static int launch_hole_fft(const float *E, const float *R, const PairIdx &ix, int64_t P, int af, float margin,
+                           float *pscores, float *nscores, uint8_t *flags, float *G, int32_t *counts,
+                           int64_t *nviol_accum, cudaStream_t st) {
+  constexpr int N = 1 << LOGD;
+  size_t smem = (size_t)(6 * N + N / 2) * sizeof(float2) + 40 * sizeof(float);
+  SKGE_CUDA(cudaFuncSetAttribute(hole_pair_fft_kernel<LOGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int threads = N >= 512 ? 256 : 128;
+  int64_t blocks = P > kNumSMs * 32 ? kNumSMs * 32 : P;
+  hole_pair_fft_kernel<LOGD><<<(int)blocks, threads, smem, st>>>(E, R, ix, P, af, margin, pscores, nscores, flags, G,
+                                                               counts, nviol_accum);
+  return 0;
+}
+
 static int pair_block_threads(int d) {
   int t = (d + 31) / 32 * 32;
   return t < 64 ? 64 : t;
@@ -238,12 +390,24 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
     }
   } else {
     SKGE_REQUIRE(d <= 1024, "HolE pair kernel supports d <= 1024");
+    bool fft_done = true;
+    switch (d) {  // power-of-two d: shared-memory FFT path
+      case 32: if (int rc = launch_hole_fft<5>(E, R, ix, P, l1_or_af, margin, pscores, nscores, flags, G, counts, nviol_accum, st)) return rc; break;
+      case 64: if (int rc = launch_hole_fft<6>(E, R, ix, P, l1_or_af, margin, pscores, nscores, flags, G, counts, nviol_accum, st)) return rc; break;
+      case 128: if (int rc = launch_hole_fft<7>(E, R, ix, P, l1_or_af, margin, pscores, nscores, flags, G, counts, nviol_accum, st)) return rc; break;
+      case 256: if (int rc = launch_hole_fft<8>(E, R, ix, P, l1_or_af, margin, pscores, nscores, flags, G, counts, nviol_accum, st)) return rc; break;
+      case 512: if (int rc = launch_hole_fft<9>(E, R, ix, P, l1_or_af, margin, pscores, nscores, flags, G, counts, nviol_accum, st)) return rc; break;
+      case 1024: if (int rc = launch_hole_fft<10>(E, R, ix, P, l1_or_af, margin, pscores, nscores, flags, G, counts, nviol_accum, st)) return rc; break;
+      default: fft_done = false;
+    }
+    if (!fft_done) {
     size_t smem = (12 * (size_t)d + 40) * sizeof(float);
     SKGE_CUDA(cudaFuncSetAttribute(hole_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = P > kNumSMs * 16 ? kNumSMs * 16 : P;
     hole_pair_kernel<<<(int)blocks, pair_block_threads(d), smem, st>>>(E, R, ix, P, d, l1_or_af, margin,
                                                                       pscores, nscores, flags, G, counts,
                                                                       nviol_accum);
+    }
   }
   SKGE_LAUNCH_CHECK();
 
