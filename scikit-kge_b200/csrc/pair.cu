@@ -199,24 +199,55 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // conj(a) * b
   return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
 
-// NF transforms of length N = 1 << LOGD, in[f][*] -> result returned in `in` or `out`
-// (the pointer to the buffer holding the result is returned).  tw[m] = exp(-2 pi i m / N).
+// NF transforms of length N = 1 << LOGD by a Stockham autosort FFT: radix-4 stages (plus one
+// leading radix-2 stage when LOGD is odd), ping-ponging between `in` and `out`; returns the
+// buffer that holds the result.  tw[m] = exp(-2 pi i m / N), m < N/2.  One butterfly index
+// per thread and stage is shared by the NF transforms (same twiddles, same addresses).
+__device__ __forceinline__ float2 tw_at(const float2 *tw, int m, int half) {  // m < N
+  float2 w = tw[m & (half - 1)];
+  return m >= half ? make_float2(-w.x, -w.y) : w;
+}
+
 template <int LOGD, int NF, bool INVERSE>
 __device__ __forceinline__ float2 *fft_batch(float2 *in, float2 *out, const float2 *tw) {
-  constexpr int N = 1 << LOGD, H = N / 2;
+  constexpr int N = 1 << LOGD, H = N / 2, Qn = N / 4;
+  int Ns = 1;
+  if (LOGD & 1) {  // radix-2 stage with Ns = 1: no twiddles
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float2 u0 = in[f * N + j], u1 = in[f * N + j + H];
+        out[f * N + 2 * j] = make_float2(u0.x + u1.x, u0.y + u1.y);
+        out[f * N + 2 * j + 1] = make_float2(u0.x - u1.x, u0.y - u1.y);
+      }
+    }
+    __syncthreads();
+    float2 *t = in; in = out; out = t;
+    Ns = 2;
+  }
 #pragma unroll 1
-  for (int s = 0; s < LOGD; ++s) {
-    const int Ns = 1 << s;
-    for (int b = threadIdx.x; b < NF * H; b += blockDim.x) {
-      const int f = b / H, j = b - f * H;
+  for (; Ns < N; Ns <<= 2) {
+    const int tstep = N / (4 * Ns);  // twiddle index of exp(-2 pi i k / (4 Ns)) is k * tstep
+    for (int j = threadIdx.x; j < Qn; j += blockDim.x) {
       const int k = j & (Ns - 1);
-      float2 w = tw[k << (LOGD - 1 - s)];
-      if (INVERSE) w.y = -w.y;
-      const float2 u0 = in[f * N + j];
-      const float2 u1 = cmul(in[f * N + j + H], w);
-      const int j0 = (j << 1) - k;
-      out[f * N + j0] = make_float2(u0.x + u1.x, u0.y + u1.y);
-      out[f * N + j0 + Ns] = make_float2(u0.x - u1.x, u0.y - u1.y);
+      const int j0 = ((j - k) << 2) + k;
+      float2 w1 = tw_at(tw, k * tstep, H), w2 = tw_at(tw, 2 * k * tstep, H), w3 = tw_at(tw, 3 * k * tstep, H);
+      if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float2 v0 = in[f * N + j];
+        const float2 v1 = cmul(in[f * N + j + Qn], w1);
+        const float2 v2 = cmul(in[f * N + j + 2 * Qn], w2);
+        const float2 v3 = cmul(in[f * N + j + 3 * Qn], w3);
+        const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+        const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+        // forward: y1 = d02 - i d13, y3 = d02 + i d13 ; inverse: the other way round
+        const float2 jd = INVERSE ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);
+        out[f * N + j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+        out[f * N + j0 + Ns] = make_float2(d02.x + jd.x, d02.y + jd.y);
+        out[f * N + j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+        out[f * N + j0 + 3 * Ns] = make_float2(d02.x - jd.x, d02.y - jd.y);
+      }
     }
     __syncthreads();
     float2 *t = in; in = out; out = t;
@@ -327,7 +358,7 @@ static int launch_hole_fft(const float *E, const float *R, const PairIdx &ix, in
   constexpr int N = 1 << LOGD;
   size_t smem = (size_t)(6 * N + N / 2) * sizeof(float2) + 40 * sizeof(float);
   SKGE_CUDA(cudaFuncSetAttribute(hole_pair_fft_kernel<LOGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int threads = N >= 512 ? 256 : 128;
+  int threads = N / 4 < 32 ? 32 : (N / 4 > 256 ? 256 : N / 4);  // one radix-4 butterfly index per thread
   int64_t blocks = P > kNumSMs * 32 ? kNumSMs * 32 : P;
   hole_pair_fft_kernel<LOGD><<<(int)blocks, threads, smem, st>>>(E, R, ix, P, af, margin, pscores, nscores, flags, G,
                                                                counts, nviol_accum);

@@ -170,3 +170,37 @@ def test_model_pickle_round_trip(tmp_path):
     assert m2.E.post is m.E.post
     s = m2._scores([0, 1], [0, 1], [2, 3])
     np.testing.assert_allclose(s, m._scores([0, 1], [0, 1], [2, 3]))
+
+
+def test_cli_experiment_flow(tmp_path, monkeypatch):
+    """run_transe / run_hole command lines of the reference (README.md:4, run_*_wn18.sh) with the
+    non-trident loader: epoch log lines, VALID/TEST ranking lines, best-model pickle at --fout."""
+    import pickle
+    from skge.run_transe import ExpTransE
+    from skge.run_hole import ExpHolE
+    from skge.run_rescal import ExpRESCAL
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(0)
+    tr = np.unique(np.stack([rng.integers(120, size=2500), rng.integers(120, size=2500), rng.integers(3, size=2500)], 1),
+                   axis=0)
+    np.savez(tmp_path / 'toy.npz', train=tr)
+    fout = str(tmp_path / 'best.pkl')
+    ExpTransE().run(['--fin', str(tmp_path / 'toy.npz'), '--test-all', '2', '--nb', '5', '--me', '4',
+                     '--margin', '2.0', '--lr', '0.1', '--ncomp', '16', '--fout', fout,
+                     '--fgrad', str(tmp_path / 'grad.csv')])
+    out = (tmp_path / 'toy-full-kognac-epochs-4-eval-2-margin-2.0.out').read_text()
+    assert out.count('violations =') == 5          # 4 epochs + the final with_eval call
+    assert 'VALID: MRR =' in out and 'TEST: MRR =' in out and 'Time to fit model' in out
+    st = pickle.load(open(fout, 'rb'))
+    assert set(st) == {'model', 'pos test', 'fpos test', 'pos valid', 'fpos valid', 'exectimes'}
+    assert st['model'].E.shape == (120, 16) and len(st['exectimes']) >= 4
+    assert (tmp_path / 'grad.csv').read_text().startswith('Entity,Degree,#(violations),#(updates)')
+    ExpHolE().run(['--fin', str(tmp_path / 'toy.npz'), '--test-all', '3', '--nb', '5', '--me', '3', '--margin', '0.2',
+                   '--lr', '0.1', '--ncomp', '16', '--sampler', 'lcwa'])
+    ExpHolE().run(['--fin', str(tmp_path / 'toy.npz'), '--test-all', '3', '--nb', '5', '--me', '2', '--lr', '0.1',
+                   '--ncomp', '8', '--no-pairwise'])
+    ExpRESCAL().run(['--fin', str(tmp_path / 'toy.npz'), '--test-all', '2', '--nb', '5', '--me', '2', '--lr', '0.1',
+                     '--ncomp', '8'])
+    with pytest.raises(ValueError, match='Unknown sampler'):
+        ExpTransE().run(['--fin', str(tmp_path / 'toy.npz'), '--nb', '5', '--me', '1', '--margin', '1', '--lr', '0.1',
+                         '--ncomp', '4', '--sampler', 'bogus'])
