@@ -384,7 +384,7 @@ def bench_train(args, mdl, N, M, d, model, pk):
         times.append(time.perf_counter() - trn.epoch_start)
         return True
 
-    trn = skge.PairwiseStochasticTrainer(mdl, nbatches=nb, margin=margin, max_epochs=3, learning_rate=0.1,
+    trn = skge.PairwiseStochasticTrainer(mdl, nbatches=nb, margin=margin, max_epochs=5, learning_rate=0.1,
                                          samplef=smp.sample, param_update=AdaGrad, post_epoch=[cb])
     mdl.track_counters = False
     l0 = kernels.LAUNCHES['n']
@@ -397,6 +397,7 @@ def bench_train(args, mdl, N, M, d, model, pk):
             'epochs_timed': len(times) - 1, 'model': model, 'd': d, 'batch_positives': T // nb,
             'pairs_per_batch': P, 'nbatches': nb, 'triples': T, 'violations_last_epoch': trn.nviolations,
             'gpu_launches': launches, 'sampler': 'on-device RandomModeSampler(1, [0,1])', 'optimizer': 'AdaGrad',
+            'epoch_times_s': [round(t, 5) for t in times],
             'note': 'steady-state epochs through PairwiseStochasticTrainer.fit (first epoch excluded)'}
 
 

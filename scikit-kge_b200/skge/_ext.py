@@ -107,7 +107,9 @@ def ptr(t):
     """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), 'expected a contiguous CUDA tensor'
+    if not t.is_cuda:
+        raise RuntimeError('skge (B200 build) computes on CUDA tensors only; there is no CPU fallback')
+    assert t.is_contiguous(), 'expected a contiguous CUDA tensor'
     return t.data_ptr()
 
 
@@ -116,6 +118,10 @@ def stream():
 
 
 def device():
+    """Where parameters live.  Without a CUDA device tensors can still be *held* (host
+    storage for pickling / inspection); every compute call goes through lib(), which raises."""
+    if not torch.cuda.is_available():
+        return torch.device('cpu')
     return torch.device('cuda', torch.cuda.current_device())
 
 

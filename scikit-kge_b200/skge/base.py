@@ -61,22 +61,69 @@ class Model(object):
     def __getstate__(self):
         return {'hyperparams': self.hyperparams, 'params': self.params}
 
+    _posts = {}             # param id -> post-hook, for pickles written by the reference (which lose it)
+
     def __setstate__(self, st):
         self.params = {}
         self.hyperparams = {}
         for pid, p in st['params'].items():
+            if not isinstance(p, Parameter):      # an ndarray from a reference-format pickle
+                p = Parameter.from_reference(p)
+                p.name = p.name or pid
+                p.post = p.post or self._posts.get(pid)
             self.add_param(pid, None, None, value=p)
         for pid, p in st['hyperparams'].items():
             self.add_hyperparam(pid, p)
 
-    def save(self, fname, protocol=pickle.HIGHEST_PROTOCOL):
+    def save(self, fname, protocol=2):
+        """Pickle in the REFERENCE's format (skge/base.py:1170-1187): the stream names the
+        same classes (skge.hole.HolE, skge.param.Parameter, ...) and stores the parameters as
+        float64 ndarray payloads, so the reference -- and its analysis scripts -- can load
+        a model trained here, and ``Model.load`` here reads models written by the reference."""
         with open(fname, 'wb') as fout:
-            pickle.dump(self, fout, protocol=protocol)
+            fout.write(dumps_reference(self, protocol))
 
     @staticmethod
     def load(fname):
         with open(fname, 'rb') as fin:
-            return pickle.load(fin)
+            return loads_reference(fin.read())
+
+
+class _RefPickler(pickle.Pickler):
+    """Writes our Parameter objects as the reference's ndarray-subclass payload."""
+
+    def reducer_override(self, obj):
+        if isinstance(obj, Parameter):
+            a = np.ascontiguousarray(np.asarray(obj, dtype=np.float64))
+            fn, args, state = a.__reduce__()      # (_reconstruct, (ndarray, (0,), b'b'), state)
+            return fn, (Parameter,) + tuple(args[1:]), state
+        return NotImplemented
+
+
+class _RefUnpickler(pickle.Unpickler):
+
+    def find_class(self, module, name):
+        if module == 'skge.param' and name == 'Parameter':
+            from .param import RefParameter
+            return RefParameter
+        return super(_RefUnpickler, self).find_class(module, name)
+
+
+def dumps_reference(obj, protocol=2):
+    """Reference-compatible pickle bytes (protocol <= 3, so module names are plain text)."""
+    import io
+    if protocol > 3:
+        protocol = 3
+    buf = io.BytesIO()
+    _RefPickler(buf, protocol=protocol).dump(obj)
+    # numpy >= 2 names its reconstructor numpy._core.multiarray; older numpy (what a
+    # reference installation may run) only knows numpy.core.multiarray, which both resolve.
+    return buf.getvalue().replace(b'cnumpy._core.multiarray\n', b'cnumpy.core.multiarray\n')
+
+
+def loads_reference(data):
+    import io
+    return _RefUnpickler(io.BytesIO(data)).load()
 
 
 def _triples_to_device(xs):
@@ -384,4 +431,5 @@ class PairwiseStochasticTrainer(StochasticTrainer):
 
 
 # the evaluator and metric helpers live in skge/base.py in the reference
-from .ranking import (FilteredRankingEval, ranking_scores, compute_scores, _print_pos)  # noqa: E402,F401
+from .ranking import (FilteredRankingEval, LinkPredictionEval, ranking_scores, compute_scores,  # noqa: E402,F401
+                      _print_pos)

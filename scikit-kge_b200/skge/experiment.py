@@ -143,8 +143,9 @@ class Experiment(object):
                 if self.args.fout is not None:
                     st = {'model': trn.model, 'pos test': pos_t, 'fpos test': fpos_t, 'pos valid': pos_v,
                           'fpos valid': fpos_v, 'exectimes': self.exectimes}
+                    from .base import dumps_reference
                     with open(self.args.fout, 'wb') as fout:
-                        pickle.dump(st, fout, protocol=2)
+                        fout.write(dumps_reference(st, 2))      # loadable by the reference too
             self.fresult.flush()
         return True
 

@@ -16,6 +16,7 @@ class HolE(Model):
     circular correlations run in shared memory instead of numpy's FFT.
     """
 
+    _posts = {'E': normless1}
     model_code = _ext.MODEL_HOLE
 
     def __init__(self, *args, **kwargs):

@@ -222,6 +222,27 @@ class Parameter(object):
         for a in ('_update_counts', '_violations', '_neighbours'):
             setattr(self, a, torch.zeros(n, dtype=torch.int32, device=self.data.device))
 
+    @classmethod
+    def from_reference(cls, arr):
+        """Wrap a reference-style Parameter (an ndarray subclass instance with ``name`` /
+        ``post`` attributes, as found in pickles written by the reference)."""
+        post = getattr(arr, 'post', None)
+        post = {'normalize': normalize, 'normless1': normless1}.get(getattr(post, '__name__', None))
+        return cls(arr.shape, 'nunif', name=getattr(arr, 'name', None), post=post,
+                   value=np.asarray(arr, dtype=np.float64))
+
+
+
+class RefParameter(np.ndarray):
+    """Stand-in for the reference's ``skge.param.Parameter`` (an ndarray subclass,
+    skge/param.py:57-105), used only to read reference-written pickles."""
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.name = getattr(obj, 'name', None)
+        self.post = getattr(obj, 'post', None)
+
 
 # ---------------------------------------------------------------------------
 # post-hooks (skge/param.py:161-174)
@@ -242,6 +263,9 @@ def _rows_post(M, idx, code):
 def normalize(M, idx=None):
     """Unit-L2 rows (all rows, or rows ``idx`` in place).  skge/param.py:161-167."""
     if isinstance(M, Parameter):
+        if idx is None:     # whole table, at creation: plain tensor arithmetic
+            M.data.div_(torch.linalg.vector_norm(M.data, dim=1, keepdim=True))
+            return M
         return _rows_post(M, idx, _ext.POST_NORMALIZE)
     if idx is None:
         return M / np.sqrt(np.sum(M ** 2, axis=1))[:, np.newaxis]

@@ -456,3 +456,19 @@ def ranking_scores(fresult, pos, fpos, epoch, txt):
     fhpos = [p for k in fpos.keys() for p in fpos[k]['head']]
     ftpos = [p for k in fpos.keys() for p in fpos[k]['tail']]
     return _print_pos(fresult, np.array(hpos + tpos), np.array(fhpos + ftpos), epoch, txt)
+
+
+class LinkPredictionEval(object):
+    """Area under the precision-recall and ROC curves of ``_scores`` on labelled triples
+    (skge/base.py:1034-1047; the metrics come from scikit-learn exactly as in the reference,
+    the scores from the device)."""
+
+    def __init__(self, xs, ys):
+        ss, os_, ps = list(zip(*xs))
+        self.ss, self.ps, self.os, self.ys = list(ss), list(ps), list(os_), ys
+
+    def scores(self, mdl):
+        from sklearn.metrics import precision_recall_curve, auc, roc_auc_score
+        scores = mdl._scores(self.ss, self.ps, self.os)
+        pr, rc, _ = precision_recall_curve(self.ys, scores)
+        return auc(rc, pr), roc_auc_score(self.ys, scores)

@@ -19,6 +19,7 @@ class TransE(Model):
     distance when l1=False (skge/transe.py:25-46).
     """
 
+    _posts = {'E': normalize}
     model_code = _ext.MODEL_TRANSE
 
     def __init__(self, *args, **kwargs):

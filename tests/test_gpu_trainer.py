@@ -204,3 +204,17 @@ def test_cli_experiment_flow(tmp_path, monkeypatch):
     with pytest.raises(ValueError, match='Unknown sampler'):
         ExpTransE().run(['--fin', str(tmp_path / 'toy.npz'), '--nb', '5', '--me', '1', '--margin', '1', '--lr', '0.1',
                          '--ncomp', '4', '--sampler', 'bogus'])
+
+
+def test_link_prediction_eval_auc():
+    """skge/base.py:1034-1047."""
+    import skge
+    from skge.base import LinkPredictionEval
+    from sklearn.metrics import roc_auc_score
+    N, M, xs = _graph(seed=9, T=400)
+    m = skge.HolE((N, N, M), 16)
+    rng = np.random.default_rng(0)
+    ys = np.where(rng.random(len(xs)) < 0.5, 1, -1)
+    pr_auc, roc = LinkPredictionEval(xs, ys).scores(m)
+    s, o, p = zip(*xs)
+    assert roc == pytest.approx(roc_auc_score(ys, m._scores(s, p, o))) and 0.0 <= pr_auc <= 1.0
