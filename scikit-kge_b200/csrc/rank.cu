@@ -128,6 +128,97 @@ __global__ void make_queries_kernel(int model, const float *__restrict__ E, cons
   }
 }
 
+// HolE query vectors for d % 8 == 0, d <= 256: one WARP per query, lane l owns outputs
+// k = 8l .. 8l+7 (lanes beyond d/8 idle).  The correlation slides a 15-wide register window
+// over a doubled copy of the given entity row in shared memory: per block of 8 inner steps a
+// lane issues 8 + 8 shared loads for 64 DFMAs, so the loop runs at the FP64 pipe's pace.
+//   tail: q_k = cconv(r, s)_k = sum_i r_i s_{(k-i) mod d}     head: q_k = ccorr(r, o)_k = sum_i r_i o_{(i+k) mod d}
+__global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__restrict__ E,
+                                                                const float *__restrict__ R,
+                                                                const uint8_t *__restrict__ kind,
+                                                                const int32_t *__restrict__ given,
+                                                                const int32_t *__restrict__ rel,
+                                                                const int32_t *__restrict__ target, int64_t Q,
+                                                                int d, float enorm_max, float coarse_rel,
+                                                                double *__restrict__ q64, float *__restrict__ q32,
+                                                                double *__restrict__ tscore, float *__restrict__ eps,
+                                                                float *__restrict__ qnorm) {
+  extern __shared__ double smd[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double *g2 = smd + (size_t)wid * 3 * d;  // [2d] doubled given row
+  double *rv = g2 + 2 * d;                 // [d] relation row
+  const int k0 = lane * 8;
+  for (int64_t qi = (int64_t)blockIdx.x * nw + wid; qi < Q; qi += (int64_t)gridDim.x * nw) {
+    const int head = kind[qi];
+    const float *eg = E + (int64_t)given[qi] * d, *rp = R + (int64_t)rel[qi] * d;
+    __syncwarp();
+    for (int i = lane; i < d; i += 32) {
+      double v = (double)__ldg(eg + i);
+      g2[i] = v;
+      g2[i + d] = v;
+      rv[i] = (double)__ldg(rp + i);
+    }
+    __syncwarp();
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double l1 = 0.0, l2 = 0.0;
+    if (k0 < d) {
+      double w[15];
+      if (head) {
+        // acc[m] += r[i] * g2[i + k0 + m]; block b covers i = 8b..8b+7: window v[t] = g2[8b + k0 + t], t < 15
+#pragma unroll
+        for (int t = 0; t < 7; ++t) w[t] = g2[k0 + t];
+        for (int b = 0; b < d / 8; ++b) {
+#pragma unroll
+          for (int t = 7; t < 15; ++t) w[t] = g2[8 * b + k0 + t];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double r = rv[8 * b + u];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[m] = fma(r, w[u + m], acc[m]);
+          }
+#pragma unroll
+          for (int t = 0; t < 7; ++t) w[t] = w[t + 8];
+        }
+      } else {
+        // acc[m] += r[i] * g2[d + k0 + m - i]; window v[t] = g2[d + k0 - 8b - 7 + t], t < 15
+#pragma unroll
+        for (int t = 8; t < 15; ++t) w[t] = g2[d + k0 - 7 + t];
+        for (int b = 0; b < d / 8; ++b) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) w[t] = g2[d + k0 - 8 * b - 7 + t];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double r = rv[8 * b + u];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[m] = fma(r, w[m - u + 7], acc[m]);
+          }
+#pragma unroll
+          for (int t = 14; t >= 8; --t) w[t] = w[t - 8];
+        }
+      }
+      double *qo = q64 + qi * d + k0;
+      float *qf = q32 + qi * d + k0;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        qo[m] = acc[m];
+        qf[m] = (float)acc[m];
+        l1 += fabs(acc[m]);
+        l2 += acc[m] * acc[m];
+      }
+    }
+    l1 = warp_sum(l1);
+    l2 = warp_sum(l2);
+    __syncwarp();  // q64 row written by this warp is read back below
+    double t = score64_warp(SKGE_RANK_DOT, q64 + qi * d, E + (int64_t)target[qi] * d, d, lane);
+    if (lane == 0) {
+      tscore[qi] = t;
+      float n2 = (float)sqrt(l2);
+      qnorm[qi] = n2;
+      eps[qi] = coarse_rel * n2 * enorm_max;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // coarse sweep on the FP32 pipes
 // ---------------------------------------------------------------------------
@@ -348,6 +439,16 @@ int skge_rank_make_queries(int model, const float *E, const float *RW, const uin
   SKGE_REQUIRE(model >= SKGE_MODEL_TRANSE && model <= SKGE_MODEL_RESCAL && d > 0 && d <= 2048 && Q >= 0,
                "bad sizes");
   if (Q == 0) return 0;
+  if (model == SKGE_MODEL_HOLE && d % 8 == 0 && d <= 256) {
+    size_t smem = (size_t)8 * 3 * d * sizeof(double);
+    SKGE_CUDA(cudaFuncSetAttribute(make_queries_hole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (Q + 7) / 8;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    make_queries_hole_kernel<<<(int)blocks, 256, smem, as_stream(stream)>>>(
+        E, RW, kind, given, rel, target, Q, d, enorm_max, coarse_rel, q64, q32, tscore, eps, qnorm);
+    SKGE_LAUNCH_CHECK();
+    return 0;
+  }
   int threads = (d + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
   int64_t blocks = Q > kNumSMs * 16 ? kNumSMs * 16 : Q;

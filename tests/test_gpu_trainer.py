@@ -191,7 +191,8 @@ def test_cli_experiment_flow(tmp_path, monkeypatch):
     out = (tmp_path / 'toy-full-kognac-epochs-4-eval-2-margin-2.0.out').read_text()
     assert out.count('violations =') == 5          # 4 epochs + the final with_eval call
     assert 'VALID: MRR =' in out and 'TEST: MRR =' in out and 'Time to fit model' in out
-    st = pickle.load(open(fout, 'rb'))
+    from skge.base import loads_reference       # reference-format stream (see Model.save)
+    st = loads_reference(open(fout, 'rb').read())
     assert set(st) == {'model', 'pos test', 'fpos test', 'pos valid', 'fpos valid', 'exectimes'}
     assert st['model'].E.shape == (120, 16) and len(st['exectimes']) >= 4
     assert (tmp_path / 'grad.csv').read_text().startswith('Entity,Degree,#(violations),#(updates)')
