@@ -116,6 +116,23 @@ SKGE_API int skge_hole_pair_step(float *E, float *R, float *p2E, float *p2R, con
                         int32_t *upd_counts_E, int32_t *upd_counts_R, void *ws, size_t ws_bytes,
                         skge_stream_t stream);
 
+/*
+ * HolE in the frequency domain (fused path, power-of-two d in [32, 1024]).  Ehat / Rhat hold
+ * the packed spectra of the rows of E / R (d floats per row: slot 0 = (X_0, X_{d/2}), slot f =
+ * (Re X_f, Im X_f)); skge_hole_spectra fills them, skge_hole_pair_step_spectral is
+ * skge_hole_pair_step with every per-pair transform removed: scores by Parseval, gradient rows
+ * summed as spectra, one inverse + one forward transform per UPDATED row, which also keeps
+ * Ehat / Rhat current (replaces the numpy.fft calls of skge/util.py:27,50 on this path).
+ */
+SKGE_API int skge_hole_spectra(const float *X, int64_t rows, int d, float *Xhat, skge_stream_t stream);
+SKGE_API int skge_hole_pair_step_spectral(float *E, float *R, float *Ehat, float *Rhat, float *p2E, float *p2R,
+                                 const int32_t *sp, const int32_t *op, const int32_t *pp,
+                                 const int32_t *sn, const int32_t *on, const int32_t *pn,
+                                 const uint8_t *valid, int64_t P, int64_t N, int64_t M, int d, int af,
+                                 float margin, float rparam, int opt, float lr, int postE, int postR,
+                                 int32_t *counts, int64_t *nviol_accum, int32_t *upd_counts_E,
+                                 int32_t *upd_counts_R, void *ws, size_t ws_bytes, skge_stream_t stream);
+
 /* ---- logistic minibatch: Model._gradients + _batch_step ---------------- */
 /*
  * n labelled examples (s, o, p, y = +-1).  loss (device double, nullable) is

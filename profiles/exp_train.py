@@ -21,6 +21,8 @@ def main(model='hole', N=1000000, M=1000, d=256, B=500000, steps=3):
                                          learning_rate=0.1, samplef=smp.sample, param_update=AdaGrad)
     trn._setup_fused()
     smp.ensure_device()
+    if hasattr(m, '_prepare_fused') and os.environ.get('SKGE_SPECTRAL', '1') == '1':
+        m._prepare_fused()      # HolE: frequency-domain training state
     perm = torch.randperm(len(xs), device=dev).to(torch.int32)
     for it in range(steps + 1):
         batch = perm[(it % 4) * B:(it % 4 + 1) * B]

@@ -3,6 +3,7 @@
 //   HolE._pairwise_gradients   : skge/hole.py:44-100
 //   PairwiseStochasticTrainer._process_batch / _batch_step : skge/base.py:1394-1427, 1306-1316
 #include "common.cuh"
+#include "fft.cuh"
 #include "hole_math.cuh"
 #include "segment.cuh"
 
@@ -192,22 +193,10 @@ __global__ void hole_pair_kernel(const float *__restrict__ E, const float *__res
 // and, for violating pairs only, three inverse FFTs return the six gradient rows
 // (two real rows per complex transform).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // conj(a) * b
-  return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
-}
-
 // NF transforms of length N = 1 << LOGD by a Stockham autosort FFT: radix-4 stages (plus one
 // leading radix-2 stage when LOGD is odd), ping-ponging between `in` and `out`; returns the
 // buffer that holds the result.  tw[m] = exp(-2 pi i m / N), m < N/2.  One butterfly index
 // per thread and stage is shared by the NF transforms (same twiddles, same addresses).
-__device__ __forceinline__ float2 tw_at(const float2 *tw, int m, int half) {  // m < N
-  float2 w = tw[m & (half - 1)];
-  return m >= half ? make_float2(-w.x, -w.y) : w;
-}
-
 template <int LOGD, int NF, bool INVERSE>
 __device__ __forceinline__ float2 *fft_batch(float2 *in, float2 *out, const float2 *tw) {
   constexpr int N = 1 << LOGD, H = N / 2, Qn = N / 4;
@@ -365,6 +354,103 @@ static int launch_hole_fft(const float *E, const float *R, const PairIdx &ix, in
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// HolE in the frequency domain (fused training path, power-of-two d).  The trainer keeps
+// packed spectra Ehat / Rhat of the parameter tables (csrc/fft.cuh) next to the tables
+// themselves, so a pair needs NO transform at all: one warp streams the six spectral rows,
+// forms the slot-wise products, reads both scores off by Parseval and, for violating pairs,
+// writes the six gradient rows AS SPECTRA.  The segmented reduction sums spectra (the mean is
+// linear), and only once per unique row goes back to the time domain, updates the row and
+// refreshes its spectrum (segment.cu, spectral mode): 2 transforms per touched row instead
+// of 6 per pair.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hole_spectra_kernel(const float *__restrict__ X, int64_t rows, int d,
+                                                           int logd, float *__restrict__ Xhat) {
+  extern __shared__ __align__(16) float sm_spec[];
+  float2 *tw = reinterpret_cast<float2 *>(sm_spec);
+  fill_twiddles(tw, d, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float2 *b0 = tw + d / 2 + (size_t)w * 2 * d, *b1 = b0 + d;
+  for (int64_t r = (int64_t)blockIdx.x * nw + w; r < rows; r += (int64_t)gridDim.x * nw) {
+    const float *x = X + r * d;
+    const float2 *S = warp_rfft([x](int i) { return __ldg(x + i); }, b0, b1, tw, logd, lane);
+    float *h = Xhat + r * d;
+    for (int p = lane; p < d; p += 32) h[p] = packed_from_full(S, p, d / 2);
+  }
+}
+
+__global__ void __launch_bounds__(256) hole_pair_spec_kernel(const float *__restrict__ Ehat,
+                                                             const float *__restrict__ Rhat, PairIdx ix, int64_t P,
+                                                             int d, int af, float margin,
+                                                             uint8_t *__restrict__ flags, float *__restrict__ G,
+                                                             int32_t *__restrict__ counts,
+                                                             int64_t *__restrict__ nviol_accum) {
+  const int lane = threadIdx.x & 31;
+  const int h = d / 2;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv_d = 1.0f / (float)d;
+  int nv = 0;
+  for (int64_t i = warp; i < P; i += nwarps) {
+    if (ix.valid && !ix.valid[i]) {
+      if (lane == 0) flags[i] = 0;
+      continue;
+    }
+    const float2 *S = reinterpret_cast<const float2 *>(Ehat + (int64_t)ix.sp[i] * d);
+    const float2 *O = reinterpret_cast<const float2 *>(Ehat + (int64_t)ix.op[i] * d);
+    const float2 *Rp = reinterpret_cast<const float2 *>(Rhat + (int64_t)ix.pp[i] * d);
+    const float2 *S2 = reinterpret_cast<const float2 *>(Ehat + (int64_t)ix.sn[i] * d);
+    const float2 *O2 = reinterpret_cast<const float2 *>(Ehat + (int64_t)ix.on[i] * d);
+    const float2 *Rn = reinterpret_cast<const float2 *>(Rhat + (int64_t)ix.pn[i] * d);
+    float accp = 0.f, accn = 0.f;
+    for (int f = lane; f < h; f += 32) {
+      const float2 s = __ldg(S + f), o = __ldg(O + f), rp = __ldg(Rp + f);
+      const float2 s2 = __ldg(S2 + f), o2 = __ldg(O2 + f), rn = __ldg(Rn + f);
+      if (f == 0) {  // slot 0 = (X_0, X_{d/2}), both real
+        accp += s.x * o.x * rp.x + s.y * o.y * rp.y;
+        accn += s2.x * o2.x * rn.x + s2.y * o2.y * rn.y;
+      } else {
+        const float2 a1 = cmulc(s, o), b1 = cmulc(s2, o2);
+        accp += 2.f * (a1.x * rp.x + a1.y * rp.y);
+        accn += 2.f * (b1.x * rn.x + b1.y * rn.y);
+      }
+    }
+    const float raw_p = warp_sum(accp) * inv_d, raw_n = warp_sum(accn) * inv_d;
+    const float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
+    const bool viol = fn + margin > fp;  // skge/hole.py:56
+    if (lane == 0) flags[i] = viol;
+    if (!viol) continue;
+    ++nv;
+    const float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // hole.py:66-67
+    float2 *g = reinterpret_cast<float2 *>(G + (int64_t)i * 6 * d);
+    for (int f = lane; f < h; f += 32) {
+      const float2 s = __ldg(S + f), o = __ldg(O + f), rp = __ldg(Rp + f);
+      const float2 s2 = __ldg(S2 + f), o2 = __ldg(O2 + f), rn = __ldg(Rn + f);
+      float2 a1, a2, a3, b1, b2, b3;
+      if (f == 0) {
+        a1 = make_float2(s.x * o.x, s.y * o.y);     b1 = make_float2(s2.x * o2.x, s2.y * o2.y);
+        a2 = make_float2(rp.x * o.x, rp.y * o.y);   b2 = make_float2(rn.x * o2.x, rn.y * o2.y);
+        a3 = make_float2(s.x * rp.x, s.y * rp.y);   b3 = make_float2(s2.x * rn.x, s2.y * rn.y);
+      } else {
+        a1 = cmulc(s, o);   b1 = cmulc(s2, o2);     // ccorr(s, o)
+        a2 = cmulc(rp, o);  b2 = cmulc(rn, o2);     // ccorr(r, o)
+        a3 = cmul(s, rp);   b3 = cmul(s2, rn);      // cconv(s, r)
+      }
+      g[0 * h + f] = make_float2(gp * a2.x, gp * a2.y);  // -> sp
+      g[1 * h + f] = make_float2(gn * b2.x, gn * b2.y);  // -> sn
+      g[2 * h + f] = make_float2(gp * a3.x, gp * a3.y);  // -> op
+      g[3 * h + f] = make_float2(gn * b3.x, gn * b3.y);  // -> on
+      g[4 * h + f] = make_float2(gp * a1.x, gp * a1.y);  // -> pp
+      g[5 * h + f] = make_float2(gn * b1.x, gn * b1.y);  // -> pn
+    }
+  }
+  if (lane == 0 && nv) {
+    atomicAdd(counts, nv);
+    if (nviol_accum) atomicAdd(reinterpret_cast<unsigned long long *>(nviol_accum), (unsigned long long)nv);
+  }
+}
+
 static int pair_block_threads(int d) {
   int t = (d + 31) / 32 * 32;
   return t < 64 ? 64 : t;
@@ -387,7 +473,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
                     int opt, float lr, int postE, int postR, float *pscores, float *nscores, float *ge,
                     int32_t *eidx, float *gr, int32_t *ridx, int32_t *counts, int64_t *nviol_accum,
                     int32_t *ent_viol, int32_t *ucE, int32_t *ucR, void *ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, float *Ehat = nullptr, float *Rhat = nullptr) {
   SKGE_REQUIRE(E && R && ix.sp && ix.op && ix.pp && ix.sn && ix.on && ix.pn && counts && ws,
                "null argument");
   SKGE_REQUIRE(P > 0 && d > 0 && N > 0 && M > 0, "bad sizes");
@@ -419,6 +505,12 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
                                                           flags, G, counts, nviol_accum, ent_viol);
         break;
     }
+  } else if (Ehat && Rhat) {
+    SKGE_REQUIRE(update && log2_exact(d) >= 5 && d <= 1024, "spectral HolE step needs a power-of-two d in [32, 1024]");
+    int64_t blocks = (P + 7) / 8;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    hole_pair_spec_kernel<<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, d, l1_or_af, margin, flags, G, counts,
+                                                      nviol_accum);
   } else {
     SKGE_REQUIRE(d <= 1024, "HolE pair kernel supports d <= 1024");
     bool fft_done = true;
@@ -457,9 +549,10 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
   }
   rm.nroles = 6;
   ParamDesc pd[2];
-  pd[0] = ParamDesc{E, p2E, postE, 0.f, ucE, ge, eidx};
-  pd[1] = ParamDesc{R, p2R, postR, rparam, ucR, gr, ridx};
-  return seg_run(rm, flags, P, N, M, d, G, rows, pd, update, opt, lr, counts, ar, st);
+  pd[0] = ParamDesc{E, p2E, postE, 0.f, ucE, ge, eidx, Ehat};
+  pd[1] = ParamDesc{R, p2R, postR, rparam, ucR, gr, ridx, Rhat};
+  return seg_run(rm, flags, P, N, M, d, G, rows, pd, update, opt, lr, counts, ar, st,
+                 (model == 1 && Ehat && Rhat) ? 1 : 0);
 }
 
 }  // namespace skge
@@ -524,6 +617,35 @@ int skge_hole_pair_step(float *E, float *R, float *p2E, float *p2R, const int32_
   return pair_run(1, E, R, p2E, p2R, ix, P, N, M, d, af, margin, rparam, true, opt, lr, postE, postR, nullptr,
                   nullptr, nullptr, nullptr, nullptr, nullptr, counts, nviol_accum, nullptr, upd_counts_E,
                   upd_counts_R, ws, ws_bytes, as_stream(stream));
+}
+
+
+int skge_hole_spectra(const float *X, int64_t rows, int d, float *Xhat, skge_stream_t stream) {
+  SKGE_REQUIRE(X && Xhat && rows >= 0, "bad arguments");
+  int logd = log2_exact(d);
+  SKGE_REQUIRE(logd >= 5 && d <= 1024, "spectra need a power-of-two d in [32, 1024]");
+  if (rows == 0) return 0;
+  size_t smem = (size_t)(d / 2) * sizeof(float2) + (size_t)8 * 2 * d * sizeof(float2);
+  SKGE_CUDA(cudaFuncSetAttribute(hole_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  hole_spectra_kernel<<<(int)blocks, 256, smem, as_stream(stream)>>>(X, rows, d, logd, Xhat);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
+int skge_hole_pair_step_spectral(float *E, float *R, float *Ehat, float *Rhat, float *p2E, float *p2R,
+                                 const int32_t *sp, const int32_t *op, const int32_t *pp, const int32_t *sn,
+                                 const int32_t *on, const int32_t *pn, const uint8_t *valid, int64_t P,
+                                 int64_t N, int64_t M, int d, int af, float margin, float rparam, int opt,
+                                 float lr, int postE, int postR, int32_t *counts, int64_t *nviol_accum,
+                                 int32_t *upd_counts_E, int32_t *upd_counts_R, void *ws, size_t ws_bytes,
+                                 skge_stream_t stream) {
+  SKGE_REQUIRE(Ehat && Rhat, "null spectra");
+  PairIdx ix{sp, op, pp, sn, on, pn, valid};
+  return pair_run(1, E, R, p2E, p2R, ix, P, N, M, d, af, margin, rparam, true, opt, lr, postE, postR, nullptr,
+                  nullptr, nullptr, nullptr, nullptr, nullptr, counts, nviol_accum, nullptr, upd_counts_E,
+                  upd_counts_R, ws, ws_bytes, as_stream(stream), Ehat, Rhat);
 }
 
 }  // extern "C"

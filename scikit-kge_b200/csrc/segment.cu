@@ -6,6 +6,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include "fft.cuh"
 #include "segment.cuh"
 
 namespace skge {
@@ -153,8 +154,20 @@ int seg_build(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int
 // post-hook and writes the row (and p2) exactly once.
 template <int VEC, int MAXC>
 __device__ __forceinline__ void row_update(float *xrow, float *p2row, float (&g)[MAXC][VEC], int d,
+                                           int lane, int opt, float lr, int post, float rparam,
+                                           float (&x)[MAXC][VEC]);
+
+template <int VEC, int MAXC>
+__device__ __forceinline__ void row_update(float *xrow, float *p2row, float (&g)[MAXC][VEC], int d,
                                            int lane, int opt, float lr, int post, float rparam) {
   float x[MAXC][VEC];
+  row_update<VEC, MAXC>(xrow, p2row, g, d, lane, opt, lr, post, rparam, x);
+}
+
+template <int VEC, int MAXC>
+__device__ __forceinline__ void row_update(float *xrow, float *p2row, float (&g)[MAXC][VEC], int d,
+                                           int lane, int opt, float lr, int post, float rparam,
+                                           float (&x)[MAXC][VEC]) {
   float ss = 0.f;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
@@ -215,7 +228,14 @@ struct SegArgs {
   int32_t *long_work;   // [long_chunk_cap][2]: segment, chunk index inside the segment
   float *partials;      // [long_chunk_cap][d]
   int long_seg_cap, long_chunk_cap;
+  int spec_logd;        // > 0: G rows are packed spectra of length 1 << spec_logd (see fft.cuh)
 };
+
+// shared memory of the spectral mode: twiddles [d/2] float2, then per warp two complex
+// buffers [d] float2 and one float row [d]
+__host__ __device__ __forceinline__ size_t spec_smem_bytes(int d, int warps) {
+  return (size_t)(d / 2) * sizeof(float2) + (size_t)warps * ((size_t)2 * d * sizeof(float2) + (size_t)d * sizeof(float));
+}
 
 // acc += signed gradient rows of occurrences [beg, end) of the sorted list
 template <int VEC, int MAXC>
@@ -245,21 +265,61 @@ __device__ __forceinline__ void accumulate_rows(const SegArgs &a, int beg, int e
 // the optimiser step in place or emit (gradient row, row id).
 template <int VEC, int MAXC, bool UPDATE>
 __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, int n, int lane,
-                                           float (&acc)[MAXC][VEC]) {
+                                           float (&acc)[MAXC][VEC], float *spec_smem = nullptr, int warp_in_cta = 0) {
   const int d = a.d;
   const int U0 = a.meta[1];
   int which = key >= a.N;
   int64_t row = which ? key - a.N : key;
   float fn = (float)n;
+  float2 *tw = nullptr, *b0 = nullptr, *b1 = nullptr;
+  float *pk = nullptr;
+  if (UPDATE && a.spec_logd > 0) {
+    // acc is a summed packed spectrum: back to the time domain (scaled by 1/d)
+    tw = reinterpret_cast<float2 *>(spec_smem);
+    b0 = tw + d / 2 + (size_t)warp_in_cta * 2 * d;
+    b1 = b0 + d;
+    pk = reinterpret_cast<float *>(tw + d / 2 + (size_t)(blockDim.x >> 5) * 2 * d) + (size_t)warp_in_cta * d;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      int col = (c * 32 + lane) * VEC;
+      if (col < d) st_vec<VEC>(pk + col, acc[c]);
+    }
+    const float *pkc = pk;
+    float2 *X = warp_irfft_packed([pkc](int i) { return pkc[i]; }, b0, b1, tw, a.spec_logd, lane);
+    const float inv_d = 1.0f / (float)d;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      int col = (c * 32 + lane) * VEC;
+      if (col < d) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[c][v] = X[col + v].x * inv_d;
+      }
+    }
+  }
 #pragma unroll
   for (int c = 0; c < MAXC; ++c)
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[c][v] /= fn;  // the mean: skge/util.py:97-101
   const ParamDesc &pd = a.pd[which];
   if (UPDATE) {
+    float x[MAXC][VEC];
     row_update<VEC, MAXC>(pd.param + row * d, pd.p2 ? pd.p2 + row * d : nullptr, acc, d, lane, a.opt, a.lr,
-                          pd.post, pd.rparam);
+                          pd.post, pd.rparam, x);
     if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
+    if (a.spec_logd > 0 && pd.hat) {
+      // refresh the row's packed spectrum from the updated time-domain row
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        int col = (c * 32 + lane) * VEC;
+        if (col < d) st_vec<VEC>(pk + col, x[c]);
+      }
+      const float *pkc = pk;
+      const float2 *X = warp_rfft([pkc](int i) { return pkc[i]; }, b0, b1, tw, a.spec_logd, lane);
+      float *hrow = pd.hat + row * d;
+      for (int p = lane; p < d; p += 32) hrow[p] = packed_from_full(X, p, d / 2);
+    }
   } else {
     int64_t u = which ? seg - U0 : seg;
 #pragma unroll
@@ -283,6 +343,11 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
 // (segment, chunk range) for passes 2 and 3.
 template <int VEC, int MAXC, bool UPDATE>
 __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
+  extern __shared__ __align__(16) float spec_smem[];
+  if (UPDATE && a.spec_logd > 0) {
+    fill_twiddles(reinterpret_cast<float2 *>(spec_smem), a.d, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int nseg = a.meta[0];
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.counts) {
@@ -321,7 +386,7 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
     accumulate_rows<VEC, MAXC>(a, beg, end, lane, acc);
-    finish_row<VEC, MAXC, UPDATE>(a, seg, key, n, lane, acc);
+    finish_row<VEC, MAXC, UPDATE>(a, seg, key, n, lane, acc, spec_smem, threadIdx.x >> 5);
   }
 }
 
@@ -356,10 +421,15 @@ __global__ void __launch_bounds__(256) seg_long_chunks_kernel(SegArgs a) {
 // combined through shared memory in warp order, then warp 0 finishes the row.
 template <int VEC, int MAXC, bool UPDATE>
 __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
-  extern __shared__ float red[];  // [8][d]
+  extern __shared__ __align__(16) float red[];  // [8][d], then the spectral scratch
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nlong = a.long_meta[0];
   const int d = a.d;
+  float *spec_smem = red + 8 * d;
+  if (UPDATE && a.spec_logd > 0) {
+    fill_twiddles(reinterpret_cast<float2 *>(spec_smem), d, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
   for (int s = blockIdx.x; s < nlong; s += gridDim.x) {
     int seg = a.long_seg[3 * s], first = a.long_seg[3 * s + 1], nch = a.long_seg[3 * s + 2];
     float acc[MAXC][VEC];
@@ -401,22 +471,35 @@ __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
         }
       }
       int n = a.seg_start[seg + 1] - a.seg_start[seg];
-      finish_row<VEC, MAXC, UPDATE>(a, seg, a.seg_key[seg], n, lane, acc);
+      finish_row<VEC, MAXC, UPDATE>(a, seg, a.seg_key[seg], n, lane, acc, spec_smem, 0);
     }
   }
 }
 
 template <int VEC, int MAXC>
 static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
-  if (update) seg_reduce_kernel<VEC, MAXC, true><<<blocks, 256, 0, st>>>(a);
-  else seg_reduce_kernel<VEC, MAXC, false><<<blocks, 256, 0, st>>>(a);
+  const bool spec = update && a.spec_logd > 0;
+  size_t sm1 = spec ? spec_smem_bytes(a.d, 8) : 0;
+  if (update) {
+    if (sm1 > 48 * 1024)
+      cudaFuncSetAttribute(seg_reduce_kernel<VEC, MAXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    seg_reduce_kernel<VEC, MAXC, true><<<blocks, 256, sm1, st>>>(a);
+  } else {
+    seg_reduce_kernel<VEC, MAXC, false><<<blocks, 256, 0, st>>>(a);
+  }
   int cb = (a.long_chunk_cap + 7) / 8;
   if (cb > kNumSMs * 8) cb = kNumSMs * 8;
   seg_long_chunks_kernel<VEC, MAXC><<<cb, 256, 0, st>>>(a);
   int sb = a.long_seg_cap < kNumSMs * 4 ? a.long_seg_cap : kNumSMs * 4;
-  size_t smem = (size_t)8 * a.d * sizeof(float);
-  if (update) seg_long_finish_kernel<VEC, MAXC, true><<<sb, 256, smem, st>>>(a);
-  else seg_long_finish_kernel<VEC, MAXC, false><<<sb, 256, smem, st>>>(a);
+  size_t smem = (size_t)8 * a.d * sizeof(float) + (spec ? spec_smem_bytes(a.d, 8) : 0);
+  if (update) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(seg_long_finish_kernel<VEC, MAXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+    seg_long_finish_kernel<VEC, MAXC, true><<<sb, 256, smem, st>>>(a);
+  } else {
+    seg_long_finish_kernel<VEC, MAXC, false><<<sb, 256, smem, st>>>(a);
+  }
 }
 
 template <int VEC>
@@ -435,7 +518,7 @@ static int dispatch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaSt
 
 int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64_t M, int d,
             const float *G, int rows_per_unit, const ParamDesc pd[2], bool update, int opt, float lr,
-            int32_t *counts, Arena &ar, cudaStream_t st) {
+            int32_t *counts, Arena &ar, cudaStream_t st, int spectral) {
   SegLists sl;
   int rc = seg_build(rm, flags, P, N, M, ar, st, &sl);
   if (rc) return rc;
@@ -452,6 +535,11 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
     return SKGE_EWORKSPACE;
   }
   SKGE_CUDA(cudaMemsetAsync(a.long_meta, 0, 16, st));
+  a.spec_logd = 0;
+  if (spectral) {
+    a.spec_logd = log2_exact(d);
+    SKGE_REQUIRE(update && a.spec_logd >= 5 && d <= 1024, "spectral mode needs update mode and a power-of-two d in [32, 1024]");
+  }
   a.seg_start = sl.seg_start;
   a.seg_key = sl.seg_key;
   a.vals = sl.vals;

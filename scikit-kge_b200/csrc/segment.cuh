@@ -28,6 +28,7 @@ struct ParamDesc {
   int32_t *upd_counts; // nullable
   float *out_g;        // emit mode: [U][d]
   int32_t *out_idx;    // emit mode: [U]
+  float *hat;          // spectral mode: packed spectra of the table's rows, refreshed on update (nullable)
 };
 
 size_t seg_workspace_bytes(int64_t L, int d);
@@ -36,9 +37,12 @@ size_t seg_workspace_bytes(int64_t L, int d);
 // either emits (mean gradient, row id) per unique row (update == false) or
 // applies the optimiser step in place (update == true).  counts[1], counts[2]
 // receive the number of unique rows of table 0 / table 1.
+// spectral != 0: the rows of G are packed spectra (csrc/fft.cuh); each unique row's summed
+// spectrum is taken back to the time domain before the update and the updated row's spectrum
+// is written to ParamDesc::hat (HolE in the frequency domain, update mode, power-of-two d).
 int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64_t M, int d,
             const float *G, int rows_per_unit, const ParamDesc pd[2], bool update, int opt, float lr,
-            int32_t *counts, Arena &ar, cudaStream_t st);
+            int32_t *counts, Arena &ar, cudaStream_t st, int spectral = 0);
 
 // *p = v on the stream (keeps the step capturable in a CUDA graph)
 int set_i32(int32_t *p, int32_t v, cudaStream_t st);

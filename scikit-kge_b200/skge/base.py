@@ -215,8 +215,11 @@ class StochasticTrainer(object):
         """The epoch loop of ``_optim`` (skge/base.py:1254-1291); ``step(batch)``
         gets an int32 CUDA tensor of example indices."""
         bounds = self._batch_bounds(n)
+        prepare = getattr(self.model, '_prepare_fused', None)
         for self.epoch in range(1, self.max_epochs + 1):
             self._pre_epoch()
+            if prepare is not None:
+                prepare()       # per-epoch derived state of the model (HolE: spectra of E, R)
             perm = self._randperm(n).to(torch.int32)
             self.epoch_start = timeit.default_timer()
             for lo, hi in bounds:
@@ -225,6 +228,8 @@ class StochasticTrainer(object):
             for f in self.post_epoch:
                 if not f(self):
                     break   # as in the reference, this only leaves the callback loop
+        if hasattr(self.model, '_end_fused'):
+            self.model._end_fused()
 
     # -- reference API ----------------------------------------------------------------
     def fit(self, xs, ys):

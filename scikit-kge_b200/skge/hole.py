@@ -57,9 +57,31 @@ class HolE(Model):
         tc = self.track_counters and opt == _ext.OPT_ADAGRAD
         return (self.E._update_counts if tc else None), (self.R._update_counts if tc else None)
 
+    # -- frequency-domain training state (power-of-two ncomp) ------------------------------
+    spectral = True         # set False to force the per-pair FFT / direct kernels
+
+    def _prepare_fused(self):
+        """Called by the trainers at the start of every fused epoch: (re)build the packed
+        spectra of E and R that the spectral step reads and keeps current."""
+        d = self.ncomp
+        if self.spectral and d >= 32 and d <= 1024 and (d & (d - 1)) == 0:
+            self._spec = (kernels.hole_spectra(self.E.data), kernels.hole_spectra(self.R.data))
+        else:
+            self._spec = None
+
+    def _end_fused(self):
+        self._spec = None
+
     def _fused_pair_step(self, updaters, pos, neg, valid, counts, nviol_accum):
         opt, lr, p2E, p2R = updater_args(updaters, 'E', 'R')
         ucE, ucR = self._uc(opt)
+        spec = getattr(self, '_spec', None)
+        if spec is not None:
+            kernels.hole_pair_step_spectral(self.E.data, self.R.data, spec[0], spec[1], p2E, p2R, pos, neg, valid,
+                                            self.margin, af.af_code(self.af), self.rparam, opt, lr,
+                                            post_code(self.E.post), post_code(self.R.post), counts, nviol_accum,
+                                            ucE=ucE, ucR=ucR)
+            return
         kernels.pair_step(self.model_code, self.E.data, self.R.data, p2E, p2R, pos, neg, valid, self.margin,
                           af.af_code(self.af), self.rparam, opt, lr, post_code(self.E.post),
                           post_code(self.R.post), counts, nviol_accum, ucE=ucE, ucR=ucR)

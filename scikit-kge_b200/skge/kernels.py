@@ -95,6 +95,27 @@ def pair_step(model, E, R, p2E, p2R, pos, neg, valid, margin, l1_or_af, rparam, 
                                         ptr(nviol_accum), ptr(ucE), ptr(ucR), ptr(ws), ws.numel(), stream()))
 
 
+def hole_spectra(X):
+    """Packed spectra of the rows of X (power-of-two d), see csrc/fft.cuh."""
+    out = torch.empty_like(X)
+    _count('scores')
+    check(lib().skge_hole_spectra(ptr(X), X.shape[0], X.shape[1], ptr(out), stream()))
+    return out
+
+
+def hole_pair_step_spectral(E, R, Ehat, Rhat, p2E, p2R, pos, neg, valid, margin, af, rparam, opt, lr, postE, postR,
+                            counts, nviol_accum, ucE=None, ucR=None):
+    (sp, op, pp), (sn, on, pn) = pos, neg
+    P, (N, d), M = sp.numel(), E.shape, R.shape[0]
+    ws = pair_workspace(P, d, 6, N, M)
+    _count('pair')
+    check(lib().skge_hole_pair_step_spectral(ptr(E), ptr(R), ptr(Ehat), ptr(Rhat), ptr(p2E), ptr(p2R), ptr(sp),
+                                             ptr(op), ptr(pp), ptr(sn), ptr(on), ptr(pn), ptr(valid), P, N, M, d,
+                                             int(af), float(margin), float(rparam), opt, float(lr), postE, postR,
+                                             ptr(counts), ptr(nviol_accum), ptr(ucE), ptr(ucR), ptr(ws), ws.numel(),
+                                             stream()))
+
+
 def logistic_grads(model, E, R2, s, o, p, y, rparam):
     """Un-fused logistic gradients.  R2 is R (HolE) or W (RESCAL).
     Returns dict(loss, ge, eidx, g2, idx2)."""

@@ -119,6 +119,49 @@ def test_pairwise_fused_step_matches_reference_golden(golden, name):
     assert int(trn._nviol_dev.item()) == int(g['nviolations1']) + int(g['nviolations2'])
 
 
+def test_hole_spectra_match_numpy_rfft():
+    """Packed spectra (csrc/fft.cuh): slot 0 = (X_0, X_{d/2}), slot f = (Re X_f, Im X_f)."""
+    from skge import kernels
+    rng = np.random.default_rng(0)
+    for d in (32, 64, 128, 256, 512, 1024):
+        x = rng.normal(size=(37, d)).astype(np.float32)
+        got = kernels.hole_spectra(torch.from_numpy(x).cuda()).cpu().numpy().astype(np.float64)
+        F = np.fft.rfft(x.astype(np.float64), axis=1)
+        want = np.empty((37, d))
+        want[:, 0], want[:, 1] = F[:, 0].real, F[:, d // 2].real
+        want[:, 2::2], want[:, 3::2] = F[:, 1:d // 2].real, F[:, 1:d // 2].imag
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+@pytest.mark.parametrize('name', ['hole_linear_adagrad_d256'])
+def test_hole_frequency_domain_step_matches_reference_golden(golden, name):
+    """The spectral fused step (what fit() runs for power-of-two ncomp): two steps vs the
+    reference's parameters, and the spectra must stay equal to the FFT of the updated tables."""
+    import skge
+    from skge import kernels
+    from skge._modelutil import idx_tensor
+    g = golden(name)
+    m = make_model(g)
+    trn = skge.PairwiseStochasticTrainer(m, nbatches=1, margin=float(g['margin']), max_epochs=1,
+                                         learning_rate=float(g['lr']), param_update=updater_cls(g))
+    trn._setup_fused()
+    m._prepare_fused()
+    assert m._spec is not None
+    pos = tuple(idx_tensor(g['pos'][:, i]) for i in range(3))
+    neg = tuple(idx_tensor(g['neg'][:, i]) for i in range(3))
+    for step in (1, 2):
+        m._fused_pair_step(trn._updaters, pos, neg, None, trn._counts, trn._nviol_dev)
+        nv, ue, ur, _ = trn._counts.tolist()
+        assert nv == int(g['nviolations%d' % step])
+        assert ue == len(g['eidx%d' % step]) and ur == len(g['ridx%d' % step])
+        tol = PARAM_TOL if step == 1 else dict(rtol=5e-5, atol=1e-5)
+        np.testing.assert_allclose(np.asarray(m.E), g['E%d' % step], **tol)
+        np.testing.assert_allclose(np.asarray(m.R), g['R%d' % step], **tol)
+        for tab, hat in ((m.E.data, m._spec[0]), (m.R.data, m._spec[1])):
+            ref = kernels.hole_spectra(tab)
+            torch.testing.assert_close(hat, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
+
+
 @pytest.mark.parametrize('name', LOGISTIC)
 def test_logistic_hooks_and_fused_match_reference_golden(golden, name):
     import skge
@@ -263,6 +306,20 @@ def test_wn18_shaped_minibatch_against_oracle(kind, d, margin, l1, opt):
         orc.sgd_update(R, ograds['R'][0], ograds['R'][1], 0.1, None)
         np.testing.assert_allclose(np.asarray(m.E), E, **PARAM_TOL)
         np.testing.assert_allclose(np.asarray(m.R), R, **PARAM_TOL)
+        if kind == 'hole':      # the same minibatch through the frequency-domain fused step
+            from skge._modelutil import idx_tensor
+            m2 = skge.HolE((N, N, M), d)
+            m2.E[...] = E0
+            m2.R[...] = R0
+            t2 = skge.PairwiseStochasticTrainer(m2, nbatches=1, margin=margin, learning_rate=0.1, param_update=SGD)
+            t2._setup_fused()
+            m2._prepare_fused()
+            assert m2._spec is not None
+            m2._fused_pair_step(t2._updaters, tuple(idx_tensor(pos[:, i]) for i in range(3)),
+                                tuple(idx_tensor(neg[:, i]) for i in range(3)), None, t2._counts, t2._nviol_dev)
+            assert int(t2._nviol_dev.item()) == info['nviolations']
+            np.testing.assert_allclose(np.asarray(m2.E), E, **PARAM_TOL)
+            np.testing.assert_allclose(np.asarray(m2.R), R, **PARAM_TOL)
         return
     orc.adagrad_update(E, np.zeros_like(E), ograds['E'][0], ograds['E'][1], 0.1, post)
     orc.adagrad_update(R, np.zeros_like(R), ograds['R'][0], ograds['R'][1], 0.1, None)
