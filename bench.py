@@ -248,12 +248,12 @@ def run_b200(args):
 
     # --- device-resident metric ("value") ----------------------------------------
     ev._device_state()                       # filter index + query descriptors resident
+    clocks = ClockSampler(local)             # sampled through warm-up + timed region (same load)
     for _ in range(max(3, args.warmup)):
         ev.count_pass(mdl)
     ranking._SweepEngine.timing = True
     ranking.TIMINGS.clear()
     l0 = kernels.LAUNCHES['n']
-    clocks = ClockSampler(local)
     ms = timed(lambda: ev.count_pass(mdl), args.steps)
     clk = clocks.stop()
     launches = kernels.LAUNCHES['n'] - l0
@@ -293,8 +293,13 @@ def run_b200(args):
         if tensor:
             achieved = work / (avg_ms * 1e-3) / 1e12
             peak = pk['tf_sust']
+            traffic = None
+            if args.workload == 'cfg5' and world == 1 and te == Te and str(stats.get('engine', '')).startswith('tcgen05'):
+                traffic = 12.875e9 + 0.180e9   # dram read + write of one launch: profiles/r01_rank_cfg5_tcgen05_v2.txt
             roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak, 'traffic': None, 'kernel': stats.get('engine'),
+                    'frac': achieved / peak, 'traffic': traffic, 'kernel': stats.get('engine'),
+                    'executed_tflops': achieved * (3 if 'x3' in str(stats.get('engine')) else 1),
+                    'tensor_pipe_active_pct_ncu': 69.2 if traffic else None,
                     'launch_ms': avg_ms, 'launches_timed': len(kt), 'peak_source': pk['src'] + ' bf16 sustained',
                     'algorithmic_flops_per_launch': work,
                     'kernel_share_of_step': sum(t for t, _ in kt) / max(ms, 1e-9)}
@@ -392,12 +397,22 @@ def bench_train(args, mdl, N, M, d, model, pk):
     launches = kernels.LAUNCHES['n'] - l0
     best = min(times[1:])
     P = 2 * (T // nb)
+    # algorithmic bytes of one minibatch: 4*d*[4P + c*(U_E+U_R)] + 24P, c = 4 (AdaGrad),
+    # with the unique-row counts of the last minibatch
+    nv, ue, ur, _ = trn._counts.tolist()
+    bytes_batch = 4.0 * d * (4 * P + 4 * (ue + ur)) + 24.0 * P
+    ach = bytes_batch / (best / nb) / 1e9
     # worst-case algorithmic bytes per pair: 4*d*[4P + c(U_E+U_R)], U <= 4P, c = 4
     return {'metric': 'train triples/s', 'value': T / best, 'unit': 'triples/s', 'epoch_s': best,
             'epochs_timed': len(times) - 1, 'model': model, 'd': d, 'batch_positives': T // nb,
             'pairs_per_batch': P, 'nbatches': nb, 'triples': T, 'violations_last_epoch': trn.nviolations,
             'gpu_launches': launches, 'sampler': 'on-device RandomModeSampler(1, [0,1])', 'optimizer': 'AdaGrad',
             'epoch_times_s': [round(t, 5) for t in times],
+            'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
+                         'algorithmic_bytes_per_minibatch': bytes_batch, 'minibatch_ms': 1e3 * best / nb,
+                         'unique_rows_last_minibatch': [ue, ur], 'violating_pairs_last_minibatch': nv,
+                         'peak_source': pk['src'], 'traffic': None,
+                         'note': 'whole fused step (sampler + pair kernel + sort + segmented update), wall clock per minibatch'},
             'note': 'steady-state epochs through PairwiseStochasticTrainer.fit (first epoch excluded)'}
 
 

@@ -32,15 +32,18 @@ __device__ __forceinline__ void fill_twiddles(float2 *tw, int N, int tid, int nt
   }
 }
 
-// One complex transform of length N = 1 << logd by ONE WARP: Stockham autosort, radix-4
-// stages (plus a leading radix-2 stage when logd is odd), ping-ponging between `in` and
-// `out` (both N float2 in shared memory, private to the warp).  Returns the buffer that
-// holds the result.  Callers must __syncwarp() after filling `in`.
+// One complex transform of length n = 1 << logn by ONE WARP: Stockham autosort, radix-4
+// stages (plus a leading radix-2 stage when logn is odd), ping-ponging between `in` and
+// `out` (n float2 each, shared memory private to the warp).  The twiddle table belongs to a
+// transform of length n * tw_stride (tw[m] = exp(-2 pi i m / (n * tw_stride))).  Returns the
+// buffer that holds the result.  Callers must __syncwarp() after filling `in`.
 template <bool INVERSE>
-__device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float2 *tw, int logd, int lane) {
-  const int N = 1 << logd, H = N >> 1, Qn = N >> 2;
+__device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float2 *tw, int tw_stride, int logn,
+                                            int lane) {
+  const int N = 1 << logn, H = N >> 1, Qn = N >> 2;
+  const int thalf = H * tw_stride;  // table entries
   int Ns = 1;
-  if (logd & 1) {
+  if (logn & 1) {
     for (int j = lane; j < H; j += 32) {
       const float2 u0 = in[j], u1 = in[j + H];
       out[2 * j] = make_float2(u0.x + u1.x, u0.y + u1.y);
@@ -51,11 +54,11 @@ __device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float
     Ns = 2;
   }
   for (; Ns < N; Ns <<= 2) {
-    const int tstep = N / (4 * Ns);
+    const int tstep = (N / (4 * Ns)) * tw_stride;
     for (int j = lane; j < Qn; j += 32) {
       const int k = j & (Ns - 1);
       const int j0 = ((j - k) << 2) + k;
-      float2 w1 = tw_at(tw, k * tstep, H), w2 = tw_at(tw, 2 * k * tstep, H), w3 = tw_at(tw, 3 * k * tstep, H);
+      float2 w1 = tw_at(tw, k * tstep, thalf), w2 = tw_at(tw, 2 * k * tstep, thalf), w3 = tw_at(tw, 3 * k * tstep, thalf);
       if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
       const float2 v0 = in[j];
       const float2 v1 = cmul(in[j + Qn], w1);
@@ -75,45 +78,51 @@ __device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float
   return in;
 }
 
-// Per-warp scratch: two complex buffers of N float2.
-__host__ __device__ __forceinline__ size_t warp_fft_scratch_bytes(int d) { return (size_t)2 * d * sizeof(float2); }
+// Real transforms of length d through ONE complex transform of length h = d/2
+// (z_m = x_{2m} + i x_{2m+1}):  with E, O the spectra of the even / odd samples,
+//   Z_f = E_f + i O_f,  conj(Z_{h-f}) = E_f - i O_f,  X_f = E_f + W_d^f O_f,  X_h = E_0 - O_0.
+// Per-warp scratch: two buffers of h float2 (= 2 d floats in total).
+__host__ __device__ __forceinline__ size_t warp_fft_scratch_floats(int d) { return (size_t)2 * d; }
 
-// packed spectrum pk[0..d) (floats, shared or global, read through `ld`) -> time-domain row
-// x[n] (unscaled: multiply by 1/d), left as the REAL parts of the returned buffer.
-template <typename Load>
-__device__ __forceinline__ float2 *warp_irfft_packed(Load ld, float2 *b0, float2 *b1, const float2 *tw, int logd,
-                                                     int lane) {
-  const int N = 1 << logd, H = N >> 1;
+// packed spectrum (floats pk[0..d), in shared memory; may alias b1) -> time-domain row.
+// The returned buffer, viewed as d floats, holds x_n * (d/2): scale by 2/d.
+__device__ __forceinline__ const float *warp_irfft_packed(const float *pk, float2 *b0, float2 *b1, const float2 *tw,
+                                                         int logd, int lane) {
+  const int h = 1 << (logd - 1);
   __syncwarp();
-  for (int f = lane; f < N; f += 32) {
-    float2 v;
-    if (f == 0) v = make_float2(ld(0), 0.f);
-    else if (f == H) v = make_float2(ld(1), 0.f);
-    else if (f < H) v = make_float2(ld(2 * f), ld(2 * f + 1));
-    else v = make_float2(ld(2 * (N - f)), -ld(2 * (N - f) + 1));   // Hermitian extension
-    b0[f] = v;
+  for (int f = lane; f < h; f += 32) {
+    float2 z;
+    if (f == 0) {
+      const float x0 = pk[0], xh = pk[1];
+      z = make_float2(0.5f * (x0 + xh), 0.5f * (x0 - xh));
+    } else {
+      const float2 xf = make_float2(pk[2 * f], pk[2 * f + 1]);
+      const float2 xg = make_float2(pk[2 * (h - f)], -pk[2 * (h - f) + 1]);   // conj X_{h-f}
+      const float2 e = make_float2(0.5f * (xf.x + xg.x), 0.5f * (xf.y + xg.y));
+      const float2 dd = make_float2(0.5f * (xf.x - xg.x), 0.5f * (xf.y - xg.y));
+      const float2 o = cmulc(tw[f], dd);                                       // W_d^{-f} * dd
+      z = make_float2(e.x - o.y, e.y + o.x);                                   // E + i O
+    }
+    b0[f] = z;
   }
   __syncwarp();
-  return warp_fft<true>(b0, b1, tw, logd, lane);
+  return reinterpret_cast<const float *>(warp_fft<true>(b0, b1, tw, 2, logd - 1, lane));
 }
 
-// real row x[0..d) (read through `ld`) -> full complex spectrum in the returned buffer
-// (only slots 0..d/2 are needed for the packed layout).
-template <typename Load>
-__device__ __forceinline__ float2 *warp_rfft(Load ld, float2 *b0, float2 *b1, const float2 *tw, int logd, int lane) {
-  const int N = 1 << logd;
+// b0 viewed as d floats holds the real row; returns Z (h float2), the half-length transform.
+__device__ __forceinline__ const float2 *warp_rfft_half(float2 *b0, float2 *b1, const float2 *tw, int logd, int lane) {
   __syncwarp();
-  for (int n = lane; n < N; n += 32) b0[n] = make_float2(ld(n), 0.f);
-  __syncwarp();
-  return warp_fft<false>(b0, b1, tw, logd, lane);
+  return warp_fft<false>(b0, b1, tw, 2, logd - 1, lane);
 }
 
-// element p of the packed layout from a full spectrum X
-__device__ __forceinline__ float packed_from_full(const float2 *X, int p, int H) {
-  if (p == 0) return X[0].x;
-  if (p == 1) return X[H].x;
-  const float2 v = X[p >> 1];
-  return (p & 1) ? v.y : v.x;
+// packed slot f (0 <= f < h) of the length-d spectrum from the half-length transform Z
+__device__ __forceinline__ float2 packed_slot(const float2 *Z, int f, int h, const float2 *tw) {
+  if (f == 0) return make_float2(Z[0].x + Z[0].y, Z[0].x - Z[0].y);   // (X_0, X_h)
+  const float2 zf = Z[f], zg = Z[h - f];
+  const float2 e = make_float2(0.5f * (zf.x + zg.x), 0.5f * (zf.y - zg.y));   // (Z_f + conj Z_g) / 2
+  const float2 o = make_float2(0.5f * (zf.y + zg.y), -0.5f * (zf.x - zg.x));  // (Z_f - conj Z_g) / (2 i)
+  const float2 wo = cmul(tw[f], o);
+  return make_float2(e.x + wo.x, e.y + wo.y);
 }
 
 static inline int log2_exact(int d) {

@@ -371,12 +371,15 @@ __global__ void __launch_bounds__(256) hole_spectra_kernel(const float *__restri
   fill_twiddles(tw, d, threadIdx.x, blockDim.x);
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float2 *b0 = tw + d / 2 + (size_t)w * 2 * d, *b1 = b0 + d;
+  const int h = d / 2;
+  float2 *b0 = tw + h + (size_t)w * 2 * h, *b1 = b0 + h;
   for (int64_t r = (int64_t)blockIdx.x * nw + w; r < rows; r += (int64_t)gridDim.x * nw) {
-    const float *x = X + r * d;
-    const float2 *S = warp_rfft([x](int i) { return __ldg(x + i); }, b0, b1, tw, logd, lane);
-    float *h = Xhat + r * d;
-    for (int p = lane; p < d; p += 32) h[p] = packed_from_full(S, p, d / 2);
+    const float2 *x = reinterpret_cast<const float2 *>(X + r * d);
+    __syncwarp();
+    for (int m = lane; m < h; m += 32) b0[m] = __ldg(x + m);   // z_m = x_{2m} + i x_{2m+1}
+    const float2 *Z = warp_rfft_half(b0, b1, tw, logd, lane);
+    float2 *hr = reinterpret_cast<float2 *>(Xhat + r * d);
+    for (int f = lane; f < h; f += 32) hr[f] = packed_slot(Z, f, h, tw);
   }
 }
 
@@ -625,7 +628,7 @@ int skge_hole_spectra(const float *X, int64_t rows, int d, float *Xhat, skge_str
   int logd = log2_exact(d);
   SKGE_REQUIRE(logd >= 5 && d <= 1024, "spectra need a power-of-two d in [32, 1024]");
   if (rows == 0) return 0;
-  size_t smem = (size_t)(d / 2) * sizeof(float2) + (size_t)8 * 2 * d * sizeof(float2);
+  size_t smem = (size_t)(d / 2) * sizeof(float2) + (size_t)8 * warp_fft_scratch_floats(d) * sizeof(float);
   SKGE_CUDA(cudaFuncSetAttribute(hole_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = (rows + 7) / 8;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;

@@ -232,9 +232,9 @@ struct SegArgs {
 };
 
 // shared memory of the spectral mode: twiddles [d/2] float2, then per warp two complex
-// buffers [d] float2 and one float row [d]
+// buffers of d/2 float2 (2 d floats)
 __host__ __device__ __forceinline__ size_t spec_smem_bytes(int d, int warps) {
-  return (size_t)(d / 2) * sizeof(float2) + (size_t)warps * ((size_t)2 * d * sizeof(float2) + (size_t)d * sizeof(float));
+  return (size_t)(d / 2) * sizeof(float2) + (size_t)warps * warp_fft_scratch_floats(d) * sizeof(float);
 }
 
 // acc += signed gradient rows of occurrences [beg, end) of the sorted list
@@ -272,28 +272,27 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
   int64_t row = which ? key - a.N : key;
   float fn = (float)n;
   float2 *tw = nullptr, *b0 = nullptr, *b1 = nullptr;
-  float *pk = nullptr;
   if (UPDATE && a.spec_logd > 0) {
-    // acc is a summed packed spectrum: back to the time domain (scaled by 1/d)
+    // acc is a summed packed spectrum: back to the time domain
+    const int h = d / 2;
     tw = reinterpret_cast<float2 *>(spec_smem);
-    b0 = tw + d / 2 + (size_t)warp_in_cta * 2 * d;
-    b1 = b0 + d;
-    pk = reinterpret_cast<float *>(tw + d / 2 + (size_t)(blockDim.x >> 5) * 2 * d) + (size_t)warp_in_cta * d;
+    b0 = tw + h + (size_t)warp_in_cta * 2 * h;
+    b1 = b0 + h;
+    float *pk = reinterpret_cast<float *>(b1);   // the packed row may live in b1 until the first stage
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
       int col = (c * 32 + lane) * VEC;
       if (col < d) st_vec<VEC>(pk + col, acc[c]);
     }
-    const float *pkc = pk;
-    float2 *X = warp_irfft_packed([pkc](int i) { return pkc[i]; }, b0, b1, tw, a.spec_logd, lane);
-    const float inv_d = 1.0f / (float)d;
+    const float *x = warp_irfft_packed(pk, b0, b1, tw, a.spec_logd, lane);
+    const float sc = 2.0f / (float)d;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
       int col = (c * 32 + lane) * VEC;
       if (col < d) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[c][v] = X[col + v].x * inv_d;
+        for (int v = 0; v < VEC; ++v) acc[c][v] = x[col + v] * sc;
       }
     }
   }
@@ -309,16 +308,17 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
     if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
     if (a.spec_logd > 0 && pd.hat) {
       // refresh the row's packed spectrum from the updated time-domain row
+      const int h = d / 2;
       __syncwarp();
+      float *xr = reinterpret_cast<float *>(b0);
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         int col = (c * 32 + lane) * VEC;
-        if (col < d) st_vec<VEC>(pk + col, x[c]);
+        if (col < d) st_vec<VEC>(xr + col, x[c]);
       }
-      const float *pkc = pk;
-      const float2 *X = warp_rfft([pkc](int i) { return pkc[i]; }, b0, b1, tw, a.spec_logd, lane);
-      float *hrow = pd.hat + row * d;
-      for (int p = lane; p < d; p += 32) hrow[p] = packed_from_full(X, p, d / 2);
+      const float2 *Z = warp_rfft_half(b0, b1, tw, a.spec_logd, lane);
+      float2 *hrow = reinterpret_cast<float2 *>(pd.hat + row * d);
+      for (int f = lane; f < h; f += 32) hrow[f] = packed_slot(Z, f, h, tw);
     }
   } else {
     int64_t u = which ? seg - U0 : seg;
