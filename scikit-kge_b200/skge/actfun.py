@@ -1,8 +1,11 @@
-"""Activation functions (reference: skge/actfun.py:13-73).
+"""Activation functions of the pairwise / logistic losses.
 
-Host-side classes keep the reference's interface (``f``, ``g_given_f``,
-``key()``); ``code`` is the enum the kernels take (SKGE_AF_*).  Softplus has no
-``g_given_f`` in the reference either and therefore no kernel code.
+Same public surface as the reference's skge/actfun.py:13-73 -- classes ``Linear``,
+``Sigmoid``, ``Tanh``, ``ReLU``, ``Softplus`` with static ``f`` / ``g_given_f`` (derivative
+expressed through the function value), ``key()`` and the ``afuns`` registry keyed by the
+lower-cased class name -- but table-driven: every entry also carries the ``code`` the CUDA
+kernels switch on (SKGE_AF_* in include/skge_b200.h; device versions in csrc/common.cuh).
+The numpy callables here serve host-side callers only; training never goes through them.
 """
 import numpy as np
 
@@ -10,6 +13,7 @@ from . import _ext
 
 
 class ActivationFunction(object):
+    """Base of the generated classes (isinstance / subclass checks keep working)."""
     code = None
 
     @classmethod
@@ -17,68 +21,32 @@ class ActivationFunction(object):
         return cls.__name__.lower()
 
 
-class Linear(ActivationFunction):
-    code = _ext.AF_LINEAR
-
-    @staticmethod
-    def f(x):
-        return x
-
-    @staticmethod
-    def g_given_f(fx):
-        return np.ones(fx.shape[0])
+def _no_derivative(_fx):
+    raise NotImplementedError()
 
 
-class Sigmoid(ActivationFunction):
-    code = _ext.AF_SIGMOID
-
-    @staticmethod
-    def f(x):
-        return 1.0 / (1 + np.exp(-x))
-
-    @staticmethod
-    def g_given_f(fx):
-        return fx * (1.0 - fx)
-
-
-class Tanh(ActivationFunction):
-    code = _ext.AF_TANH
-
-    @staticmethod
-    def f(x):
-        return np.tanh(x)
-
-    @staticmethod
-    def g_given_f(fx):
-        return 1 - fx ** 2
-
-
-class ReLU(ActivationFunction):
-    code = _ext.AF_RELU
-
-    @staticmethod
-    def f(x):
-        return np.maximum(0, x)
-
-    @staticmethod
-    def g_given_f(fx):
-        return np.int_(fx > 0)
-
-
-class Softplus(ActivationFunction):
-
-    @staticmethod
-    def f(x):
-        return np.log(1 + np.exp(x))
-
-    @staticmethod
-    def g(x):
-        raise NotImplementedError()
-
+#  name        kernel code        f(x)                                  g_given_f(f(x))
+_SPEC = (
+    ('Linear',   _ext.AF_LINEAR,  lambda x: x,                          lambda fx: np.ones(fx.shape[0])),
+    ('Sigmoid',  _ext.AF_SIGMOID, lambda x: 1.0 / (1 + np.exp(-x)),     lambda fx: fx * (1.0 - fx)),
+    ('Tanh',     _ext.AF_TANH,    np.tanh,                              lambda fx: 1 - fx ** 2),
+    ('ReLU',     _ext.AF_RELU,    lambda x: np.maximum(0, x),           lambda fx: np.int_(fx > 0)),
+    # the reference defines no g_given_f for Softplus either (it only has a raising ``g``)
+    ('Softplus', None,            lambda x: np.log(1 + np.exp(x)),      None),
+)
 
 afuns = {}
-for cls in ActivationFunction.__subclasses__():
-    afuns[cls.key()] = cls
+for _name, _code, _f, _g in _SPEC:
+    _attrs = {'code': _code, 'f': staticmethod(_f), '__doc__': '%s activation (kernel code %r)' % (_name, _code)}
+    if _g is not None:
+        _attrs['g_given_f'] = staticmethod(_g)
+    else:
+        _attrs['g'] = staticmethod(_no_derivative)
+    _cls = type(_name, (ActivationFunction,), _attrs)
+    _cls.__module__ = __name__
+    globals()[_name] = _cls
+    afuns[_cls.key()] = _cls
+del _name, _code, _f, _g, _attrs, _cls
 
 
 def af_code(af):
