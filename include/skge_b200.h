@@ -186,7 +186,9 @@ SKGE_API int skge_rows_post(float *param, const int32_t *idx, int64_t U, int64_t
  * training triple (and, with lcwa != 0, while (s', p') was never seen:
  * skge/sample.py:103-110, needs sp_table).  Output pair index =
  * (b * n_per + r) * nmodes + m.  out_valid[i] = 0 where all tries failed (the
- * reference skips those, sample.py:22-24).
+ * reference skips those, sample.py:22-24).  The Philox counter of pair i is
+ * offset + *offset_dev + i (offset_dev nullable, device memory): a step captured in a CUDA
+ * graph keeps drawing fresh numbers when the caller advances *offset_dev between replays.
  */
 SKGE_API size_t skge_tripleset_bytes(int64_t T);
 SKGE_API int skge_tripleset_build(void *table, size_t table_bytes, const int32_t *s, const int32_t *o,
@@ -198,9 +200,9 @@ SKGE_API int skge_sample_corrupt(const void *table, size_t table_bytes, const vo
                         size_t sp_table_bytes, const int32_t *s, const int32_t *o,
                         const int32_t *p, const int32_t *batch_idx, int64_t B, int n_per,
                         int modes_mask, int64_t N, int64_t M, int ntries, uint64_t seed,
-                        uint64_t offset, int32_t *out_sp, int32_t *out_op, int32_t *out_pp,
-                        int32_t *out_sn, int32_t *out_on, int32_t *out_pn, uint8_t *out_valid,
-                        skge_stream_t stream);
+                        uint64_t offset, const uint64_t *offset_dev, int32_t *out_sp, int32_t *out_op,
+                        int32_t *out_pp, int32_t *out_sn, int32_t *out_on, int32_t *out_pn,
+                        uint8_t *out_valid, skge_stream_t stream);
 
 /* ---- filtered ranking: FilteredRankingEval.positions -------------------- */
 /*

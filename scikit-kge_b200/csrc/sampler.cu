@@ -78,6 +78,7 @@ struct SampleArgs {
   uint32_t sz[3];
   int ntries;
   uint64_t seed, offset;
+  const uint64_t *offset_dev;
   int32_t *out_sp, *out_op, *out_pp, *out_sn, *out_on, *out_pn;
   uint8_t *out_valid;
 };
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) sample_corrupt_kernel(SampleArgs a) {
     uint32_t x[3] = {(uint32_t)a.s[src], (uint32_t)a.o[src], (uint32_t)a.p[src]};
     uint32_t nx[3] = {x[0], x[1], x[2]};
     bool ok = false;
-    uint64_t ctr = a.offset + (uint64_t)t;
+    uint64_t ctr = a.offset + (a.offset_dev ? *a.offset_dev : 0ull) + (uint64_t)t;
     uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     for (int tr = 0; tr < a.ntries && !ok; tr += 4) {
       uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(tr >> 2), 0x5a3c9e1du), key);
@@ -167,9 +168,9 @@ int skge_sample_corrupt(const void *table, size_t table_bytes, const void *sp_ta
                         size_t sp_table_bytes, const int32_t *s, const int32_t *o,
                         const int32_t *p, const int32_t *batch_idx, int64_t B, int n_per,
                         int modes_mask, int64_t N, int64_t M, int ntries, uint64_t seed,
-                        uint64_t offset, int32_t *out_sp, int32_t *out_op, int32_t *out_pp,
-                        int32_t *out_sn, int32_t *out_on, int32_t *out_pn, uint8_t *out_valid,
-                        skge_stream_t stream) {
+                        uint64_t offset, const uint64_t *offset_dev, int32_t *out_sp, int32_t *out_op,
+                        int32_t *out_pp, int32_t *out_sn, int32_t *out_on, int32_t *out_pn,
+                        uint8_t *out_valid, skge_stream_t stream) {
   SampleArgs a;
   SKGE_REQUIRE(table && s && o && p && out_sp && out_op && out_pp && out_sn && out_on && out_pn && out_valid,
                "null argument");
@@ -190,7 +191,7 @@ int skge_sample_corrupt(const void *table, size_t table_bytes, const void *sp_ta
   for (int m = 0; m < 3; ++m)
     if (modes_mask & (1 << m)) a.modes[a.nmodes++] = m;
   a.sz[0] = (uint32_t)N; a.sz[1] = (uint32_t)N; a.sz[2] = (uint32_t)M;  // sz = (N, N, M): skge/base.py:496
-  a.ntries = ntries; a.seed = seed; a.offset = offset;
+  a.ntries = ntries; a.seed = seed; a.offset = offset; a.offset_dev = offset_dev;
   a.out_sp = out_sp; a.out_op = out_op; a.out_pp = out_pp;
   a.out_sn = out_sn; a.out_on = out_on; a.out_pn = out_pn; a.out_valid = out_valid;
   int64_t total = B * n_per * a.nmodes;

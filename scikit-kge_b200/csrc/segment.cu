@@ -82,13 +82,14 @@ static size_t cub_scan_bytes(int64_t L) {
   return bytes;
 }
 
-// Segments longer than kSegChunk occurrences (hot rows: a hub entity, a frequent relation)
+// Segments longer than seg_chunk occurrences (hot rows: a hub entity, a frequent relation)
 // are cut into chunks reduced by different warps and combined by one CTA per segment, in a
 // fixed order (deterministic, no atomics on parameter rows).
-static constexpr int kSegChunk = 128;
-
-static int64_t long_chunk_cap(int64_t L) { return L / (kSegChunk / 2) + 8; }  // sum ceil(len/128) over len > 128
-static int64_t long_seg_cap(int64_t L) { return L / kSegChunk + 8; }
+// The chunk length trades parallelism against partial-sum traffic: small minibatches (latency
+// bound: the longest serial chain sets the kernel time) use 32, large ones 128.
+static int seg_chunk_for(int64_t L) { return L <= (1 << 18) ? 32 : 128; }
+static int64_t long_chunk_cap(int64_t L) { return L / (seg_chunk_for(L) / 2) + 8; }  // sum ceil(len/c) over len > c
+static int64_t long_seg_cap(int64_t L) { return L / seg_chunk_for(L) + 8; }
 
 size_t seg_workspace_bytes(int64_t L, int d) {
   if (L < 1) L = 1;
@@ -222,12 +223,13 @@ struct SegArgs {
   int opt;
   float lr;
   int32_t *counts;
-  // long segments (more than kSegChunk occurrences)
+  // long segments (more than seg_chunk occurrences)
   int32_t *long_meta;   // [0] number of long segments, [1] number of chunks allocated
   int32_t *long_seg;    // [long_seg_cap][3]: segment, first chunk, number of chunks
   int32_t *long_work;   // [long_chunk_cap][2]: segment, chunk index inside the segment
   float *partials;      // [long_chunk_cap][d]
   int long_seg_cap, long_chunk_cap;
+  int seg_chunk;        // segments longer than this are reduced chunk-wise
   int spec_logd;        // > 0: G rows are packed spectra of length 1 << spec_logd (see fft.cuh)
 };
 
@@ -237,26 +239,45 @@ __host__ __device__ __forceinline__ size_t spec_smem_bytes(int d, int warps) {
   return (size_t)(d / 2) * sizeof(float2) + (size_t)warps * warp_fft_scratch_floats(d) * sizeof(float);
 }
 
-// acc += signed gradient rows of occurrences [beg, end) of the sorted list
-template <int VEC, int MAXC>
+// acc += signed gradient rows of occurrences [beg, end) of the sorted list.  The payloads of
+// up to 32 occurrences are fetched with one coalesced load and broadcast by shuffle; row loads
+// are issued BATCH at a time before they are consumed (memory-level parallelism: a warp that
+// walks a long segment is latency bound otherwise).  BATCH = 4 for small, latency-bound
+// minibatches; BATCH = 1 keeps the register count (hence the occupancy) up for the large,
+// bandwidth-bound ones.
+template <int VEC, int MAXC, int BATCH>
 __device__ __forceinline__ void accumulate_rows(const SegArgs &a, int beg, int end, int lane,
                                                 float (&acc)[MAXC][VEC]) {
   const int d = a.d;
-#pragma unroll 2
-  for (int j = beg; j < end; ++j) {
-    int val = a.vals[j];
-    int r = val & 7;
-    const float *g = a.G + ((int64_t)(val >> 3) * a.rows_per_unit + a.grow[r]) * d;
-    float sgn = a.gsign[r];
+  for (int j0 = beg; j0 < end; j0 += 32) {
+    const int cnt = min(32, end - j0);
+    const int myval = lane < cnt ? a.vals[j0 + lane] : 0;
+    for (int t0 = 0; t0 < cnt; t0 += BATCH) {
+      float tmp[BATCH][MAXC][VEC];
+      float sgn[BATCH];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      int col = (c * 32 + lane) * VEC;
-      if (col < d) {
-        float t[VEC];
-        ld_vec<VEC>(g + col, t);
+      for (int b = 0; b < BATCH; ++b) {
+        const int val = __shfl_sync(kFull, myval, min(t0 + b, cnt - 1));
+        const int r = val & 7;
+        const bool live = t0 + b < cnt;
+        sgn[b] = live ? a.gsign[r] : 0.f;
+        const float *g = a.G + ((int64_t)(val >> 3) * a.rows_per_unit + a.grow[r]) * d;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(sgn, t[v], acc[c][v]);
+        for (int c = 0; c < MAXC; ++c) {
+          int col = (c * 32 + lane) * VEC;
+          if (col < d) ld_vec<VEC>(g + col, tmp[b][c]);
+        }
       }
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b)
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          int col = (c * 32 + lane) * VEC;
+          if (col < d) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(sgn[b], tmp[b][c][v], acc[c][v]);
+          }
+        }
     }
   }
 }
@@ -341,7 +362,7 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
 
 // Pass 1: one warp per segment.  Short segments are finished here; long ones are registered
 // (segment, chunk range) for passes 2 and 3.
-template <int VEC, int MAXC, bool UPDATE>
+template <int VEC, int MAXC, bool UPDATE, int BATCH>
 __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
   extern __shared__ __align__(16) float spec_smem[];
   if (UPDATE && a.spec_logd > 0) {
@@ -360,8 +381,8 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
     int key = a.seg_key[seg];
     int beg = a.seg_start[seg], end = a.seg_start[seg + 1];
     int n = end - beg;
-    if (n > kSegChunk) {
-      int nch = (n + kSegChunk - 1) / kSegChunk;
+    if (n > a.seg_chunk) {
+      int nch = (n + a.seg_chunk - 1) / a.seg_chunk;
       int slot = 0, first = 0;
       if (lane == 0) {
         slot = atomicAdd(a.long_meta, 1);
@@ -385,13 +406,13 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
     for (int c = 0; c < MAXC; ++c)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
-    accumulate_rows<VEC, MAXC>(a, beg, end, lane, acc);
+    accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
     finish_row<VEC, MAXC, UPDATE>(a, seg, key, n, lane, acc, spec_smem, threadIdx.x >> 5);
   }
 }
 
 // Pass 2: one warp per chunk of a long segment -> partial sum row.
-template <int VEC, int MAXC>
+template <int VEC, int MAXC, int BATCH>
 __global__ void __launch_bounds__(256) seg_long_chunks_kernel(SegArgs a) {
   const int lane = threadIdx.x & 31;
   const int nchunks = a.long_meta[1];
@@ -400,14 +421,14 @@ __global__ void __launch_bounds__(256) seg_long_chunks_kernel(SegArgs a) {
   const int d = a.d;
   for (int c = warp; c < nchunks; c += nwarps) {
     int seg = a.long_work[2 * c], k = a.long_work[2 * c + 1];
-    int beg = a.seg_start[seg] + k * kSegChunk;
-    int end = min(a.seg_start[seg + 1], beg + kSegChunk);
+    int beg = a.seg_start[seg] + k * a.seg_chunk;
+    int end = min(a.seg_start[seg + 1], beg + a.seg_chunk);
     float acc[MAXC][VEC];
 #pragma unroll
     for (int cc = 0; cc < MAXC; ++cc)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[cc][v] = 0.f;
-    accumulate_rows<VEC, MAXC>(a, beg, end, lane, acc);
+    accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
     float *dst = a.partials + (int64_t)c * d;
 #pragma unroll
     for (int cc = 0; cc < MAXC; ++cc) {
@@ -476,20 +497,21 @@ __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
   }
 }
 
-template <int VEC, int MAXC>
-static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
+template <int VEC, int MAXC, int BATCH>
+static void launch_seg_reduce_b(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
   const bool spec = update && a.spec_logd > 0;
   size_t sm1 = spec ? spec_smem_bytes(a.d, 8) : 0;
   if (update) {
     if (sm1 > 48 * 1024)
-      cudaFuncSetAttribute(seg_reduce_kernel<VEC, MAXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-    seg_reduce_kernel<VEC, MAXC, true><<<blocks, 256, sm1, st>>>(a);
+      cudaFuncSetAttribute(seg_reduce_kernel<VEC, MAXC, true, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sm1);
+    seg_reduce_kernel<VEC, MAXC, true, BATCH><<<blocks, 256, sm1, st>>>(a);
   } else {
-    seg_reduce_kernel<VEC, MAXC, false><<<blocks, 256, 0, st>>>(a);
+    seg_reduce_kernel<VEC, MAXC, false, BATCH><<<blocks, 256, 0, st>>>(a);
   }
   int cb = (a.long_chunk_cap + 7) / 8;
   if (cb > kNumSMs * 8) cb = kNumSMs * 8;
-  seg_long_chunks_kernel<VEC, MAXC><<<cb, 256, 0, st>>>(a);
+  seg_long_chunks_kernel<VEC, MAXC, BATCH><<<cb, 256, 0, st>>>(a);
   int sb = a.long_seg_cap < kNumSMs * 4 ? a.long_seg_cap : kNumSMs * 4;
   size_t smem = (size_t)8 * a.d * sizeof(float) + (spec ? spec_smem_bytes(a.d, 8) : 0);
   if (update) {
@@ -500,6 +522,14 @@ static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStr
   } else {
     seg_long_finish_kernel<VEC, MAXC, false><<<sb, 256, smem, st>>>(a);
   }
+}
+
+template <int VEC, int MAXC>
+static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
+  // small minibatches (short chunks) are latency bound: more loads in flight per warp
+  constexpr int BIG = MAXC <= 2 ? 4 : (MAXC == 4 ? 2 : 1);
+  if (a.seg_chunk <= 32) launch_seg_reduce_b<VEC, MAXC, BIG>(a, update, blocks, st);
+  else launch_seg_reduce_b<VEC, MAXC, 1>(a, update, blocks, st);
 }
 
 template <int VEC>
@@ -524,6 +554,7 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
   if (rc) return rc;
   int64_t L = (int64_t)rm.nroles * P;
   SegArgs a;
+  a.seg_chunk = seg_chunk_for(L);
   a.long_seg_cap = (int)long_seg_cap(L);
   a.long_chunk_cap = (int)long_chunk_cap(L);
   a.long_meta = ar.take<int32_t>(4);

@@ -49,7 +49,7 @@ SIGNATURES = {
     'skge_tripleset_bytes': (_Z, [_L]),
     'skge_tripleset_build': (_I, [_P, _Z, _P, _P, _P, _L, _I, _P]),
     'skge_tripleset_contains': (_I, [_P, _Z, _P, _P, _P, _L, _P, _P]),
-    'skge_sample_corrupt': (_I, [_P, _Z, _P, _Z, _P, _P, _P, _P, _L, _I, _I, _L, _L, _I, _U64, _U64]
+    'skge_sample_corrupt': (_I, [_P, _Z, _P, _Z, _P, _P, _P, _P, _L, _I, _I, _L, _L, _I, _U64, _U64, _P]
                             + [_P] * 7 + [_P]),
     'skge_rank_make_queries': (_I, [_I, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F] + [_P] * 5 + [_P]),
     'skge_rank_sweep': (_I, [_I, _P, _L, _L, _I, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P]),

@@ -15,11 +15,15 @@ Two execution paths:
 import pickle
 import timeit
 
+import logging
+
 import numpy as np
 import torch
 
 from . import _ext, kernels
 from .param import Parameter, AdaGrad, SGD, post_code
+
+log = logging.getLogger('EX-KG')
 
 _DEF_NBATCHES = 100
 _DEF_POST_EPOCH = []
@@ -145,6 +149,49 @@ def _opt_code(pu):
     return None
 
 
+class _GraphedStep(object):
+    """Runs ``body(idx)`` -- one fused minibatch -- through a CUDA graph.
+
+    Minibatches of configs 1-4 are a few thousand pairs: ~16 short kernels whose launch gaps
+    dominate.  The first call for a given minibatch length runs eagerly (sizes the workspace),
+    the second is captured, later ones copy the new example indices into the static index
+    buffer and replay.  Everything the step reads besides ``idx`` lives at fixed addresses
+    (parameters, optimiser state, counters, the sampler's device-side Philox offset).  Any
+    capture failure falls back to eager launches."""
+
+    def __init__(self, body, enabled=True):
+        self.body, self.enabled, self.slots = body, enabled, {}
+
+    def __call__(self, batch):
+        B = batch.numel()
+        slot = self.slots.get(B)
+        if slot is None:
+            slot = self.slots[B] = dict(idx=torch.empty(B, dtype=torch.int32, device=batch.device), graph=None,
+                                        warm=0, launches=0)
+        slot['idx'].copy_(batch)
+        if slot['graph'] is not None:
+            slot['graph'].replay()
+            kernels.LAUNCHES['n'] += slot['launches']
+            return
+        if not self.enabled or slot['warm'] < 1:
+            self.body(slot['idx'])
+            slot['warm'] += 1
+            return
+        try:
+            n0 = kernels.LAUNCHES['n']
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.body(slot['idx'])
+            slot['launches'] = kernels.LAUNCHES['n'] - n0
+            slot['graph'] = g
+            g.replay()          # capturing records the work, it does not run it
+        except Exception as e:  # noqa: BLE001 -- e.g. a driver that refuses the capture
+            log.warning('CUDA graph capture failed (%s); continuing with eager launches', e)
+            self.enabled = False
+            torch.cuda.synchronize()
+            self.body(slot['idx'])
+
+
 class StochasticTrainer(object):
     """Stochastic gradient descent trainer with scalar (logistic) loss
     (skge/base.py:1195-1316).  Models implement ``_gradients(xys)``."""
@@ -162,6 +209,7 @@ class StochasticTrainer(object):
         self._updaters = {key: pu(param, self.learning_rate) for key, param in self.model.params.items()}
         self.seed = kwargs.pop('seed', 42)       # the reference seeds numpy with 42 at import
         self.fused = kwargs.pop('fused', True)   # set False to force the reference's hook path
+        self.cuda_graphs = kwargs.pop('cuda_graphs', True)   # replay fused minibatches as CUDA graphs
         self._gen = None
 
     def set_max_epochs(self, epoch):
@@ -352,29 +400,30 @@ class PairwiseStochasticTrainer(StochasticTrainer):
         sampler = self._device_sampler()
         sampler.ensure_device(xs)
         n = sampler.train_size()
-        state = {'calls': 0}
+        philox = torch.zeros(1, dtype=torch.int64, device=_ext.device())   # device-side draw counter
+        per_pos = sampler.n * len(sampler.modes)
 
-        def step(batch):
-            pos, neg, valid = sampler.device_sample(batch, batch.numel(), state['calls'])
-            state['calls'] += 1
+        def body(idx):
+            pos, neg, valid = sampler.device_sample(idx, idx.numel(), 0, offset_dev=philox)
+            philox.add_(idx.numel() * per_pos)
             self.model._fused_pair_step(self._updaters, pos, neg, valid, self._counts, self._nviol_dev)
 
-        self._run_epochs(n, step)
+        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs))
 
     def _fit_fused_supplied(self, n):
         self._setup_fused()
         P = torch.stack(_triples_to_device(self.pxs), 1)
         Nn = torch.stack(_triples_to_device(self.nxs), 1)
-        self._sup = [P, Nn]
+        self._sup = [P, Nn]       # shuffled IN PLACE every epoch (graph-captured steps keep the pointers)
 
-        def step(batch):
-            bl = batch.long()
+        def body(idx):
+            bl = idx.long()
             pp, nn = self._sup[0][bl], self._sup[1][bl]
             pos = tuple(pp[:, i].contiguous() for i in range(3))
             neg = tuple(nn[:, i].contiguous() for i in range(3))
             self.model._fused_pair_step(self._updaters, pos, neg, None, self._counts, self._nviol_dev)
 
-        self._run_epochs(n, step)
+        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs))
 
     def _pre_epoch(self):
         self.nviolations = 0
@@ -383,7 +432,8 @@ class PairwiseStochasticTrainer(StochasticTrainer):
         if self.samplef is None:
             if getattr(self, '_sup', None) is not None:
                 # independent shuffles of positives and negatives (skge/base.py:1390-1392)
-                self._sup = [t[self._randperm(t.shape[0])] for t in self._sup]
+                for t in self._sup:
+                    t.copy_(t[self._randperm(t.shape[0])])
             else:
                 rng = np.random.RandomState(self.seed + getattr(self, 'epoch', 0))
                 rng.shuffle(self.pxs)

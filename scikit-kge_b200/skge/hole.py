@@ -1,5 +1,6 @@
 """HolE on the device (reference: skge/hole.py)."""
 import numpy as np
+import torch
 
 from . import _ext, kernels
 from . import actfun as af
@@ -65,12 +66,15 @@ class HolE(Model):
         spectra of E and R that the spectral step reads and keeps current."""
         d = self.ncomp
         if self.spectral and d >= 32 and d <= 1024 and (d & (d - 1)) == 0:
-            self._spec = (kernels.hole_spectra(self.E.data), kernels.hole_spectra(self.R.data))
+            old = getattr(self, '_spec', None)      # refresh in place: captured graphs keep the pointers
+            if old is None or old[0].shape != self.E.data.shape or old[0].device != self.E.data.device:
+                old = (torch.empty_like(self.E.data), torch.empty_like(self.R.data))
+            self._spec = (kernels.hole_spectra(self.E.data, out=old[0]), kernels.hole_spectra(self.R.data, out=old[1]))
         else:
             self._spec = None
 
     def _end_fused(self):
-        self._spec = None
+        self._spec_keep, self._spec = getattr(self, '_spec', None), None
 
     def _fused_pair_step(self, updaters, pos, neg, valid, counts, nviol_accum):
         opt, lr, p2E, p2R = updater_args(updaters, 'E', 'R')

@@ -95,9 +95,10 @@ def pair_step(model, E, R, p2E, p2R, pos, neg, valid, margin, l1_or_af, rparam, 
                                         ptr(nviol_accum), ptr(ucE), ptr(ucR), ptr(ws), ws.numel(), stream()))
 
 
-def hole_spectra(X):
+def hole_spectra(X, out=None):
     """Packed spectra of the rows of X (power-of-two d), see csrc/fft.cuh."""
-    out = torch.empty_like(X)
+    if out is None:
+        out = torch.empty_like(X)
     _count('scores')
     check(lib().skge_hole_spectra(ptr(X), X.shape[0], X.shape[1], ptr(out), stream()))
     return out
@@ -173,10 +174,11 @@ class TripleSet(object):
                                             ptr(out), stream()))
         return out
 
-    def sample(self, batch_idx, B, n_per, modes_mask, ntries, seed, offset, src=None):
+    def sample(self, batch_idx, B, n_per, modes_mask, ntries, seed, offset, src=None, offset_dev=None):
         """Returns (pos, neg, valid): pos/neg are (s, o, p) int32 tensors of
         B * n_per * nmodes pairs.  ``src`` overrides the (s, o, p) arrays the
-        positives are read from (default: the training arrays)."""
+        positives are read from (default: the training arrays).  ``offset_dev`` (int64
+        CUDA scalar, optional) is added to the Philox counter on the device."""
         s, o, p = src if src is not None else (self.s, self.o, self.p)
         nm = bin(modes_mask & 7).count('1')
         n = B * n_per * nm
@@ -186,8 +188,8 @@ class TripleSet(object):
         check(lib().skge_sample_corrupt(ptr(self.table), self.table.numel(), ptr(self.sp_table),
                                         self.sp_table.numel() if self.sp_table is not None else 0, ptr(s), ptr(o),
                                         ptr(p), ptr(batch_idx), B, n_per, modes_mask, self.N, self.M, ntries,
-                                        seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), *[ptr(t) for t in outs],
-                                        ptr(valid), stream()))
+                                        seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), ptr(offset_dev),
+                                        *[ptr(t) for t in outs], ptr(valid), stream()))
         return tuple(outs[:3]), tuple(outs[3:]), valid
 
 
