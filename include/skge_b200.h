@@ -135,33 +135,34 @@ SKGE_API int skge_hole_pair_step_spectral(float *E, float *R, float *Ehat, float
 
 /* ---- logistic minibatch: Model._gradients + _batch_step ---------------- */
 /*
- * n labelled examples (s, o, p, y = +-1).  loss (device double, nullable) is
- * SET to sum logaddexp(0, -y*score) (skge/hole.py:26, skge/rescal.py:52);
- * loss_accum (nullable) += that value.  counts = {n, U_E, U_second, 0}.
+ * n labelled examples (s, o, p, y = +-1); `valid` (nullable, uint8[n]) masks examples the
+ * sampler could not produce (the reference never appends those).  loss (device double,
+ * nullable) is SET to sum logaddexp(0, -y*score) (skge/hole.py:26, skge/rescal.py:52);
+ * loss_accum (nullable) += that value.  counts = {valid examples, U_E, U_second, 0}.
  */
 SKGE_API size_t skge_logistic_workspace_bytes(int model, int64_t n, int d, int64_t N, int64_t M);
 
 /* skge/hole.py:22-42 */
 SKGE_API int skge_hole_logistic_grads(const float *E, const float *R, const int32_t *s, const int32_t *o,
-                             const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
-                             int d, float rparam, float *ge, int32_t *eidx, float *gr,
+                             const int32_t *p, const float *y, const uint8_t *valid, int64_t n, int64_t N,
+                             int64_t M, int d, float rparam, float *ge, int32_t *eidx, float *gr,
                              int32_t *ridx, int32_t *counts, double *loss, void *ws,
                              size_t ws_bytes, skge_stream_t stream);
 SKGE_API int skge_hole_logistic_step(float *E, float *R, float *p2E, float *p2R, const int32_t *s,
-                            const int32_t *o, const int32_t *p, const float *y, int64_t n,
-                            int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                            const int32_t *o, const int32_t *p, const float *y, const uint8_t *valid,
+                            int64_t n, int64_t N, int64_t M, int d, float rparam, int opt, float lr,
                             int postE, int postR, int32_t *counts, double *loss_accum,
                             int32_t *upd_counts_E, int32_t *upd_counts_R, void *ws,
                             size_t ws_bytes, skge_stream_t stream);
 /* skge/rescal.py:37-76 ; gw[U_W][d][d], pidx ascending */
 SKGE_API int skge_rescal_logistic_grads(const float *E, const float *W, const int32_t *s, const int32_t *o,
-                               const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
-                               int d, float rparam, float *ge, int32_t *eidx, float *gw,
+                               const int32_t *p, const float *y, const uint8_t *valid, int64_t n, int64_t N,
+                               int64_t M, int d, float rparam, float *ge, int32_t *eidx, float *gw,
                                int32_t *pidx, int32_t *counts, double *loss, void *ws,
                                size_t ws_bytes, skge_stream_t stream);
 SKGE_API int skge_rescal_logistic_step(float *E, float *W, float *p2E, float *p2W, const int32_t *s,
-                              const int32_t *o, const int32_t *p, const float *y, int64_t n,
-                              int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                              const int32_t *o, const int32_t *p, const float *y, const uint8_t *valid,
+                              int64_t n, int64_t N, int64_t M, int d, float rparam, int opt, float lr,
                               int postE, int postW, int32_t *counts, double *loss_accum,
                               int32_t *upd_counts_E, int32_t *upd_counts_W, void *ws,
                               size_t ws_bytes, skge_stream_t stream);

@@ -20,13 +20,17 @@ __device__ __forceinline__ void logistic_terms(float y, float raw, float *loss, 
 //   G[i][0] = fs ccorr(R[p],E[o]) -> s   G[i][1] = fs cconv(E[s],R[p]) -> o   G[i][2] = fs ccorr(E[s],E[o]) -> p
 __global__ void hole_logistic_kernel(const float *__restrict__ E, const float *__restrict__ R,
                                      const int32_t *__restrict__ s, const int32_t *__restrict__ o,
-                                     const int32_t *__restrict__ p, const float *__restrict__ y, int64_t n,
-                                     int d, float *__restrict__ G, double *__restrict__ loss,
-                                     double *__restrict__ loss_accum) {
+                                     const int32_t *__restrict__ p, const float *__restrict__ y,
+                                     const uint8_t *__restrict__ valid, int64_t n, int d, float *__restrict__ G,
+                                     double *__restrict__ loss, double *__restrict__ loss_accum,
+                                     int32_t *__restrict__ counts) {
   extern __shared__ float sm[];
   float *es = sm, *rp = es + d, *o2 = rp + d, *rr = o2 + 2 * d, *red = rr + 2 * d;
   double lsum = 0.0;
+  int nvalid = 0;
   for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    if (valid && !valid[i]) continue;   // a negative the sampler could not produce (skge/sample.py:22-24)
+    ++nvalid;
     __syncthreads();
     const float *rg = R + (int64_t)p[i] * d;
     smem_load(es, E + (int64_t)s[i] * d, d);
@@ -47,9 +51,10 @@ __global__ void hole_logistic_kernel(const float *__restrict__ E, const float *_
       g[2 * d + k] = fs * cso;
     }
   }
-  if (threadIdx.x == 0 && lsum != 0.0) {
+  if (threadIdx.x == 0 && nvalid) {
     if (loss) atomicAdd(loss, lsum);
     if (loss_accum) atomicAdd(loss_accum, lsum);
+    atomicAdd(counts, nvalid);
   }
 }
 
@@ -58,14 +63,18 @@ __global__ void hole_logistic_kernel(const float *__restrict__ E, const float *_
 //   G[i][0] = fs * WE -> s     G[i][1] = fs * EW -> o        (skge/rescal.py:72-73)
 __global__ void rescal_logistic_kernel(const float *__restrict__ E, const float *__restrict__ W,
                                        const int32_t *__restrict__ s, const int32_t *__restrict__ o,
-                                       const int32_t *__restrict__ p, const float *__restrict__ y, int64_t n,
-                                       int d, float *__restrict__ G, float *__restrict__ fsv,
-                                       double *__restrict__ loss, double *__restrict__ loss_accum) {
+                                       const int32_t *__restrict__ p, const float *__restrict__ y,
+                                       const uint8_t *__restrict__ valid, int64_t n, int d,
+                                       float *__restrict__ G, float *__restrict__ fsv, double *__restrict__ loss,
+                                       double *__restrict__ loss_accum, int32_t *__restrict__ counts) {
   extern __shared__ float sm[];
   float *es = sm, *eo = es + d, *we = eo + d, *red = we + d;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   double lsum = 0.0;
+  int nvalid = 0;
   for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    if (valid && !valid[i]) continue;
+    ++nvalid;
     __syncthreads();
     smem_load(es, E + (int64_t)s[i] * d, d);
     smem_load(eo, E + (int64_t)o[i] * d, d);
@@ -103,28 +112,34 @@ __global__ void rescal_logistic_kernel(const float *__restrict__ E, const float 
     }
     if (threadIdx.x == 0) fsv[i] = fs;
   }
-  if (threadIdx.x == 0 && lsum != 0.0) {
+  if (threadIdx.x == 0 && nvalid) {
     if (loss) atomicAdd(loss, lsum);
     if (loss_accum) atomicAdd(loss_accum, lsum);
+    atomicAdd(counts, nvalid);
   }
 }
 
 // gw[u] = mean_{i in relation u} fs_i E[s_i] E[o_i]^T + rparam W[p_u]   (skge/rescal.py:61-70)
-// grid = (tiles_b, tiles_a, max segments); 32x32 output tile per CTA, 256 threads x 4 outputs.
-__global__ void __launch_bounds__(256) rescal_gw_kernel(const float *__restrict__ E, const float *__restrict__ W,
-                                                        const int32_t *__restrict__ s,
-                                                        const int32_t *__restrict__ o,
-                                                        const float *__restrict__ fsv, SegLists sl, int d,
-                                                        float rparam, float *__restrict__ gw,
-                                                        int32_t *__restrict__ pidx, int32_t *__restrict__ counts) {
+// A frequent relation owns a large share of the minibatch, so its examples are cut into
+// kGwSlices slices reduced by different CTAs into partial sums (pass 1, grid = (tiles_b,
+// tiles_a, segments * slices); 32x32 output tile per CTA, 256 threads x 4 outputs); pass 2
+// adds the slices in a fixed order, takes the mean and adds the regulariser.
+static constexpr int kGwSlices = 8;
+
+__global__ void __launch_bounds__(256) rescal_gw_partial_kernel(const float *__restrict__ E,
+                                                                const int32_t *__restrict__ s,
+                                                                const int32_t *__restrict__ o,
+                                                                const float *__restrict__ fsv, SegLists sl, int d,
+                                                                float *__restrict__ part, int maxseg) {
   __shared__ float ts[32][33], to[32][33], tf[32];
   const int nseg = sl.meta[0];
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && counts) counts[2] = nseg;
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty in 0..7, rows ty, ty+8, ty+16, ty+24
-  for (int seg = blockIdx.z; seg < nseg; seg += gridDim.z) {
-    int beg = sl.seg_start[seg], end = sl.seg_start[seg + 1];
-    int rel = sl.seg_key[seg];
+  for (int item = blockIdx.z; item < nseg * kGwSlices; item += gridDim.z) {
+    const int seg = item / kGwSlices, slice = item - seg * kGwSlices;
+    const int sbeg = sl.seg_start[seg], len = sl.seg_start[seg + 1] - sbeg;
+    const int beg = sbeg + (int)((int64_t)len * slice / kGwSlices);
+    const int end = sbeg + (int)((int64_t)len * (slice + 1) / kGwSlices);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j0 = beg; j0 < end; j0 += 32) {
       int cnt = min(32, end - j0);
@@ -148,17 +163,34 @@ __global__ void __launch_bounds__(256) rescal_gw_kernel(const float *__restrict_
         for (int q = 0; q < 4; ++q) acc[q] = fmaf(ts[e][ty + 8 * q], fo, acc[q]);
       }
     }
-    float inv = 1.0f / (float)(end - beg);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       int a = a0 + ty + 8 * q, b = b0 + tx;
-      if (a < d && b < d) {
-        float v = acc[q] * inv;
-        if (rparam != 0.f) v += rparam * __ldg(W + ((int64_t)rel * d + a) * d + b);
-        gw[((int64_t)seg * d + a) * d + b] = v;
-      }
+      if (a < d && b < d) part[(((int64_t)slice * maxseg + seg) * d + a) * d + b] = acc[q];
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) pidx[seg] = rel;
+  }
+}
+
+__global__ void __launch_bounds__(256) rescal_gw_finish_kernel(const float *__restrict__ W, SegLists sl, int d,
+                                                               float rparam, const float *__restrict__ part,
+                                                               int maxseg, float *__restrict__ gw,
+                                                               int32_t *__restrict__ pidx,
+                                                               int32_t *__restrict__ counts) {
+  const int nseg = sl.meta[0];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && counts) counts[2] = nseg;
+  const int64_t dd = (int64_t)d * d;
+  for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
+    const int rel = sl.seg_key[seg];
+    const float inv = 1.0f / (float)(sl.seg_start[seg + 1] - sl.seg_start[seg]);
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < dd; c += (int64_t)gridDim.x * blockDim.x) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < kGwSlices; ++k) v += part[((int64_t)k * maxseg + seg) * dd + c];
+      v *= inv;
+      if (rparam != 0.f) v += rparam * __ldg(W + (int64_t)rel * dd + c);
+      gw[(int64_t)seg * dd + c] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) pidx[seg] = rel;
   }
 }
 
@@ -178,12 +210,13 @@ static size_t logistic_ws_bytes(int model, int64_t n, int d, int64_t M) {
     b += seg_workspace_bytes(n, 0);                               // relation grouping
     b += align_up((size_t)uw * d * d * sizeof(float));            // gw (step mode)
     b += align_up((size_t)uw * sizeof(int32_t));                  // pidx (step mode)
+    b += align_up((size_t)kGwSlices * uw * d * d * sizeof(float));  // per-slice partial sums of gw
   }
   return b + 1024;
 }
 
 static int hole_logistic_run(float *E, float *R, float *p2E, float *p2R, const int32_t *s, const int32_t *o,
-                             const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M, int d,
+                             const int32_t *p, const float *y, const uint8_t *valid, int64_t n, int64_t N, int64_t M, int d,
                              float rparam, bool update, int opt, float lr, int postE, int postR, float *ge,
                              int32_t *eidx, float *gr, int32_t *ridx, int32_t *counts, double *loss,
                              double *loss_accum, int32_t *ucE, int32_t *ucR, void *ws, size_t ws_bytes,
@@ -203,9 +236,9 @@ static int hole_logistic_run(float *E, float *R, float *p2E, float *p2R, const i
   size_t smem = (6 * (size_t)d + 40) * sizeof(float);
   SKGE_CUDA(cudaFuncSetAttribute(hole_logistic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = n > kNumSMs * 16 ? kNumSMs * 16 : n;
-  hole_logistic_kernel<<<(int)blocks, block_threads(d), smem, st>>>(E, R, s, o, p, y, n, d, G, loss, loss_accum);
+  hole_logistic_kernel<<<(int)blocks, block_threads(d), smem, st>>>(E, R, s, o, p, y, valid, n, d, G, loss,
+                                                                    loss_accum, counts);
   SKGE_LAUNCH_CHECK();
-  if (int rc0 = set_i32(counts, (int32_t)n, st)) return rc0;
   RoleMap rm;
   const int32_t *idx[3] = {s, o, p};  // entity keys ss+os, relation keys ps: hole.py:31-39
   for (int r = 0; r < 3; ++r) { rm.idx[r] = idx[r]; rm.is_rel[r] = r == 2; rm.grow[r] = r; rm.gsign[r] = 1.f; }
@@ -213,7 +246,7 @@ static int hole_logistic_run(float *E, float *R, float *p2E, float *p2R, const i
   ParamDesc pd[2];
   pd[0] = ParamDesc{E, p2E, postE, rparam, ucE, ge, eidx};
   pd[1] = ParamDesc{R, p2R, postR, rparam, ucR, gr, ridx};
-  return seg_run(rm, nullptr, n, N, M, d, G, 3, pd, update, opt, lr, counts, ar, st);
+  return seg_run(rm, valid, n, N, M, d, G, 3, pd, update, opt, lr, counts, ar, st);
 }
 
 // sparse update whose row count lives on the device: run over the maximum and
@@ -244,7 +277,7 @@ __global__ void __launch_bounds__(256) rescal_w_update_kernel(float *W, float *p
 }
 
 static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const int32_t *s, const int32_t *o,
-                               const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M, int d,
+                               const int32_t *p, const float *y, const uint8_t *valid, int64_t n, int64_t N, int64_t M, int d,
                                float rparam, bool update, int opt, float lr, int postE, int postW, float *ge,
                                int32_t *eidx, float *gw, int32_t *pidx, int32_t *counts, double *loss,
                                double *loss_accum, int32_t *ucE, int32_t *ucW, void *ws, size_t ws_bytes,
@@ -262,6 +295,7 @@ static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const
     gw = ar.take<float>((size_t)uw * d * d);
     pidx = ar.take<int32_t>(uw);
   }
+  float *gw_part = ar.take<float>((size_t)kGwSlices * uw * d * d);
   if (!ar.ok()) {
     set_error("workspace too small");
     return SKGE_EWORKSPACE;
@@ -273,18 +307,23 @@ static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const
   SKGE_REQUIRE(threads * 4 >= d, "d too large");
   size_t smem = (3 * (size_t)d + 40) * sizeof(float);
   int64_t blocks = n > kNumSMs * 16 ? kNumSMs * 16 : n;
-  rescal_logistic_kernel<<<(int)blocks, threads, smem, st>>>(E, W, s, o, p, y, n, d, G, fsv, loss, loss_accum);
+  rescal_logistic_kernel<<<(int)blocks, threads, smem, st>>>(E, W, s, o, p, y, valid, n, d, G, fsv, loss, loss_accum,
+                                                             counts);
   SKGE_LAUNCH_CHECK();
-  if (int rc0 = set_i32(counts, (int32_t)n, st)) return rc0;
   // group examples by relation, then the per-relation outer-product mean (reads the OLD E)
   RoleMap rmw;
   rmw.idx[0] = p; rmw.is_rel[0] = 0; rmw.grow[0] = 0; rmw.gsign[0] = 1.f; rmw.nroles = 1;
   SegLists sl;
-  int rc = seg_build(rmw, nullptr, n, M, 0, ar, st, &sl);
+  int rc = seg_build(rmw, valid, n, M, 0, ar, st, &sl);
   if (rc) return rc;
   int tiles = (d + 31) / 32;
-  dim3 grid(tiles, tiles, (unsigned)(uw > 65535 ? 65535 : uw));
-  rescal_gw_kernel<<<grid, 256, 0, st>>>(E, W, s, o, fsv, sl, d, rparam, gw, pidx, counts);
+  int64_t items = uw * kGwSlices;
+  dim3 grid(tiles, tiles, (unsigned)(items > 65535 ? 65535 : items));
+  rescal_gw_partial_kernel<<<grid, 256, 0, st>>>(E, s, o, fsv, sl, d, gw_part, (int)uw);
+  SKGE_LAUNCH_CHECK();
+  int64_t dd = (int64_t)d * d;
+  dim3 gridf((unsigned)((dd + 255) / 256 > 64 ? 64 : (dd + 255) / 256), (unsigned)(uw > 65535 ? 65535 : uw));
+  rescal_gw_finish_kernel<<<gridf, 256, 0, st>>>(W, sl, d, rparam, gw_part, (int)uw, gw, pidx, counts);
   SKGE_LAUNCH_CHECK();
   // entity rows: keys ss+os get (fs*WE, fs*EW): rescal.py:72-74
   RoleMap rm;
@@ -301,7 +340,7 @@ static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const
     set_error("workspace too small");
     return SKGE_EWORKSPACE;
   }
-  rc = seg_run(rm, nullptr, n, N, 1, d, G, 2, pd, update, opt, lr, scratch, ar, st);
+  rc = seg_run(rm, valid, n, N, 1, d, G, 2, pd, update, opt, lr, scratch, ar, st);
   if (rc) return rc;
   SKGE_CUDA(cudaMemcpyAsync(counts_e + 1, scratch + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   if (update) {
@@ -327,44 +366,44 @@ size_t skge_logistic_workspace_bytes(int model, int64_t n, int d, int64_t N, int
 }
 
 int skge_hole_logistic_grads(const float *E, const float *R, const int32_t *s, const int32_t *o,
-                             const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
-                             int d, float rparam, float *ge, int32_t *eidx, float *gr,
+                             const int32_t *p, const float *y, const uint8_t *valid, int64_t n, int64_t N,
+                             int64_t M, int d, float rparam, float *ge, int32_t *eidx, float *gr,
                              int32_t *ridx, int32_t *counts, double *loss, void *ws,
                              size_t ws_bytes, skge_stream_t stream) {
-  return hole_logistic_run(const_cast<float *>(E), const_cast<float *>(R), nullptr, nullptr, s, o, p, y, n, N,
+  return hole_logistic_run(const_cast<float *>(E), const_cast<float *>(R), nullptr, nullptr, s, o, p, y, valid, n, N,
                            M, d, rparam, false, SKGE_OPT_SGD, 0.f, SKGE_POST_NONE, SKGE_POST_NONE, ge, eidx,
                            gr, ridx, counts, loss, nullptr, nullptr, nullptr, ws, ws_bytes, as_stream(stream));
 }
 
 int skge_hole_logistic_step(float *E, float *R, float *p2E, float *p2R, const int32_t *s,
-                            const int32_t *o, const int32_t *p, const float *y, int64_t n,
-                            int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                            const int32_t *o, const int32_t *p, const float *y, const uint8_t *valid,
+                            int64_t n, int64_t N, int64_t M, int d, float rparam, int opt, float lr,
                             int postE, int postR, int32_t *counts, double *loss_accum,
                             int32_t *upd_counts_E, int32_t *upd_counts_R, void *ws,
                             size_t ws_bytes, skge_stream_t stream) {
-  return hole_logistic_run(E, R, p2E, p2R, s, o, p, y, n, N, M, d, rparam, true, opt, lr, postE, postR,
+  return hole_logistic_run(E, R, p2E, p2R, s, o, p, y, valid, n, N, M, d, rparam, true, opt, lr, postE, postR,
                            nullptr, nullptr, nullptr, nullptr, counts, nullptr, loss_accum, upd_counts_E,
                            upd_counts_R, ws, ws_bytes, as_stream(stream));
 }
 
 int skge_rescal_logistic_grads(const float *E, const float *W, const int32_t *s, const int32_t *o,
-                               const int32_t *p, const float *y, int64_t n, int64_t N, int64_t M,
-                               int d, float rparam, float *ge, int32_t *eidx, float *gw,
+                               const int32_t *p, const float *y, const uint8_t *valid, int64_t n, int64_t N,
+                               int64_t M, int d, float rparam, float *ge, int32_t *eidx, float *gw,
                                int32_t *pidx, int32_t *counts, double *loss, void *ws,
                                size_t ws_bytes, skge_stream_t stream) {
-  return rescal_logistic_run(const_cast<float *>(E), const_cast<float *>(W), nullptr, nullptr, s, o, p, y, n,
+  return rescal_logistic_run(const_cast<float *>(E), const_cast<float *>(W), nullptr, nullptr, s, o, p, y, valid, n,
                              N, M, d, rparam, false, SKGE_OPT_SGD, 0.f, SKGE_POST_NONE, SKGE_POST_NONE, ge,
                              eidx, gw, pidx, counts, loss, nullptr, nullptr, nullptr, ws, ws_bytes,
                              as_stream(stream));
 }
 
 int skge_rescal_logistic_step(float *E, float *W, float *p2E, float *p2W, const int32_t *s,
-                              const int32_t *o, const int32_t *p, const float *y, int64_t n,
-                              int64_t N, int64_t M, int d, float rparam, int opt, float lr,
+                              const int32_t *o, const int32_t *p, const float *y, const uint8_t *valid,
+                              int64_t n, int64_t N, int64_t M, int d, float rparam, int opt, float lr,
                               int postE, int postW, int32_t *counts, double *loss_accum,
                               int32_t *upd_counts_E, int32_t *upd_counts_W, void *ws,
                               size_t ws_bytes, skge_stream_t stream) {
-  return rescal_logistic_run(E, W, p2E, p2W, s, o, p, y, n, N, M, d, rparam, true, opt, lr, postE, postW,
+  return rescal_logistic_run(E, W, p2E, p2W, s, o, p, y, valid, n, N, M, d, rparam, true, opt, lr, postE, postW,
                              nullptr, nullptr, nullptr, nullptr, counts, nullptr, loss_accum, upd_counts_E,
                              upd_counts_W, ws, ws_bytes, as_stream(stream));
 }

@@ -40,10 +40,10 @@ SIGNATURES = {
     'skge_hole_pair_step_spectral': (_I, [_P] * 6 + [_P] * 7 + [_L, _L, _L, _I, _I, _F, _F, _I, _F, _I, _I] + [_P] * 4
                                      + [_P, _Z, _P]),
     'skge_logistic_workspace_bytes': (_Z, [_I, _L, _I, _L, _L]),
-    'skge_hole_logistic_grads': (_I, [_P] * 6 + [_L, _L, _L, _I, _F] + [_P] * 6 + [_P, _Z, _P]),
-    'skge_hole_logistic_step': (_I, [_P] * 8 + [_L, _L, _L, _I, _F, _I, _F, _I, _I] + [_P] * 4 + [_P, _Z, _P]),
-    'skge_rescal_logistic_grads': (_I, [_P] * 6 + [_L, _L, _L, _I, _F] + [_P] * 6 + [_P, _Z, _P]),
-    'skge_rescal_logistic_step': (_I, [_P] * 8 + [_L, _L, _L, _I, _F, _I, _F, _I, _I] + [_P] * 4 + [_P, _Z, _P]),
+    'skge_hole_logistic_grads': (_I, [_P] * 7 + [_L, _L, _L, _I, _F] + [_P] * 6 + [_P, _Z, _P]),
+    'skge_hole_logistic_step': (_I, [_P] * 9 + [_L, _L, _L, _I, _F, _I, _F, _I, _I] + [_P] * 4 + [_P, _Z, _P]),
+    'skge_rescal_logistic_grads': (_I, [_P] * 7 + [_L, _L, _L, _I, _F] + [_P] * 6 + [_P, _Z, _P]),
+    'skge_rescal_logistic_step': (_I, [_P] * 9 + [_L, _L, _L, _I, _F, _I, _F, _I, _I] + [_P] * 4 + [_P, _Z, _P]),
     'skge_sparse_update': (_I, [_P, _P, _P, _P, _L, _L, _I, _F, _I, _P, _P]),
     'skge_rows_post': (_I, [_P, _P, _L, _L, _I, _P]),
     'skge_tripleset_bytes': (_Z, [_L]),

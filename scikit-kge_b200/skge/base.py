@@ -303,23 +303,25 @@ class StochasticTrainer(object):
         self._loss_dev = torch.zeros(1, dtype=torch.float64, device=dev)
         self._counts = torch.zeros(4, dtype=torch.int32, device=dev)
         sampler = self._device_sampler() if self.samplef is not None else None
-        state = {'calls': 0}
+        philox = torch.zeros(1, dtype=torch.int64, device=dev)
+        per_pos = sampler.n * len(sampler.modes) if sampler is not None else 0
 
-        def step(batch):
-            bl = batch.long()
+        def body(idx):
+            bl = idx.long()
             bs, bo, bp, by = s[bl], o[bl], p[bl], y[bl]
+            valid = None
             if sampler is not None:
-                _, neg, valid = sampler.device_sample(None, batch.numel(), state['calls'], src=(bs, bo, bp))
-                state['calls'] += 1
-                keep = valid.bool()
-                bs = torch.cat([bs, neg[0][keep]])
-                bo = torch.cat([bo, neg[1][keep]])
-                bp = torch.cat([bp, neg[2][keep]])
-                by = torch.cat([by, torch.full((int(keep.sum()),), -1.0, device=dev)])
+                # xys += samplef(xys): positives, then their negatives labelled -1 (skge/base.py:1295-1296);
+                # negatives that exhausted their tries are masked out instead of compacted (no host sync)
+                _, neg, ok = sampler.device_sample(None, idx.numel(), 0, src=(bs, bo, bp), offset_dev=philox)
+                philox.add_(idx.numel() * per_pos)
+                bs, bo, bp = torch.cat([bs, neg[0]]), torch.cat([bo, neg[1]]), torch.cat([bp, neg[2]])
+                by = torch.cat([by, torch.full((neg[0].numel(),), -1.0, device=dev)])
+                valid = torch.cat([torch.ones(idx.numel(), dtype=torch.uint8, device=dev), ok])
             self.model._fused_logistic_step(self._updaters, bs.contiguous(), bo.contiguous(), bp.contiguous(),
-                                            by.contiguous(), self._counts, self._loss_dev)
+                                            by.contiguous(), self._counts, self._loss_dev, valid=valid)
 
-        self._run_epochs(n, step)
+        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs))
 
     def _optim(self, xys):
         """Hook path: the reference's loop on host lists (skge/base.py:1242-1291)."""

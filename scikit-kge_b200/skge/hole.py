@@ -90,8 +90,8 @@ class HolE(Model):
                           af.af_code(self.af), self.rparam, opt, lr, post_code(self.E.post),
                           post_code(self.R.post), counts, nviol_accum, ucE=ucE, ucR=ucR)
 
-    def _fused_logistic_step(self, updaters, s, o, p, y, counts, loss_accum):
+    def _fused_logistic_step(self, updaters, s, o, p, y, counts, loss_accum, valid=None):
         opt, lr, p2E, p2R = updater_args(updaters, 'E', 'R')
         ucE, ucR = self._uc(opt)
         kernels.logistic_step(self.model_code, self.E.data, self.R.data, p2E, p2R, s, o, p, y, self.rparam, opt,
-                              lr, post_code(self.E.post), post_code(self.R.post), counts, loss_accum, ucE, ucR)
+                              lr, post_code(self.E.post), post_code(self.R.post), counts, loss_accum, ucE, ucR, valid=valid)

@@ -13,7 +13,7 @@ _ws = _ext.Workspace()
 # Number of libskge_b200 kernels launched so far (CUB sort/scan passes and memsets
 # are not counted): bench.py reports the delta over its timed region.
 LAUNCHES = {'n': 0}
-_OWN_KERNELS = {'scores': 1, 'pair': 5, 'logistic_hole': 5, 'logistic_rescal': 11, 'sample': 1, 'set': 1,
+_OWN_KERNELS = {'scores': 1, 'pair': 7, 'logistic_hole': 7, 'logistic_rescal': 13, 'sample': 1, 'set': 1,
                 'make_queries': 1, 'sweep': 1, 'rescore': 1, 'scores_one': 1, 'pack': 1, 'gemm': 1}
 
 
@@ -117,7 +117,7 @@ def hole_pair_step_spectral(E, R, Ehat, Rhat, p2E, p2R, pos, neg, valid, margin,
                                              stream()))
 
 
-def logistic_grads(model, E, R2, s, o, p, y, rparam):
+def logistic_grads(model, E, R2, s, o, p, y, rparam, valid=None):
     """Un-fused logistic gradients.  R2 is R (HolE) or W (RESCAL).
     Returns dict(loss, ge, eidx, g2, idx2)."""
     n, (N, d), M = s.numel(), E.shape, R2.shape[0]
@@ -128,12 +128,12 @@ def logistic_grads(model, E, R2, s, o, p, y, rparam):
     _count('logistic_hole' if model == HOLE else 'logistic_rescal')
     if model == HOLE:
         g2 = _f32(u2, d)
-        check(lib().skge_hole_logistic_grads(ptr(E), ptr(R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d,
+        check(lib().skge_hole_logistic_grads(ptr(E), ptr(R2), ptr(s), ptr(o), ptr(p), ptr(y), ptr(valid), n, N, M, d,
                                              float(rparam), ptr(ge), ptr(eidx), ptr(g2), ptr(idx2), ptr(counts),
                                              ptr(loss), ptr(ws), ws.numel(), stream()))
     else:
         g2 = _f32(u2, d, d)
-        check(lib().skge_rescal_logistic_grads(ptr(E), ptr(R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d,
+        check(lib().skge_rescal_logistic_grads(ptr(E), ptr(R2), ptr(s), ptr(o), ptr(p), ptr(y), ptr(valid), n, N, M, d,
                                                float(rparam), ptr(ge), ptr(eidx), ptr(g2), ptr(idx2), ptr(counts),
                                                ptr(loss), ptr(ws), ws.numel(), stream()))
     _, U_E, U_2, _ = counts.tolist()
@@ -141,12 +141,12 @@ def logistic_grads(model, E, R2, s, o, p, y, rparam):
 
 
 def logistic_step(model, E, R2, p2E, p2R2, s, o, p, y, rparam, opt, lr, postE, post2, counts, loss_accum,
-                  ucE=None, uc2=None):
+                  ucE=None, uc2=None, valid=None):
     n, (N, d), M = s.numel(), E.shape, R2.shape[0]
     ws = _ws.get(lib().skge_logistic_workspace_bytes(model, n, d, N, M))
     fn = lib().skge_hole_logistic_step if model == HOLE else lib().skge_rescal_logistic_step
     _count('logistic_hole' if model == HOLE else 'logistic_rescal')
-    check(fn(ptr(E), ptr(R2), ptr(p2E), ptr(p2R2), ptr(s), ptr(o), ptr(p), ptr(y), n, N, M, d, float(rparam), opt,
+    check(fn(ptr(E), ptr(R2), ptr(p2E), ptr(p2R2), ptr(s), ptr(o), ptr(p), ptr(y), ptr(valid), n, N, M, d, float(rparam), opt,
              float(lr), postE, post2, ptr(counts), ptr(loss_accum), ptr(ucE), ptr(uc2), ptr(ws), ws.numel(),
              stream()))
 

@@ -47,9 +47,9 @@ class RESCAL(Model):
         raise NotImplementedError('RESCAL pairwise training is broken in the reference '
                                   '(skge/rescal.py:84) and not provided')
 
-    def _fused_logistic_step(self, updaters, s, o, p, y, counts, loss_accum):
+    def _fused_logistic_step(self, updaters, s, o, p, y, counts, loss_accum, valid=None):
         opt, lr, p2E, p2W = updater_args(updaters, 'E', 'W')
         tc = self.track_counters and opt == _ext.OPT_ADAGRAD
         kernels.logistic_step(self.model_code, self.E.data, self.W.data, p2E, p2W, s, o, p, y, self.rparam, opt,
                               lr, post_code(self.E.post), post_code(self.W.post), counts, loss_accum,
-                              self.E._update_counts if tc else None, self.W._update_counts if tc else None)
+                              self.E._update_counts if tc else None, self.W._update_counts if tc else None, valid=valid)

@@ -199,6 +199,37 @@ def test_logistic_hooks_and_fused_match_reference_golden(golden, name):
             np.testing.assert_allclose(np.asarray(getattr(m, second)), g['P2_%d' % step], **tol)
 
 
+@pytest.mark.parametrize('name', ['hole_logistic_sgd_d150', 'rescal_logistic_sgd'])
+def test_logistic_step_skips_masked_examples(golden, name):
+    """Examples the sampler could not produce are masked, not compacted: the step must equal
+    the oracle's step on the valid subset (skge/sample.py:22-24, skge/base.py:1295-1304)."""
+    import skge
+    from skge._modelutil import idx_tensor
+    g = golden(name)
+    rescal = 'W0' in g
+    xs, ys = g['xs'], g['ys']
+    rng = np.random.default_rng(1)
+    keep = rng.random(len(xs)) < 0.7
+    m = make_model(g)
+    trn = skge.StochasticTrainer(m, nbatches=1, max_epochs=1, learning_rate=float(g['lr']), param_update=updater_cls(g))
+    trn._loss_dev = torch.zeros(1, dtype=torch.float64, device='cuda')
+    trn._counts = torch.zeros(4, dtype=torch.int32, device='cuda')
+    m._fused_logistic_step(trn._updaters, idx_tensor(xs[:, 0]), idx_tensor(xs[:, 1]), idx_tensor(xs[:, 2]),
+                           torch.tensor(ys, dtype=torch.float32, device='cuda'), trn._counts, trn._loss_dev,
+                           valid=torch.tensor(keep.astype(np.uint8), device='cuda'))
+    E, P2 = g['E0'].copy(), (g['W0'] if rescal else g['R0']).copy()
+    fn = orc.rescal_gradients if rescal else orc.hole_gradients
+    grads, loss = fn(E, P2, xs[keep], ys[keep], float(g['rparam']))
+    k2 = 'W' if rescal else 'R'
+    orc.sgd_update(E, grads['E'][0], grads['E'][1], float(g['lr']), None if rescal else 'normless1')
+    orc.sgd_update(P2, grads[k2][0], grads[k2][1], float(g['lr']), None)
+    n, ue, u2, _ = trn._counts.tolist()
+    assert n == int(keep.sum()) and ue == len(grads['E'][1]) and u2 == len(grads[k2][1])
+    assert float(trn._loss_dev.item()) == pytest.approx(loss, rel=1e-4)
+    np.testing.assert_allclose(np.asarray(m.E), E, **PARAM_TOL)
+    np.testing.assert_allclose(np.asarray(getattr(m, k2)), P2, **PARAM_TOL)
+
+
 def test_appendix_a_known_answers(golden):
     import skge
     g = golden('appendix_a')
