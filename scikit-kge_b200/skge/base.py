@@ -184,6 +184,9 @@ class _GraphedStep(object):
                 self.body(slot['idx'])
             slot['launches'] = kernels.LAUNCHES['n'] - n0
             slot['graph'] = g
+            # the captured kernels hold raw pointers into the shared scratch buffer: keep that very
+            # tensor alive even if a later, larger call makes the library wrapper allocate a new one
+            slot['keep'] = kernels._ws.buf
             g.replay()          # capturing records the work, it does not run it
         except Exception as e:  # noqa: BLE001 -- e.g. a driver that refuses the capture
             log.warning('CUDA graph capture failed (%s); continuing with eager launches', e)
