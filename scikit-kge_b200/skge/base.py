@@ -130,6 +130,16 @@ def loads_reference(data):
     return _RefUnpickler(io.BytesIO(data)).load()
 
 
+def _check_ids(xs, sz):
+    """Out-of-range ids would be an IndexError in the reference (fancy indexing); the kernels
+    do not bounds-check, so validate once per fit on the host."""
+    if sz is None or len(xs) == 0:
+        return
+    a = xs if isinstance(xs, np.ndarray) else np.asarray(xs, dtype=np.int64).reshape(-1, 3)
+    if a.min() < 0 or a[:, :2].max() >= sz[0] or a[:, 2].max() >= sz[2]:
+        raise IndexError('triple ids out of range for sz=%r' % (tuple(sz),))
+
+
 def _triples_to_device(xs):
     """list / array of (s, o, p) -> three int32 CUDA tensors (SoA)."""
     if isinstance(xs, torch.Tensor):
@@ -300,6 +310,7 @@ class StochasticTrainer(object):
 
     def _fit_fused(self, xs, ys):
         dev = _ext.device()
+        _check_ids(xs, getattr(self.model, 'sz', None))
         s, o, p = _triples_to_device(xs)
         y = _ext.as_f32(np.asarray(ys, dtype=np.float32))
         n = s.numel()
@@ -401,6 +412,7 @@ class PairwiseStochasticTrainer(StochasticTrainer):
         self._counts = torch.zeros(4, dtype=torch.int32, device=dev)
 
     def _fit_fused_sampled(self, xs):
+        _check_ids(xs, getattr(self.model, 'sz', None))
         self._setup_fused()
         sampler = self._device_sampler()
         sampler.ensure_device(xs)
@@ -416,6 +428,7 @@ class PairwiseStochasticTrainer(StochasticTrainer):
         self._run_epochs(n, _GraphedStep(body, self.cuda_graphs))
 
     def _fit_fused_supplied(self, n):
+        _check_ids(self.pxs + self.nxs, getattr(self.model, 'sz', None))
         self._setup_fused()
         P = torch.stack(_triples_to_device(self.pxs), 1)
         Nn = torch.stack(_triples_to_device(self.nxs), 1)

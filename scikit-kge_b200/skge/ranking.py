@@ -61,6 +61,9 @@ def build_filter_pairs(true_triples, kind, given, rel, target, device=None):
     (the reference writes -inf twice).  Returns int32 tensors (pair_q ascending,
     pair_e) on ``device``; torch ops only, so it runs on CPU or GPU."""
     dev = device if device is not None else torch.device('cpu')
+    if len(given) == 0:
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return z, z.clone()
     if isinstance(true_triples, torch.Tensor):
         tt = true_triples.to(device=dev, dtype=torch.int64).reshape(-1, 3)
     else:
@@ -219,6 +222,8 @@ class FilteredRankingEval(object):
         if self.model_code is None:
             raise NotImplementedError('derive from TransEEval / HolEEval / RESCALEval: the device ranking '
                                       'pass needs to know the model family (there is no host fallback)')
+        if self.sz == 0:
+            return {}, {}
         cnt = self.count_pass(mdl)
         raw, filt = ranks_from_counts(cnt)
         return regroup(self.test, raw.cpu().numpy(), filt.cpu().numpy())

@@ -158,3 +158,23 @@ def test_score_hooks_match_reference_scorers(golden):
             ev.prepare(m, p)
             np.testing.assert_allclose(ev.scores_o(m, s, p), so(s, p), rtol=1e-12, atol=1e-13)
             np.testing.assert_allclose(ev.scores_s(m, o, p), ss(o, p), rtol=1e-12, atol=1e-13)
+
+
+def test_ranking_edge_cases():
+    """Empty test set, queries without filter entries, duplicated true triples, a table whose
+    size is not a multiple of any tile, a single entity shard smaller than a tile."""
+    from skge.ranking import HolEEval, TransEEval
+    rng = np.random.default_rng(3)
+    N, M, d = 131, 2, 64
+    E0 = (rng.normal(size=(N, d)) * 0.3).astype(np.float32).astype(np.float64)
+    R0 = (rng.normal(size=(M, d)) * 0.3).astype(np.float32).astype(np.float64)
+    for kind, Ev in (('hole', HolEEval), ('transe', TransEEval)):
+        m = _model(kind, E0, R0)
+        assert Ev(np.zeros((0, 3), dtype=np.int64), [(0, 1, 0)]).positions(m) == ({}, {})
+        test = np.array([(5, 6, 0), (7, 8, 1), (5, 9, 0)])
+        true = np.array([(5, 6, 0), (5, 6, 0), (7, 8, 1), (5, 9, 0), (5, 9, 0), (100, 6, 0)])   # duplicates
+        got = Ev(test, true).positions(m)
+        assert got == orc.rank_positions(kind, E0, R0, test, true, tie='count')
+        ev = Ev(test, true)
+        acc = sum(ev.count_pass(m, world=(r, 8)) for r in range(8))      # 17-row shards
+        assert torch.equal(acc, ev.count_pass(m, world=(0, 1)))

@@ -219,3 +219,35 @@ def test_link_prediction_eval_auc():
     pr_auc, roc = LinkPredictionEval(xs, ys).scores(m)
     s, o, p = zip(*xs)
     assert roc == pytest.approx(roc_auc_score(ys, m._scores(s, p, o))) and 0.0 <= pr_auc <= 1.0
+
+
+def test_fused_step_with_nothing_to_update_and_bad_ids():
+    """A minibatch in which no pair violates leaves the parameters untouched (the reference
+    returns None and skips _batch_step, skge/base.py:1425-1427); a fully masked minibatch too;
+    out-of-range ids raise like the reference's fancy indexing would."""
+    import skge
+    from skge._modelutil import idx_tensor
+    for cls, d in ((skge.TransE, 16), (skge.HolE, 64), (skge.HolE, 20)):
+        m = cls((30, 30, 3), d)
+        trn = skge.PairwiseStochasticTrainer(m, nbatches=1, margin=-1e6, learning_rate=0.1)
+        trn._setup_fused()
+        if hasattr(m, '_prepare_fused'):
+            m._prepare_fused()
+        E0, R0 = np.asarray(m.E).copy(), np.asarray(m.R).copy()
+        rng = np.random.default_rng(0)
+        pos = tuple(idx_tensor(rng.integers(n, size=50)) for n in (30, 30, 3))
+        neg = tuple(idx_tensor(rng.integers(n, size=50)) for n in (30, 30, 3))
+        m._fused_pair_step(trn._updaters, pos, neg, None, trn._counts, trn._nviol_dev)
+        assert trn._counts.tolist()[:3] == [0, 0, 0] and int(trn._nviol_dev.item()) == 0
+        m.margin = 1e6          # everything would violate, but every pair is masked out
+        m._fused_pair_step(trn._updaters, pos, neg, torch.zeros(50, dtype=torch.uint8, device='cuda'),
+                           trn._counts, trn._nviol_dev)
+        assert trn._counts.tolist()[:3] == [0, 0, 0]
+        np.testing.assert_array_equal(np.asarray(m.E), E0)
+        np.testing.assert_array_equal(np.asarray(m.R), R0)
+    from skge.sample import RandomModeSampler
+    xs = [(0, 1, 0), (2, 31, 1)]
+    smp = RandomModeSampler(1, [0, 1], xs, (30, 30, 3))
+    trn = skge.PairwiseStochasticTrainer(skge.TransE((30, 30, 3), 8), nbatches=1, max_epochs=1, samplef=smp.sample)
+    with pytest.raises(IndexError):
+        trn.fit(xs, np.ones(2))
