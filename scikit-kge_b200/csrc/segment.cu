@@ -528,6 +528,7 @@ template <int VEC, int MAXC>
 static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
   // small minibatches (short chunks) are latency bound: more loads in flight per warp
   constexpr int BIG = MAXC <= 2 ? 4 : (MAXC == 4 ? 2 : 1);
+  // (2 loads in flight were measured slower than 1 on the large, bandwidth-bound minibatches)
   if (a.seg_chunk <= 32) launch_seg_reduce_b<VEC, MAXC, BIG>(a, update, blocks, st);
   else launch_seg_reduce_b<VEC, MAXC, 1>(a, update, blocks, st);
 }
