@@ -111,6 +111,10 @@ __device__ __forceinline__ void st_vec(float *p, const float (&v)[VEC]) {
   }
 }
 
+// AdaGrad's 1 / max(sqrt(p2), 1e-7) (skge/param.py:152-155) as one MUFU.RSQ (2 ulp) instead of
+// an IEEE sqrt followed by an IEEE division: the row update is issue-bound, not byte-bound.
+__device__ __forceinline__ float adagrad_rscale(float p2) { return fminf(rsqrtf(p2), 1e7f); }
+
 __device__ __forceinline__ float act_f(int af, float x) {
   switch (af) {
     case SKGE_AF_SIGMOID: return 1.0f / (1.0f + expf(-x));

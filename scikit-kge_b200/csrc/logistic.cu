@@ -148,14 +148,14 @@ __global__ void __launch_bounds__(256) rescal_gw_partial_kernel(const float *__r
         int e = t >> 5, c = t & 31;
         float vs = 0.f, vo = 0.f;
         if (e < cnt) {
-          int ex = sl.vals[j0 + e] >> 3;
+          int ex = sl.vals[j0 + e] >> 4;
           if (a0 + c < d) vs = __ldg(E + (int64_t)s[ex] * d + a0 + c);
           if (b0 + c < d) vo = __ldg(E + (int64_t)o[ex] * d + b0 + c);
         }
         ts[e][c] = vs;
         to[e][c] = vo;
       }
-      if (threadIdx.x < 32) tf[threadIdx.x] = threadIdx.x < cnt ? fsv[sl.vals[j0 + threadIdx.x] >> 3] : 0.f;
+      if (threadIdx.x < 32) tf[threadIdx.x] = threadIdx.x < cnt ? fsv[sl.vals[j0 + threadIdx.x] >> 4] : 0.f;
       __syncthreads();
       for (int e = 0; e < cnt; ++e) {
         float fo = tf[e] * to[e][tx];
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) rescal_w_update_kernel(float *W, float *p
       if (opt == SKGE_OPT_ADAGRAD) {
         float a = a2[c] + gg * gg;
         a2[c] = a;
-        xv -= lr * gg / fmaxf(sqrtf(a), 1e-7f);
+        xv -= lr * gg * adagrad_rscale(a);
       } else {
         xv -= lr * gg;
       }

@@ -110,6 +110,96 @@ __global__ void __launch_bounds__(256) transe_pair_kernel(const float *__restric
   }
 }
 
+// Same, for rows of at most MAXC * 32 * VEC floats: the two difference vectors stay in registers
+// between the score and the gradient rows, so every input row is requested once.
+__device__ __forceinline__ float sign0(float x) { return copysignf(x != 0.f ? 1.f : 0.f, x); }  // np.sign
+
+template <int VEC, int MAXC>
+__global__ void __launch_bounds__(256, 4) transe_pair_reg_kernel(const float *__restrict__ E,
+                                                                 const float *__restrict__ R, PairIdx ix,
+                                                                 int64_t P, int d, int l1, float margin,
+                                                                 float *__restrict__ pscores,
+                                                                 float *__restrict__ nscores,
+                                                                 uint8_t *__restrict__ flags,
+                                                                 float *__restrict__ G,
+                                                                 int32_t *__restrict__ counts,
+                                                                 int64_t *__restrict__ nviol_accum,
+                                                                 int32_t *__restrict__ ent_viol) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int nv = 0;
+  for (int64_t i = warp; i < P; i += nwarps) {
+    if (ix.valid && !ix.valid[i]) {
+      if (lane == 0) {
+        flags[i] = 0;
+        if (pscores) pscores[i] = 0.f;
+        if (nscores) nscores[i] = 0.f;
+      }
+      continue;
+    }
+    int sp = ix.sp[i], op = ix.op[i], pp = ix.pp[i], sn = ix.sn[i], on = ix.on[i], pn = ix.pn[i];
+    const float *esp = E + (int64_t)sp * d, *eop = E + (int64_t)op * d, *rpp = R + (int64_t)pp * d;
+    const float *esn = E + (int64_t)sn * d, *eon = E + (int64_t)on * d, *rpn = R + (int64_t)pn * d;
+    float x[MAXC][VEC], y[MAXC][VEC];  // E[s]+R[p]-E[o] of the positive / negative triple
+    float ap = 0.f, an = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * 32 + lane) * VEC;
+      if (col < d) {
+        float a[VEC], b[VEC], r[VEC], a2[VEC], b2[VEC], r2[VEC];
+        ld_vec<VEC>(esp + col, a);
+        ld_vec<VEC>(rpp + col, r);
+        ld_vec<VEC>(eop + col, b);
+        ld_vec<VEC>(esn + col, a2);
+        ld_vec<VEC>(rpn + col, r2);
+        ld_vec<VEC>(eon + col, b2);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          x[c][v] = a[v] + r[v] - b[v];
+          y[c][v] = a2[v] + r2[v] - b2[v];
+          ap += l1 ? fabsf(x[c][v]) : x[c][v] * x[c][v];
+          an += l1 ? fabsf(y[c][v]) : y[c][v] * y[c][v];
+        }
+      }
+    }
+    float ps = -warp_sum(ap), ns = -warp_sum(an);
+    bool viol = ns + margin > ps;  // skge/transe.py:73
+    if (lane == 0) {
+      flags[i] = viol;
+      if (pscores) pscores[i] = ps;
+      if (nscores) nscores[i] = ns;
+    }
+    if (!viol) continue;
+    ++nv;
+    if (ent_viol && lane == 0) {  // distinct entities of the pair: skge/transe.py:78-83
+      atomicAdd(ent_viol + sn, 1);
+      if (on != sn) atomicAdd(ent_viol + on, 1);
+      if (sp != sn && sp != on) atomicAdd(ent_viol + sp, 1);
+      if (op != sn && op != on && op != sp) atomicAdd(ent_viol + op, 1);
+    }
+    float *gp = G + (int64_t)i * 2 * d, *gn = gp + d;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = (c * 32 + lane) * VEC;
+      if (col < d) {
+        float o1[VEC], o2[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          o1[v] = l1 ? sign0(x[c][v]) : x[c][v];     // -(E[op]-R[pp]-E[sp])
+          o2[v] = l1 ? -sign0(y[c][v]) : -y[c][v];   //   E[on]-R[pn]-E[sn]
+        }
+        st_vec<VEC>(gp + col, o1);
+        st_vec<VEC>(gn + col, o2);
+      }
+    }
+  }
+  if (lane == 0 && nv) {
+    atomicAdd(counts, nv);
+    if (nviol_accum) atomicAdd(reinterpret_cast<unsigned long long *>(nviol_accum), (unsigned long long)nv);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // HolE: one CTA per pair, thread k owns component k of every correlation.
 // Phase 1: ccorr(s,o) for the positive and the negative triple -> raw scores
@@ -120,6 +210,31 @@ __global__ void __launch_bounds__(256) transe_pair_kernel(const float *__restric
 //   G[i][4] = gp ccorr(E[sp],E[op]) -> pp     G[i][5] = gn ccorr(E[sn],E[on]) -> pn
 // (skge/hole.py:66-97)
 // ---------------------------------------------------------------------------
+// Rows (2q, 2q + 1) of a pair go to the same slot (subject / object / relation) of the positive
+// and the negative triple.  When both triples hold the same id there, the two contributions are
+// summed here and only row 2q is used (RoleMap::twin): a corrupted pair shares two of its three
+// slots, so it emits four gradient rows instead of six.
+template <typename T>
+__device__ __forceinline__ void store_folded(T *row, int stride, bool same, T vp, T vn);
+template <>
+__device__ __forceinline__ void store_folded<float>(float *row, int stride, bool same, float vp, float vn) {
+  if (same) {
+    row[0] = vp + vn;
+  } else {
+    row[0] = vp;
+    row[stride] = vn;
+  }
+}
+template <>
+__device__ __forceinline__ void store_folded<float2>(float2 *row, int stride, bool same, float2 vp, float2 vn) {
+  if (same) {
+    row[0] = make_float2(vp.x + vn.x, vp.y + vn.y);
+  } else {
+    row[0] = vp;
+    row[stride] = vn;
+  }
+}
+
 __global__ void hole_pair_kernel(const float *__restrict__ E, const float *__restrict__ R, PairIdx ix,
                                  int64_t P, int d, int af, float margin, float *__restrict__ pscores,
                                  float *__restrict__ nscores, uint8_t *__restrict__ flags,
@@ -174,12 +289,10 @@ __global__ void hole_pair_kernel(const float *__restrict__ E, const float *__res
     float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // skge/hole.py:66-67
     float *g = G + (int64_t)i * 6 * d;
     int offc = (d - k) % d;
-    g[0 * d + k] = gp * sliding_dot(r_p, o2_p, k, d);
-    g[1 * d + k] = gn * sliding_dot(r_n, o2_n, k, d);
-    g[2 * d + k] = gp * sliding_dot(s_p, rr_p, offc, d);
-    g[3 * d + k] = gn * sliding_dot(s_n, rr_n, offc, d);
-    g[4 * d + k] = gp * cso_p;
-    g[5 * d + k] = gn * cso_n;
+    store_folded(g + k, d, ix.sp[i] == ix.sn[i], gp * sliding_dot(r_p, o2_p, k, d), gn * sliding_dot(r_n, o2_n, k, d));
+    store_folded(g + 2 * d + k, d, ix.op[i] == ix.on[i], gp * sliding_dot(s_p, rr_p, offc, d),
+                 gn * sliding_dot(s_n, rr_n, offc, d));
+    store_folded(g + 4 * d + k, d, ix.pp[i] == ix.pn[i], gp * cso_p, gn * cso_n);
   }
 }
 
@@ -324,14 +437,15 @@ __global__ void __launch_bounds__(256) hole_pair_fft_kernel(const float *__restr
     const float2 *Z = fft_batch<LOGD, 3, true>(Y, other, tw);
     const float gp = -act_g_given_f(af, fp) * inv_n, gn = act_g_given_f(af, fn) * inv_n;  // hole.py:66-67
     float *g = G + (int64_t)i * 6 * N;
+    const bool same_s = ix.sp[i] == ix.sn[i], same_o = ix.op[i] == ix.on[i], same_r = ix.pp[i] == ix.pn[i];
     for (int t = threadIdx.x; t < N; t += blockDim.x) {
       const float2 y0 = Z[t], y1 = Z[N + t], y2 = Z[2 * N + t];
-      g[0 * N + t] = gp * y1.x;   // gp ccorr(R[pp], E[op]) -> sp
-      g[1 * N + t] = gn * y2.x;   // gn ccorr(R[pn], E[on]) -> sn
-      g[2 * N + t] = gp * y1.y;   // gp cconv(E[sp], R[pp]) -> op
-      g[3 * N + t] = gn * y2.y;   // gn cconv(E[sn], R[pn]) -> on
-      g[4 * N + t] = gp * y0.x;   // gp ccorr(E[sp], E[op]) -> pp
-      g[5 * N + t] = gn * y0.y;   // gn ccorr(E[sn], E[on]) -> pn
+      // gp ccorr(R[pp], E[op]) -> sp | gn ccorr(R[pn], E[on]) -> sn
+      store_folded(g + t, N, same_s, gp * y1.x, gn * y2.x);
+      // gp cconv(E[sp], R[pp]) -> op | gn cconv(E[sn], R[pn]) -> on
+      store_folded(g + 2 * N + t, N, same_o, gp * y1.y, gn * y2.y);
+      // gp ccorr(E[sp], E[op]) -> pp | gn ccorr(E[sn], E[on]) -> pn
+      store_folded(g + 4 * N + t, N, same_r, gp * y0.x, gn * y0.y);
     }
   }
   if (threadIdx.x == 0 && nv) {
@@ -427,6 +541,7 @@ __global__ void __launch_bounds__(256) hole_pair_spec_kernel(const float *__rest
     ++nv;
     const float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // hole.py:66-67
     float2 *g = reinterpret_cast<float2 *>(G + (int64_t)i * 6 * d);
+    const bool same_s = S == S2, same_o = O == O2, same_r = Rp == Rn;
     for (int f = lane; f < h; f += 32) {
       const float2 s = __ldg(S + f), o = __ldg(O + f), rp = __ldg(Rp + f);
       const float2 s2 = __ldg(S2 + f), o2 = __ldg(O2 + f), rn = __ldg(Rn + f);
@@ -440,12 +555,9 @@ __global__ void __launch_bounds__(256) hole_pair_spec_kernel(const float *__rest
         a2 = cmulc(rp, o);  b2 = cmulc(rn, o2);     // ccorr(r, o)
         a3 = cmul(s, rp);   b3 = cmul(s2, rn);      // cconv(s, r)
       }
-      g[0 * h + f] = make_float2(gp * a2.x, gp * a2.y);  // -> sp
-      g[1 * h + f] = make_float2(gn * b2.x, gn * b2.y);  // -> sn
-      g[2 * h + f] = make_float2(gp * a3.x, gp * a3.y);  // -> op
-      g[3 * h + f] = make_float2(gn * b3.x, gn * b3.y);  // -> on
-      g[4 * h + f] = make_float2(gp * a1.x, gp * a1.y);  // -> pp
-      g[5 * h + f] = make_float2(gn * b1.x, gn * b1.y);  // -> pn
+      store_folded(g + 0 * h + f, h, same_s, make_float2(gp * a2.x, gp * a2.y), make_float2(gn * b2.x, gn * b2.y));  // -> sp | sn
+      store_folded(g + 2 * h + f, h, same_o, make_float2(gp * a3.x, gp * a3.y), make_float2(gn * b3.x, gn * b3.y));  // -> op | on
+      store_folded(g + 4 * h + f, h, same_r, make_float2(gp * a1.x, gp * a1.y), make_float2(gn * b1.x, gn * b1.y));  // -> pp | pn
     }
   }
   if (lane == 0 && nv) {
@@ -494,20 +606,21 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
   if (model == 0) {
     int64_t blocks = (P + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    switch (pick_vec(d)) {
-      case 4:
-        transe_pair_kernel<4><<<(int)blocks, 256, 0, st>>>(E, R, ix, P, d, l1_or_af, margin, pscores, nscores,
-                                                          flags, G, counts, nviol_accum, ent_viol);
-        break;
-      case 2:
-        transe_pair_kernel<2><<<(int)blocks, 256, 0, st>>>(E, R, ix, P, d, l1_or_af, margin, pscores, nscores,
-                                                          flags, G, counts, nviol_accum, ent_viol);
-        break;
-      default:
-        transe_pair_kernel<1><<<(int)blocks, 256, 0, st>>>(E, R, ix, P, d, l1_or_af, margin, pscores, nscores,
-                                                          flags, G, counts, nviol_accum, ent_viol);
-        break;
-    }
+    const int vec = pick_vec(d);
+    const int chunks = (d + 32 * vec - 1) / (32 * vec);
+#define SKGE_TRANSE_PAIR(KERNEL) \
+    KERNEL<<<(int)blocks, 256, 0, st>>>(E, R, ix, P, d, l1_or_af, margin, pscores, nscores, flags, G, counts, \
+                                        nviol_accum, ent_viol)
+    if (vec == 4 && chunks == 1) SKGE_TRANSE_PAIR((transe_pair_reg_kernel<4, 1>));
+    else if (vec == 4 && chunks == 2) SKGE_TRANSE_PAIR((transe_pair_reg_kernel<4, 2>));
+    else if (vec == 2 && chunks == 1) SKGE_TRANSE_PAIR((transe_pair_reg_kernel<2, 1>));
+    else if (vec == 2 && chunks == 2) SKGE_TRANSE_PAIR((transe_pair_reg_kernel<2, 2>));
+    else if (vec == 1 && chunks == 1) SKGE_TRANSE_PAIR((transe_pair_reg_kernel<1, 1>));
+    else if (vec == 1 && chunks == 2) SKGE_TRANSE_PAIR((transe_pair_reg_kernel<1, 2>));
+    else if (vec == 4) SKGE_TRANSE_PAIR(transe_pair_kernel<4>);
+    else if (vec == 2) SKGE_TRANSE_PAIR(transe_pair_kernel<2>);
+    else SKGE_TRANSE_PAIR(transe_pair_kernel<1>);
+#undef SKGE_TRANSE_PAIR
   } else if (Ehat && Rhat) {
     SKGE_REQUIRE(update && log2_exact(d) >= 5 && d <= 1024, "spectral HolE step needs a power-of-two d in [32, 1024]");
     int64_t blocks = (P + 7) / 8;
@@ -548,7 +661,10 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
     // entity keys sp+sn+op+on, relation keys pp+pn: hole.py:69-97
     const int32_t *idx[6] = {ix.sp, ix.sn, ix.op, ix.on, ix.pp, ix.pn};
     const int isrel[6] = {0, 0, 0, 0, 1, 1}, grow[6] = {0, 1, 2, 3, 4, 5};
-    for (int r = 0; r < 6; ++r) { rm.idx[r] = idx[r]; rm.is_rel[r] = isrel[r]; rm.grow[r] = grow[r]; rm.gsign[r] = 1.f; }
+    for (int r = 0; r < 6; ++r) {
+      rm.idx[r] = idx[r]; rm.is_rel[r] = isrel[r]; rm.grow[r] = grow[r]; rm.gsign[r] = 1.f;
+      rm.twin[r] = r ^ 1;  // the kernels above fold rows (2q, 2q + 1) when the ids coincide
+    }
   }
   rm.nroles = 6;
   ParamDesc pd[2];

@@ -22,8 +22,12 @@ __global__ void build_keys_kernel(RoleMap rm, const uint8_t *__restrict__ flags,
     int r = (int)(t / P);
     int64_t i = t - (int64_t)r * P;
     bool ok = flags ? flags[i] != 0 : true;
-    keys[t] = ok ? rm.idx[r][i] + (rm.is_rel[r] ? N : 0) : sentinel;
-    vals[t] = (int32_t)(i * 8 + r);
+    const int id = rm.idx[r][i];
+    const int q = rm.twin[r];
+    const bool same = q >= 0 && rm.idx[q][i] == id;
+    if (same && q < r) ok = false;  // folded into the twin's row
+    keys[t] = ok ? id + (rm.is_rel[r] ? N : 0) : sentinel;
+    vals[t] = (int32_t)(i * 16 + (same && q > r ? 8 : 0) + r);
   }
 }
 
@@ -94,7 +98,7 @@ static int64_t long_seg_cap(int64_t L) { return L / seg_chunk_for(L) + 8; }
 size_t seg_workspace_bytes(int64_t L, int d) {
   if (L < 1) L = 1;
   size_t b = 0;
-  b += align_up((size_t)long_seg_cap(L) * 3 * 4) + align_up((size_t)long_chunk_cap(L) * 2 * 4) + align_up(16);
+  b += align_up((size_t)long_seg_cap(L) * 3 * 4) + align_up((size_t)long_chunk_cap(L) * 3 * 4) + 256 + align_up(16);
   b += align_up((size_t)long_chunk_cap(L) * (d > 0 ? d : 1) * sizeof(float));
   b += 4 * align_up((size_t)L * 4);        // keys in/out, vals in/out
   b += 2 * align_up((size_t)L * 4);        // head, pos
@@ -108,7 +112,7 @@ size_t seg_workspace_bytes(int64_t L, int d) {
 int seg_build(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64_t M, Arena &ar,
               cudaStream_t st, SegLists *out) {
   int64_t L = (int64_t)rm.nroles * P;
-  SKGE_REQUIRE(L > 0 && L < ((int64_t)1 << 31) && P < ((int64_t)1 << 28), "minibatch too large");
+  SKGE_REQUIRE(L > 0 && L < ((int64_t)1 << 31) && P < ((int64_t)1 << 27), "minibatch too large");
   SKGE_REQUIRE(N + M < ((int64_t)1 << 31) - 1, "too many rows");
   int32_t *keys_in = ar.take<int32_t>(L), *keys_out = ar.take<int32_t>(L);
   int32_t *vals_in = ar.take<int32_t>(L), *vals_out = ar.take<int32_t>(L);
@@ -182,8 +186,7 @@ __device__ __forceinline__ void row_update(float *xrow, float *p2row, float (&g)
         for (int v = 0; v < VEC; ++v) {
           float gg = g[c][v] + rparam * x[c][v];
           p2[v] += gg * gg;                                   // skge/param.py:147
-          float H = fmaxf(sqrtf(p2[v]), 1e-7f);               // skge/param.py:152
-          x[c][v] -= lr * gg / H;                             // skge/param.py:155
+          x[c][v] -= lr * gg * adagrad_rscale(p2[v]);         // skge/param.py:152-155
         }
         st_vec<VEC>(p2row + col, p2);
       } else {
@@ -197,7 +200,7 @@ __device__ __forceinline__ void row_update(float *xrow, float *p2row, float (&g)
   float scale = 1.f;
   if (post != SKGE_POST_NONE) {
     ss = warp_sum(ss);
-    if (post == SKGE_POST_NORMALIZE) scale = 1.0f / sqrtf(ss);           // skge/param.py:165-166
+    if (post == SKGE_POST_NORMALIZE) scale = rsqrtf(ss);                 // skge/param.py:165-166
     else scale = 1.0f / (ss < 1.0f ? 1.0f : ss);                        // skge/param.py:171-173 (squared norm)
   }
 #pragma unroll
@@ -228,6 +231,7 @@ struct SegArgs {
   int32_t *long_seg;    // [long_seg_cap][3]: segment, first chunk, number of chunks
   int32_t *long_work;   // [long_chunk_cap][2]: segment, chunk index inside the segment
   float *partials;      // [long_chunk_cap][d]
+  int32_t *partial_occ; // [long_chunk_cap] occurrences behind each partial sum
   int long_seg_cap, long_chunk_cap;
   int seg_chunk;        // segments longer than this are reduced chunk-wise
   int spec_logd;        // > 0: G rows are packed spectra of length 1 << spec_logd (see fft.cuh)
@@ -245,13 +249,16 @@ __host__ __device__ __forceinline__ size_t spec_smem_bytes(int d, int warps) {
 // walks a long segment is latency bound otherwise).  BATCH = 4 for small, latency-bound
 // minibatches; BATCH = 1 keeps the register count (hence the occupancy) up for the large,
 // bandwidth-bound ones.
+// Returns the number of occurrences the rows stand for (a folded twin row counts twice).
 template <int VEC, int MAXC, int BATCH>
-__device__ __forceinline__ void accumulate_rows(const SegArgs &a, int beg, int end, int lane,
-                                                float (&acc)[MAXC][VEC]) {
+__device__ __forceinline__ int accumulate_rows(const SegArgs &a, int beg, int end, int lane,
+                                               float (&acc)[MAXC][VEC]) {
   const int d = a.d;
+  int folded = 0;
   for (int j0 = beg; j0 < end; j0 += 32) {
     const int cnt = min(32, end - j0);
     const int myval = lane < cnt ? a.vals[j0 + lane] : 0;
+    folded += __popc(__ballot_sync(kFull, (myval & 8) != 0));
     for (int t0 = 0; t0 < cnt; t0 += BATCH) {
       float tmp[BATCH][MAXC][VEC];
       float sgn[BATCH];
@@ -261,7 +268,7 @@ __device__ __forceinline__ void accumulate_rows(const SegArgs &a, int beg, int e
         const int r = val & 7;
         const bool live = t0 + b < cnt;
         sgn[b] = live ? a.gsign[r] : 0.f;
-        const float *g = a.G + ((int64_t)(val >> 3) * a.rows_per_unit + a.grow[r]) * d;
+        const float *g = a.G + ((int64_t)(val >> 4) * a.rows_per_unit + a.grow[r]) * d;
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
           int col = (c * 32 + lane) * VEC;
@@ -280,6 +287,7 @@ __device__ __forceinline__ void accumulate_rows(const SegArgs &a, int beg, int e
         }
     }
   }
+  return (end - beg) + folded;
 }
 
 // acc holds the SUM over the n occurrences of segment seg: take the mean and either apply
@@ -291,7 +299,7 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
   const int U0 = a.meta[1];
   int which = key >= a.N;
   int64_t row = which ? key - a.N : key;
-  float fn = (float)n;
+  const float inv_n = 1.0f / (float)n;
   float2 *tw = nullptr, *b0 = nullptr, *b1 = nullptr;
   if (UPDATE && a.spec_logd > 0) {
     // acc is a summed packed spectrum: back to the time domain
@@ -320,7 +328,7 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
 #pragma unroll
   for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[c][v] /= fn;  // the mean: skge/util.py:97-101
+    for (int v = 0; v < VEC; ++v) acc[c][v] *= inv_n;  // the mean: skge/util.py:97-101
   const ParamDesc &pd = a.pd[which];
   if (UPDATE) {
     float x[MAXC][VEC];
@@ -406,8 +414,8 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
     for (int c = 0; c < MAXC; ++c)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
-    accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
-    finish_row<VEC, MAXC, UPDATE>(a, seg, key, n, lane, acc, spec_smem, threadIdx.x >> 5);
+    const int occ = accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
+    finish_row<VEC, MAXC, UPDATE>(a, seg, key, occ, lane, acc, spec_smem, threadIdx.x >> 5);
   }
 }
 
@@ -428,7 +436,8 @@ __global__ void __launch_bounds__(256) seg_long_chunks_kernel(SegArgs a) {
     for (int cc = 0; cc < MAXC; ++cc)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[cc][v] = 0.f;
-    accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
+    const int occ = accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
+    if (lane == 0) a.partial_occ[c] = occ;
     float *dst = a.partials + (int64_t)c * d;
 #pragma unroll
     for (int cc = 0; cc < MAXC; ++cc) {
@@ -491,7 +500,10 @@ __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
           }
         }
       }
-      int n = a.seg_start[seg + 1] - a.seg_start[seg];
+      int n = 0;
+      for (int k = lane; k < nch; k += 32) n += a.partial_occ[first + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
       finish_row<VEC, MAXC, UPDATE>(a, seg, a.seg_key[seg], n, lane, acc, spec_smem, 0);
     }
   }
@@ -528,7 +540,10 @@ template <int VEC, int MAXC>
 static void launch_seg_reduce(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
   // small minibatches (short chunks) are latency bound: more loads in flight per warp
   constexpr int BIG = MAXC <= 2 ? 4 : (MAXC == 4 ? 2 : 1);
-  // (2 loads in flight were measured slower than 1 on the large, bandwidth-bound minibatches)
+  // (on the large minibatches 2 loads in flight, and a software-pipelined variant that fetches the next
+  // segment's table entry / payloads and the parameter row ahead of the gradient rows, were both
+  // measured slower than this: they cost registers, and with ~900 instructions per segment the
+  // kernel lives on resident warps, not on per-warp memory parallelism)
   if (a.seg_chunk <= 32) launch_seg_reduce_b<VEC, MAXC, BIG>(a, update, blocks, st);
   else launch_seg_reduce_b<VEC, MAXC, 1>(a, update, blocks, st);
 }
@@ -562,6 +577,7 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
   a.long_seg = ar.take<int32_t>((size_t)a.long_seg_cap * 3);
   a.long_work = ar.take<int32_t>((size_t)a.long_chunk_cap * 2);
   a.partials = ar.take<float>((size_t)a.long_chunk_cap * d);
+  a.partial_occ = ar.take<int32_t>((size_t)a.long_chunk_cap);
   if (!ar.ok()) {
     set_error("workspace too small: need %zu bytes, have %zu", ar.off, ar.cap);
     return SKGE_EWORKSPACE;
@@ -653,7 +669,7 @@ __global__ void __launch_bounds__(256) sparse_update_block_kernel(float *param, 
       if (opt == SKGE_OPT_ADAGRAD) {
         float a = a2[c] + gg * gg;
         a2[c] = a;
-        xv -= lr * gg / fmaxf(sqrtf(a), 1e-7f);
+        xv -= lr * gg * adagrad_rscale(a);
       } else {
         xv -= lr * gg;
       }
@@ -673,7 +689,7 @@ __global__ void __launch_bounds__(256) sparse_update_block_kernel(float *param, 
       }
       __syncthreads();
       float tot = red[32];
-      float scale = post == SKGE_POST_NORMALIZE ? 1.0f / sqrtf(tot) : 1.0f / (tot < 1.0f ? 1.0f : tot);
+      float scale = post == SKGE_POST_NORMALIZE ? rsqrtf(tot) : 1.0f / (tot < 1.0f ? 1.0f : tot);
       for (int64_t c = threadIdx.x; c < rowlen; c += blockDim.x) x[c] *= scale;
       __syncthreads();
     }

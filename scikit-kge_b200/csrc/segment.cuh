@@ -11,11 +11,16 @@ static constexpr int kMaxRoles = 6;
 // How the occurrences of rows in a minibatch map to per-unit gradient rows.
 // Unit i (a pair or an example) owns `rows_per_unit` rows in G; role r says
 // "row idx[r][i] of table is_rel[r] receives gsign[r] * G[i][grow[r]]".
+// twin[r] = q >= 0 pairs two roles whose ids often coincide within a unit (the subject of a
+// positive triple and of its object-corrupted negative): when idx[r][i] == idx[q][i] the producer
+// has already summed both contributions into the row of the LOWER role, which then counts as two
+// occurrences in the mean, and the higher role's occurrence is dropped.
 struct RoleMap {
   const int32_t *idx[kMaxRoles];
   int is_rel[kMaxRoles];
   int grow[kMaxRoles];
   float gsign[kMaxRoles];
+  int twin[kMaxRoles] = {-1, -1, -1, -1, -1, -1};
   int nroles;
 };
 
@@ -50,7 +55,7 @@ int set_i32(int32_t *p, int32_t v, cudaStream_t st);
 // Sort-only service for callers with their own reduction (RESCAL's W gradient):
 // sorted unit ids grouped by key, with segment starts/keys and meta[0] = nseg.
 struct SegLists {
-  const int32_t *vals;       // sorted payload (unit * 8 + role)
+  const int32_t *vals;       // sorted payload (unit * 16 + (weight - 1) * 8 + role)
   const int32_t *seg_start;  // [nseg + 1]
   const int32_t *seg_key;    // [nseg]
   const int32_t *meta;       // [0] = nseg, [1] = segments of table 0
