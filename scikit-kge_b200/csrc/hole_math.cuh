@@ -50,6 +50,41 @@ __device__ __forceinline__ float sliding_dot(const float *a, const float *x2, in
   return (acc0 + acc1) + (acc2 + acc3);
 }
 
+// ---- register-blocked form --------------------------------------------------------------
+// A thread owns FOUR consecutive outputs k0..k0+3 (k0 % 4 == 0) and walks the inputs four at a
+// time: one 128-bit load of a[i0..i0+3] (a broadcast) and two of the window x2[i0+k0 .. +7]
+// feed 16 FMAs, instead of two 32-bit loads per FMA.  Layout (d4 = d rounded up to 4):
+//   a  : d4 floats, a[i] = 0 for i >= d
+//   x2 : 2*d4 floats, x2[j] = x[j mod d]  (periodic, so i + k never needs a modulo)
+// and cconv(a, b) = ccorr(rev(a), b) with rev(a)_m = a_{(d-m) mod d}, so one doubled copy of b
+// serves both.  Outputs k >= d are garbage and must be discarded by the caller.
+__host__ __device__ __forceinline__ int round4(int d) { return (d + 3) & ~3; }
+
+__device__ __forceinline__ void smem_load_padded(float *dst, const float *__restrict__ src, int d, int d4) {
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) dst[i] = i < d ? __ldg(src + i) : 0.f;
+}
+__device__ __forceinline__ void smem_load_rev_padded(float *dst, const float *__restrict__ src, int d, int d4) {
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) dst[i] = i < d ? __ldg(src + (i == 0 ? 0 : d - i)) : 0.f;
+}
+__device__ __forceinline__ void smem_load_periodic(float *dst, const float *__restrict__ src, int d, int d4) {
+  for (int j = threadIdx.x; j < 2 * d4; j += blockDim.x) dst[j] = __ldg(src + j % d);
+}
+
+// out[m] += sum_{i in [i_beg, i_end)} a[i] * x2[i + k0 + m], m = 0..3 (i_beg, i_end, k0 multiples of 4)
+__device__ __forceinline__ void sliding_dot4(const float *a, const float *x2, int k0, int i_beg, int i_end,
+                                             float (&out)[4]) {
+  const float *x = x2 + k0;
+  for (int i0 = i_beg; i0 < i_end; i0 += 4) {
+    const float4 av = *reinterpret_cast<const float4 *>(a + i0);
+    const float4 w0 = *reinterpret_cast<const float4 *>(x + i0);
+    const float4 w1 = *reinterpret_cast<const float4 *>(x + i0 + 4);
+    out[0] = fmaf(av.x, w0.x, fmaf(av.y, w0.y, fmaf(av.z, w0.z, fmaf(av.w, w0.w, out[0]))));
+    out[1] = fmaf(av.x, w0.y, fmaf(av.y, w0.z, fmaf(av.z, w0.w, fmaf(av.w, w1.x, out[1]))));
+    out[2] = fmaf(av.x, w0.z, fmaf(av.y, w0.w, fmaf(av.z, w1.x, fmaf(av.w, w1.y, out[2]))));
+    out[3] = fmaf(av.x, w0.w, fmaf(av.y, w1.x, fmaf(av.z, w1.y, fmaf(av.w, w1.z, out[3]))));
+  }
+}
+
 // Block-wide sum; `red` is >= 33 floats of shared memory. All threads get the result.
 __device__ __forceinline__ float block_sum(float v, float *red) {
   v = warp_sum(v);

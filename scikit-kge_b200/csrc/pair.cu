@@ -235,16 +235,27 @@ __device__ __forceinline__ void store_folded<float2>(float2 *row, int stride, bo
   }
 }
 
+// Register-blocked (hole_math.cuh): the CTA is four groups of d4/4 threads, thread j of a group
+// owns outputs 4j..4j+3 of the group's correlation.
+//   phase 1: groups (0, 2) / (1, 3) each take half of the input range of ccorr(s, o) of the
+//            positive / negative triple; the score is linear in the partial results.
+//   phase 2: groups 0..3 take ccorr(r,o)+, ccorr(r,o)-, cconv(s,r)+, cconv(s,r)-; the six scaled
+//            rows are staged in shared memory and written out folded and coalesced.
 __global__ void hole_pair_kernel(const float *__restrict__ E, const float *__restrict__ R, PairIdx ix,
                                  int64_t P, int d, int af, float margin, float *__restrict__ pscores,
                                  float *__restrict__ nscores, uint8_t *__restrict__ flags,
                                  float *__restrict__ G, int32_t *__restrict__ counts,
                                  int64_t *__restrict__ nviol_accum) {
-  extern __shared__ float sm[];
-  // per triple: s[d], r[d], o2[2d], rrev2[2d]
-  float *s_p = sm, *r_p = s_p + d, *o2_p = r_p + d, *rr_p = o2_p + 2 * d;
-  float *s_n = rr_p + 2 * d, *r_n = s_n + d, *o2_n = r_n + d, *rr_n = o2_n + 2 * d;
-  float *red = rr_n + 2 * d;
+  extern __shared__ __align__(16) float sm[];
+  const int d4 = round4(d), T4 = d4 >> 2;
+  // per triple: s[d4], srev[d4], r[d4], o2[2 d4], r2[2 d4]; then the staging rows [6][d4]
+  float *tri[2];
+  tri[0] = sm;
+  tri[1] = sm + 7 * d4;
+  float *stage = sm + 14 * d4;
+  float *red = stage + 6 * d4;
+  const int grp = threadIdx.x / T4, j = threadIdx.x - grp * T4, k0 = 4 * j;
+  const bool worker = grp < 4;
   for (int64_t i = blockIdx.x; i < P; i += gridDim.x) {
     if (ix.valid && !ix.valid[i]) {
       if (threadIdx.x == 0) {
@@ -255,27 +266,34 @@ __global__ void hole_pair_kernel(const float *__restrict__ E, const float *__res
       continue;
     }
     __syncthreads();
-    const float *rp = R + (int64_t)ix.pp[i] * d, *rn = R + (int64_t)ix.pn[i] * d;
-    smem_load(s_p, E + (int64_t)ix.sp[i] * d, d);
-    smem_load(r_p, rp, d);
-    smem_load_doubled(o2_p, E + (int64_t)ix.op[i] * d, d);
-    smem_load_rev_doubled(rr_p, rp, d);
-    smem_load(s_n, E + (int64_t)ix.sn[i] * d, d);
-    smem_load(r_n, rn, d);
-    smem_load_doubled(o2_n, E + (int64_t)ix.on[i] * d, d);
-    smem_load_rev_doubled(rr_n, rn, d);
-    __syncthreads();
-    // phase 1 (d <= blockDim.x is guaranteed by the launcher)
-    const int k = threadIdx.x;
-    float cso_p = 0.f, cso_n = 0.f;
-    if (k < d) {
-      cso_p = sliding_dot(s_p, o2_p, k, d);
-      cso_n = sliding_dot(s_n, o2_n, k, d);
+    const int sid[2] = {ix.sp[i], ix.sn[i]}, oid[2] = {ix.op[i], ix.on[i]}, pid[2] = {ix.pp[i], ix.pn[i]};
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const float *es = E + (int64_t)sid[t] * d, *eo = E + (int64_t)oid[t] * d, *rr = R + (int64_t)pid[t] * d;
+      smem_load_padded(tri[t], es, d, d4);
+      smem_load_rev_padded(tri[t] + d4, es, d, d4);
+      smem_load_padded(tri[t] + 2 * d4, rr, d, d4);
+      smem_load_periodic(tri[t] + 3 * d4, eo, d, d4);
+      smem_load_periodic(tri[t] + 5 * d4, rr, d, d4);
     }
-    float raw_p = block_sum(k < d ? r_p[k] * cso_p : 0.f, red);
-    float raw_n = block_sum(k < d ? r_n[k] * cso_n : 0.f, red);
-    float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
-    bool viol = fn + margin > fp;  // skge/hole.py:56
+    __syncthreads();
+    // phase 1
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    float part = 0.f;
+    const int t1 = grp & 1;
+    const float *mine = sm + t1 * 7 * d4;  // this group's triple
+    if (worker) {
+      const int ih = ((T4 + 1) >> 1) << 2;  // first half of the input range, a multiple of 4
+      const int ib = (grp >> 1) ? ih : 0, ie = (grp >> 1) ? d4 : ih;
+      sliding_dot4(mine, mine + 3 * d4, k0, ib, ie, c);
+      const float *rv = mine + 2 * d4;  // zero beyond d, so garbage outputs k >= d drop out
+#pragma unroll
+      for (int m = 0; m < 4; ++m) part += rv[k0 + m] * c[m];
+    }
+    const float raw_p = block_sum(worker && t1 == 0 ? part : 0.f, red);
+    const float raw_n = block_sum(worker && t1 == 1 ? part : 0.f, red);
+    const float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
+    const bool viol = fn + margin > fp;  // skge/hole.py:56
     if (threadIdx.x == 0) {
       flags[i] = viol;
       if (pscores) pscores[i] = raw_p;
@@ -285,14 +303,34 @@ __global__ void hole_pair_kernel(const float *__restrict__ E, const float *__res
         if (nviol_accum) atomicAdd(reinterpret_cast<unsigned long long *>(nviol_accum), 1ull);
       }
     }
-    if (!viol || k >= d) continue;
-    float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // skge/hole.py:66-67
+    if (!viol) continue;  // uniform over the CTA
+    const float gs[2] = {-act_g_given_f(af, fp), act_g_given_f(af, fn)};  // skge/hole.py:66-67
+    // rows 4, 5 (-> pp, pn): g * ccorr(s, o); the two halves meet in the staging row
+    if (worker && (grp >> 1) == 1)
+      *reinterpret_cast<float4 *>(stage + (4 + t1) * d4 + k0) = make_float4(c[0], c[1], c[2], c[3]);
+    __syncthreads();
+    if (worker && (grp >> 1) == 0) {
+      float4 *dst = reinterpret_cast<float4 *>(stage + (4 + t1) * d4 + k0);
+      const float4 o = *dst;
+      const float g = gs[t1];
+      *dst = make_float4(g * (c[0] + o.x), g * (c[1] + o.y), g * (c[2] + o.z), g * (c[3] + o.w));
+    }
+    // phase 2: rows 0, 1 (-> sp, sn): g * ccorr(r, o); rows 2, 3 (-> op, on): g * cconv(s, r)
+    if (worker) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const float *a = (grp >> 1) ? mine + d4 : mine + 2 * d4;        // rev(s) | r
+      const float *x2 = (grp >> 1) ? mine + 5 * d4 : mine + 3 * d4;  // r2 | o2
+      sliding_dot4(a, x2, k0, 0, d4, v);
+      const float g = gs[t1];
+      *reinterpret_cast<float4 *>(stage + grp * d4 + k0) = make_float4(g * v[0], g * v[1], g * v[2], g * v[3]);
+    }
+    __syncthreads();
     float *g = G + (int64_t)i * 6 * d;
-    int offc = (d - k) % d;
-    store_folded(g + k, d, ix.sp[i] == ix.sn[i], gp * sliding_dot(r_p, o2_p, k, d), gn * sliding_dot(r_n, o2_n, k, d));
-    store_folded(g + 2 * d + k, d, ix.op[i] == ix.on[i], gp * sliding_dot(s_p, rr_p, offc, d),
-                 gn * sliding_dot(s_n, rr_n, offc, d));
-    store_folded(g + 4 * d + k, d, ix.pp[i] == ix.pn[i], gp * cso_p, gn * cso_n);
+    const bool same[3] = {sid[0] == sid[1], oid[0] == oid[1], pid[0] == pid[1]};
+    for (int e = threadIdx.x; e < 3 * d; e += blockDim.x) {
+      const int q = e / d, k = e - q * d;
+      store_folded(g + 2 * q * d + k, d, same[q], stage[2 * q * d4 + k], stage[(2 * q + 1) * d4 + k]);
+    }
   }
 }
 
@@ -566,8 +604,8 @@ __global__ void __launch_bounds__(256) hole_pair_spec_kernel(const float *__rest
   }
 }
 
-static int pair_block_threads(int d) {
-  int t = (d + 31) / 32 * 32;
+static int pair_block_threads(int d) {  // four groups of d4/4 threads (hole_pair_kernel)
+  int t = (round4(d) + 31) / 32 * 32;
   return t < 64 ? 64 : t;
 }
 
@@ -640,7 +678,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
       default: fft_done = false;
     }
     if (!fft_done) {
-    size_t smem = (12 * (size_t)d + 40) * sizeof(float);
+    size_t smem = (20 * (size_t)round4(d) + 40) * sizeof(float);
     SKGE_CUDA(cudaFuncSetAttribute(hole_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = P > kNumSMs * 16 ? kNumSMs * 16 : P;
     hole_pair_kernel<<<(int)blocks, pair_block_threads(d), smem, st>>>(E, R, ix, P, d, l1_or_af, margin,

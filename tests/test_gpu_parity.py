@@ -573,3 +573,62 @@ def test_fused_step_is_bit_reproducible(kind, d):
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('d', [150, 64, 24])
+def test_hole_twin_rows_fold_for_every_sharing_pattern(d):
+    """The HolE kernels sum the positive's and the negative's contribution to a shared slot
+    into one gradient row that counts twice in the mean.  Negatives that share 0, 1, 2 or all 3
+    slots with their positive (supplied-negatives mode, predicate corruption, a pair scored
+    against itself) must all give the reference's means: direct (d = 150, 24), shared-memory FFT
+    (d = 64) and, for d = 64, the frequency-domain fused step."""
+    import skge
+    from skge.param import SGD
+    from skge._modelutil import idx_tensor
+    N, M, B = 500, 7, 600
+    rng = np.random.default_rng(d)
+    E0 = (rng.uniform(-1, 1, (N, d)) * 0.2).astype(np.float32).astype(np.float64)
+    R0 = (rng.uniform(-1, 1, (M, d)) * 0.3).astype(np.float32).astype(np.float64)
+    pos = np.stack([rng.integers(N, size=B), rng.integers(N, size=B), rng.integers(M, size=B)], 1)
+    neg = pos.copy()
+    kind = np.arange(B) % 6
+    neg[kind == 0, 0] = rng.integers(N, size=(kind == 0).sum())          # subject corrupted
+    neg[kind == 1, 1] = rng.integers(N, size=(kind == 1).sum())          # object corrupted
+    neg[kind == 2, 2] = rng.integers(M, size=(kind == 2).sum())          # predicate corrupted
+    k3 = kind == 3                                                       # nothing shared
+    neg[k3] = np.stack([rng.integers(N, size=k3.sum()), rng.integers(N, size=k3.sum()),
+                        rng.integers(M, size=k3.sum())], 1)
+    k4 = kind == 4                                                       # subject and object corrupted
+    neg[k4, 0] = rng.integers(N, size=k4.sum())
+    neg[k4, 1] = rng.integers(N, size=k4.sum())
+    # kind == 5: the negative IS the positive (violates for every margin > 0)
+    pos[::50, 1] = pos[::50, 0]                                          # self loops: s == o
+    neg[::50] = pos[::50]
+    neg[::50, 0] = (pos[::50, 0] + 1) % N
+    margin = 0.2
+    ograds, info = orc.hole_pairwise_gradients(E0, R0, pos, neg, margin, 'sigmoid', 0.0)
+    assert not _near_margin(info, margin, 1e-5).any()
+    m = skge.HolE((N, N, M), d)
+    m.E[...] = E0
+    m.R[...] = R0
+    skge.PairwiseStochasticTrainer(m, nbatches=1, margin=margin, learning_rate=0.1, param_update=SGD)  # sets m.margin
+    grads = m._pairwise_gradients(as_xys(pos), as_xys(neg))
+    assert m.nviolations == info['nviolations']
+    for k in ('E', 'R'):
+        np.testing.assert_array_equal(np.asarray(grads[k][1]), ograds[k][1])
+        np.testing.assert_allclose(np.asarray(grads[k][0]), ograds[k][0], rtol=1e-4, atol=1e-6)
+    E, R = E0.copy(), R0.copy()
+    orc.sgd_update(E, ograds['E'][0], ograds['E'][1], 0.1, 'normless1')
+    orc.sgd_update(R, ograds['R'][0], ograds['R'][1], 0.1, None)
+    m2 = skge.HolE((N, N, M), d)
+    m2.E[...] = E0
+    m2.R[...] = R0
+    t2 = skge.PairwiseStochasticTrainer(m2, nbatches=1, margin=margin, learning_rate=0.1, param_update=SGD)
+    t2._setup_fused()
+    m2._prepare_fused()
+    assert (m2._spec is not None) == (d == 64)
+    m2._fused_pair_step(t2._updaters, tuple(idx_tensor(pos[:, i]) for i in range(3)),
+                        tuple(idx_tensor(neg[:, i]) for i in range(3)), None, t2._counts, t2._nviol_dev)
+    assert int(t2._nviol_dev.item()) == info['nviolations']
+    np.testing.assert_allclose(np.asarray(m2.E), E, **PARAM_TOL)
+    np.testing.assert_allclose(np.asarray(m2.R), R, **PARAM_TOL)
