@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Diagnostic: what does ONE rank of an N-way sharded config-5 ranking pass cost on its own GPU?
+Emulates shard 0 of `world` on a single GPU (count_pass(world=(0, world)): same kernels, no
+all-reduce) and prints the pass time next to the ideal T(world=1) / world, plus the time of the
+phases that do not shrink with the shard (query construction, packing, filter-pair selection)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'scikit-kge_b200')]
+import torch
+import skge
+from skge import kernels, ranking, _ext
+from skge.synth import make_graph, init_embeddings, SHAPES
+
+
+def ev_ms(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def main(worlds=(1, 2, 4, 8)):
+    dev = torch.device('cuda')
+    N, M, T, V, Te = SHAPES['syn1m']
+    g = make_graph((N, M, T, V, Te), device=dev)
+    true = torch.cat([g['train'], g['valid'], g['test']])
+    mdl = skge.HolE((N, N, M), 256)
+    E, R = init_embeddings('hole', N, M, 256, device=dev)
+    mdl.E.data.copy_(E)
+    mdl.R.data.copy_(R)
+    ev = ranking.HolEEval(g['test'], true)
+    del true, g
+    st = ev._device_state()
+    Q = 2 * Te
+    t1 = None
+    for w in worlds:
+        ms = ev_ms(lambda: ev.count_pass(mdl, world=(0, w)))
+        t1 = t1 or ms
+        print('world %d: shard-0 pass %.1f ms (ideal %.1f ms) -> %.2f M queries/s if every rank takes this long'
+              % (w, ms, t1 / w, Q / ms / 1e3), flush=True)
+    enorm = float(torch.linalg.vector_norm(mdl.E.data, dim=1).max().item())
+    mq = ev_ms(lambda: kernels.make_queries(ev.model_code, mdl.E.data, mdl.R.data, st['kind'], st['given'], st['rel'],
+                                            st['target'], enorm, 2.0 ** -17))
+    nm = ev_ms(lambda: torch.linalg.vector_norm(mdl.E.data, dim=1).max().item())
+    print('fixed per rank: make_queries(%d) %.2f ms, max row norm of E %.2f ms' % (Q, mq, nm), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -132,6 +132,9 @@ __global__ void make_queries_kernel(int model, const float *__restrict__ E, cons
 // k = 8l .. 8l+7 (lanes beyond d/8 idle).  The correlation slides a 15-wide register window
 // over a doubled copy of the given entity row in shared memory: per block of 8 inner steps a
 // lane issues 8 + 8 shared loads for 64 DFMAs, so the loop runs at the FP64 pipe's pace.
+// Lane l reads the window at 8 l + c: with a plain layout that is a 64-byte lane stride and a
+// 16-way bank conflict, so the doubled row is stored with one pad slot per 8 (index i lives
+// at i + i / 8: lane stride 72 bytes, conflict-free for 64-bit loads).
 //   tail: q_k = cconv(r, s)_k = sum_i r_i s_{(k-i) mod d}     head: q_k = ccorr(r, o)_k = sum_i r_i o_{(i+k) mod d}
 __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__restrict__ E,
                                                                 const float *__restrict__ R,
@@ -145,8 +148,10 @@ __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__r
                                                                 float *__restrict__ qnorm) {
   extern __shared__ double smd[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double *g2 = smd + (size_t)wid * 3 * d;  // [2d] doubled given row
-  double *rv = g2 + 2 * d;                 // [d] relation row
+  const int g2len = 2 * d + d / 4 + 8;                // padded doubled row
+  double *g2 = smd + (size_t)wid * (g2len + d);      // doubled given row, index i at HP(i)
+  double *rv = g2 + g2len;                           // [d] relation row
+#define HP(i) ((i) + ((i) >> 3))
   const int k0 = lane * 8;
   for (int64_t qi = (int64_t)blockIdx.x * nw + wid; qi < Q; qi += (int64_t)gridDim.x * nw) {
     const int head = kind[qi];
@@ -154,8 +159,8 @@ __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__r
     __syncwarp();
     for (int i = lane; i < d; i += 32) {
       double v = (double)__ldg(eg + i);
-      g2[i] = v;
-      g2[i + d] = v;
+      g2[HP(i)] = v;
+      g2[HP(i + d)] = v;
       rv[i] = (double)__ldg(rp + i);
     }
     __syncwarp();
@@ -166,10 +171,10 @@ __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__r
       if (head) {
         // acc[m] += r[i] * g2[i + k0 + m]; block b covers i = 8b..8b+7: window v[t] = g2[8b + k0 + t], t < 15
 #pragma unroll
-        for (int t = 0; t < 7; ++t) w[t] = g2[k0 + t];
+        for (int t = 0; t < 7; ++t) w[t] = g2[HP(k0 + t)];
         for (int b = 0; b < d / 8; ++b) {
 #pragma unroll
-          for (int t = 7; t < 15; ++t) w[t] = g2[8 * b + k0 + t];
+          for (int t = 7; t < 15; ++t) w[t] = g2[HP(8 * b + k0 + t)];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const double r = rv[8 * b + u];
@@ -182,10 +187,10 @@ __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__r
       } else {
         // acc[m] += r[i] * g2[d + k0 + m - i]; window v[t] = g2[d + k0 - 8b - 7 + t], t < 15
 #pragma unroll
-        for (int t = 8; t < 15; ++t) w[t] = g2[d + k0 - 7 + t];
+        for (int t = 8; t < 15; ++t) w[t] = g2[HP(d + k0 - 7 + t)];
         for (int b = 0; b < d / 8; ++b) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) w[t] = g2[d + k0 - 8 * b - 7 + t];
+          for (int t = 0; t < 8; ++t) w[t] = g2[HP(d + k0 - 8 * b - 7 + t)];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const double r = rv[8 * b + u];
@@ -217,6 +222,7 @@ __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__r
       eps[qi] = coarse_rel * n2 * enorm_max;
     }
   }
+#undef HP
 }
 
 // ---------------------------------------------------------------------------
@@ -440,7 +446,7 @@ int skge_rank_make_queries(int model, const float *E, const float *RW, const uin
                "bad sizes");
   if (Q == 0) return 0;
   if (model == SKGE_MODEL_HOLE && d % 8 == 0 && d <= 256) {
-    size_t smem = (size_t)8 * 3 * d * sizeof(double);
+    size_t smem = (size_t)8 * (3 * d + d / 4 + 8) * sizeof(double);
     SKGE_CUDA(cudaFuncSetAttribute(make_queries_hole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (Q + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;

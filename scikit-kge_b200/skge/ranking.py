@@ -245,15 +245,9 @@ class FilteredRankingEval(object):
         cnt = torch.zeros(2, Q, dtype=torch.int32, device=dev)
         enorm = float(torch.linalg.vector_norm(E, dim=1).max().item()) if op == _ext.RANK_DOT else 1.0
         # filter entries are settled by the rank that owns the entity
-        pq, pe = st['pair_q'], st['pair_e']
-        if world > 1:
-            own = (pe >= lo) & (pe < hi)
-            pq, pe = pq[own].contiguous(), pe[own].contiguous()
+        pq, pe, pair_bounds = self._shard_pairs(st, lo, hi, world, Q)
         engine = self._coarse_engine(E, lo, hi, enorm)
         engine.reserve(min(Q, self.chunk_queries))
-        pair_bounds = torch.searchsorted(pq.to(torch.int64),
-                                         torch.arange(0, Q + self.chunk_queries, self.chunk_queries, device=dev)
-                                         ).tolist()
         ncand = 0
         for ci, q0 in enumerate(range(0, Q, self.chunk_queries)):
             q1 = min(Q, q0 + self.chunk_queries)
@@ -268,6 +262,24 @@ class FilteredRankingEval(object):
         self.last_stats = dict(candidates=ncand, filter_pairs=int(pq.numel()), shard=(lo, hi), world=world,
                                engine=engine.name, dtype=engine.dtype)
         return cnt if emulated else allreduce_counts(cnt)
+
+    def _shard_pairs(self, st, lo, hi, world, Q):
+        """This shard's filter pairs (the index does not change between passes, so the
+        selection is done once per shard) and their per-chunk boundaries."""
+        key = (lo, hi, world, self.chunk_queries)
+        cache = self.__dict__.setdefault('_pair_cache', {})
+        hit = cache.get(key)
+        if hit is None:
+            pq, pe = st['pair_q'], st['pair_e']
+            if world > 1:
+                own = (pe >= lo) & (pe < hi)
+                pq, pe = pq[own].contiguous(), pe[own].contiguous()
+            edges = torch.arange(0, Q + self.chunk_queries, self.chunk_queries, device=pq.device)
+            bounds = torch.searchsorted(pq.to(torch.int64), edges).tolist()
+            if len(cache) >= 16:
+                cache.clear()
+            hit = cache[key] = (pq, pe, bounds)
+        return hit
 
     engine = 'auto'             # 'auto' | 'sweep' (fp32 CUDA cores) | 'umma' (tcgen05, DOT models, d <= 256)
     nsplit = 3                  # fp16 hi/lo products accumulated by the tcgen05 engine (1 or 3)
