@@ -228,6 +228,10 @@ __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__r
 // ---------------------------------------------------------------------------
 // coarse sweep on the FP32 pipes
 // ---------------------------------------------------------------------------
+// (Both sweeps need two instructions per (query, entity, k) element -- FADD + FADD|.| or one FFMA
+// with three register operands at half rate -- so they are bound by instruction issue at 64
+// elements / clk / SM.  Rewriting |q - e| as 2 max(q, e) - q - e to move half of the work to the
+// alu pipe (FMNMX) was measured: same time, since the issue slot, not a pipe, is the limit.)
 // 128 queries x 128 entities per CTA step, k staged in chunks of KC through
 // double-buffered shared memory (cp.async), 8x8 accumulators per thread.  Rows
 // are stored with a stride of KC+4 floats so that the 128-bit reads of eight
@@ -273,7 +277,7 @@ __device__ __forceinline__ void stage_tile(float *dst, const float *__restrict__
 }
 
 template <int OP, bool VEC4>
-__global__ void __launch_bounds__(256) rank_sweep_kernel(const float *__restrict__ Eshard, int64_t n_shard,
+__global__ void __launch_bounds__(256, 2) rank_sweep_kernel(const float *__restrict__ Eshard, int64_t n_shard,
                                                          int64_t shard_base, int d,
                                                          const float *__restrict__ q32,
                                                          const double *__restrict__ tscore,
@@ -473,13 +477,22 @@ int skge_rank_sweep(int op, const float *Eshard, int64_t n_shard, int64_t shard_
   SKGE_REQUIRE((op == SKGE_RANK_L1 || op == SKGE_RANK_DOT) && d > 0 && n_shard >= 0 && Q >= 0, "bad sizes");
   if (Q == 0 || n_shard == 0) return 0;
   int64_t qtiles = (Q + BQ - 1) / BQ, etiles = (n_shard + BE - 1) / BE;
-  // split the entity range when there are too few query tiles to fill the GPU
-  int64_t want = 2 * kNumSMs;
-  int64_t ysplit = qtiles >= want ? 1 : (want + qtiles - 1) / qtiles;
-  if (ysplit > etiles) ysplit = etiles;
-  if (ysplit > 65535) ysplit = 65535;
-  int per = (int)((etiles + ysplit - 1) / ysplit);
-  ysplit = (etiles + per - 1) / per;
+  // Split the entity range so that the CTAs fill whole waves of the GPU (2 resident CTAs per SM):
+  // a 128-query tile against the whole shard is a long CTA, and a ragged last wave costs up to
+  // a full CTA time.  Take the smallest split whose wave efficiency is >= 97 %, else the best.
+  const int64_t slots = 2 * kNumSMs;
+  int64_t ysplit = 1;
+  int per = (int)etiles;
+  double best = -1.0;
+  for (int64_t ys = 1; ys <= etiles && ys <= 64; ++ys) {
+    const int64_t p = (etiles + ys - 1) / ys, yeff = (etiles + p - 1) / p;
+    if (yeff != ys) continue;  // same partition as a smaller split
+    const int64_t total = qtiles * ys, waves = (total + slots - 1) / slots;
+    // work is counted in entity tiles: the last slice of the split may be shorter than `per`
+    const double eff = (double)(qtiles * etiles) / ((double)waves * slots * p);
+    if (eff > best + 1e-9) { best = eff; ysplit = ys; per = (int)p; }
+    if (eff >= 0.97) break;
+  }
   dim3 grid((unsigned)qtiles, (unsigned)ysplit);
   cudaStream_t st = as_stream(stream);
   bool v4 = d % 4 == 0;

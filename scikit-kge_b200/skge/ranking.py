@@ -19,6 +19,7 @@ all-reduce of 2Q int32 counts combines them; results are identical on every
 rank and for every world size.
 """
 import logging
+import gc
 import math
 
 import numpy as np
@@ -130,16 +131,30 @@ def regroup(test, raw, filt):
     pos, fpos = {}, {}
     if te == 0:
         return pos, fpos
-    order = np.argsort(t[:, 2], kind='stable')          # triples of one relation stay in test order
+    rel = t[:, 2]
+    if rel.max() < 65536:
+        rel = rel.astype(np.uint16)                     # numpy's stable sort is a radix sort for 16-bit keys
+    order = np.argsort(rel, kind='stable')              # triples of one relation stay in test order
     ps = t[order, 2]
-    cuts = np.nonzero(np.diff(ps))[0] + 1
-    # permute once, then cut views (a fancy index per relation would dominate at 1k relations)
-    cols = [np.split(a, cuts) for a in (raw[order], raw[te + order], filt[order], filt[te + order])]
-    firsts = np.split(order, cuts)
-    for g in sorted(range(len(firsts)), key=lambda i: firsts[i][0]):      # relations in order of first appearance
-        p = int(t[firsts[g][0], 2])
-        pos[p] = {'head': cols[1][g].tolist(), 'tail': cols[0][g].tolist()}
-        fpos[p] = {'head': cols[3][g].tolist(), 'tail': cols[2][g].tolist()}
+    bounds = np.concatenate([[0], np.nonzero(np.diff(ps))[0] + 1, [te]]).tolist()
+    # permute once and convert to Python ints once; a relation's lists are then plain list slices
+    # (per-relation numpy views + tolist() dominate the pass at 1k relations)
+    tails, heads = raw[order].tolist(), raw[te + order].tolist()
+    ftails, fheads = filt[order].tolist(), filt[te + order].tolist()
+    first = order[bounds[:-1]]                          # first test position of each relation
+    rels = ps[bounds[:-1]].tolist()
+    # Thousands of new containers would trigger generational collections that each walk the four
+    # big lists; nothing here can form a cycle, so the collector is paused for the loop.
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        for g in np.argsort(first, kind='stable').tolist():  # relations in order of first appearance
+            a, b = bounds[g], bounds[g + 1]
+            pos[rels[g]] = {'head': heads[a:b], 'tail': tails[a:b]}
+            fpos[rels[g]] = {'head': fheads[a:b], 'tail': ftails[a:b]}
+    finally:
+        if gc_was_on:
+            gc.enable()
     return pos, fpos
 
 
