@@ -43,6 +43,29 @@ def main(worlds=(1, 2, 4, 8)):
         t1 = t1 or ms
         print('world %d: shard-0 pass %.1f ms (ideal %.1f ms) -> %.2f M queries/s if every rank takes this long'
               % (w, ms, t1 / w, Q / ms / 1e3), flush=True)
+    # phase breakdown of one world-1 pass (CUDA events around the library calls)
+    spans = {}
+
+    def wrap(name):
+        fn = getattr(kernels, name)
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            spans.setdefault(name, []).append((e0, e1))
+            return r
+        setattr(kernels, name, timed)
+        return fn
+    names = ['make_queries', 'rank_rescore', 'rank_gemm_count', 'pack_f16', 'query_scale', 'rank_sweep']
+    saved = {n: wrap(n) for n in names if hasattr(kernels, n)}
+    ev.count_pass(mdl, world=(0, 1))
+    torch.cuda.synchronize()
+    for n, fn in saved.items():
+        setattr(kernels, n, fn)
+    print('one pass: ' + ', '.join('%s %.2f ms x%d' % (n, sum(a.elapsed_time(b) for a, b in v), len(v))
+                                   for n, v in spans.items()), flush=True)
     enorm = float(torch.linalg.vector_norm(mdl.E.data, dim=1).max().item())
     mq = ev_ms(lambda: kernels.make_queries(ev.model_code, mdl.E.data, mdl.R.data, st['kind'], st['given'], st['rel'],
                                             st['target'], enorm, 2.0 ** -17))

@@ -398,6 +398,61 @@ __global__ void __launch_bounds__(256, 2) rank_sweep_kernel(const float *__restr
 // ---------------------------------------------------------------------------
 // fp64 settlement
 // ---------------------------------------------------------------------------
+// Four (query, entity) pairs by one warp.  NC > 0: d == 32 * NC, everything unrolled -- the 4 * NC
+// entity loads are issued before the first use, and when the four pairs share the query (the
+// lists are sorted by query) its row is read once.  NC == 0: any d.  Each pair's sum is formed
+// in score64_warp's order (c = lane, lane + 32, ...; then the warp tree), so the result is
+// bit-identical to the routine that produced the target score.
+template <int NC>
+__device__ __forceinline__ void settle4(int op, const double *__restrict__ q64, const float *__restrict__ E, int d,
+                                        const int (&qs)[4], const int (&es)[4], bool same, int lane,
+                                        double (&acc)[4]) {
+  const double *qp[4];
+  const float *ep[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    qp[k] = q64 + (int64_t)qs[k] * d;
+    ep[k] = E + (int64_t)es[k] * d;
+    acc[k] = 0.0;
+  }
+  if (NC > 0) {
+    constexpr int NCC = NC > 0 ? NC : 1;
+    float ev[4][NCC];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < NCC; ++j) ev[k][j] = __ldg(ep[k] + lane + 32 * j);
+    if (same) {
+      double qv[NCC];
+#pragma unroll
+      for (int j = 0; j < NCC; ++j) qv[j] = qp[0][lane + 32 * j];
+#pragma unroll
+      for (int j = 0; j < NCC; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          acc[k] = op == SKGE_RANK_L1 ? acc[k] + fabs((double)ev[k][j] - qv[j]) : fma((double)ev[k][j], qv[j], acc[k]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NCC; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double qv = qp[k][lane + 32 * j];
+          acc[k] = op == SKGE_RANK_L1 ? acc[k] + fabs((double)ev[k][j] - qv) : fma((double)ev[k][j], qv, acc[k]);
+        }
+    }
+  } else {
+    for (int c = lane; c < d; c += 32)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double qv = qp[k][c];
+        acc[k] = op == SKGE_RANK_L1 ? acc[k] + fabs((double)__ldg(ep[k] + c) - qv) : fma((double)__ldg(ep[k] + c), qv, acc[k]);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = op == SKGE_RANK_L1 ? -warp_sum(acc[k]) : warp_sum(acc[k]);
+}
+
+template <int NC>
 __global__ void __launch_bounds__(256) rank_rescore_kernel(int op, const float *__restrict__ E, int d,
                                                            const double *__restrict__ q64,
                                                            const double *__restrict__ tscore,
@@ -410,14 +465,29 @@ __global__ void __launch_bounds__(256) rank_rescore_kernel(int op, const float *
     unsigned long long n = *npairs_dev;
     if ((int64_t)n < npairs) npairs = (int64_t)n;
   }
+  if (npairs <= 0) return;
   const int lane = threadIdx.x & 31;
   int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t i = warp; i < npairs; i += nwarps) {
-    int q = pair_q[i], e = pair_e[i];
-    if (target && target[q] == e) continue;
-    double s = score64_warp(op, q64 + (int64_t)q * d, E + (int64_t)e * d, d, lane);
-    if (lane == 0 && s > tscore[q]) atomicAdd(cnt + q, 1);
+  for (int64_t base = warp * 4; base < npairs; base += nwarps * 4) {
+    int qs[4], es[4];
+    bool live[4];
+    bool same = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = base + k < npairs ? base + k : npairs - 1;
+      qs[k] = pair_q[i];
+      es[k] = pair_e[i];
+      live[k] = base + k < npairs && !(target && target[qs[k]] == es[k]);
+      same = same && qs[k] == qs[0];
+    }
+    double acc[4];
+    settle4<NC>(op, q64, E, d, qs, es, same, lane, acc);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (live[k] && acc[k] > tscore[qs[k]]) atomicAdd(cnt + qs[k], 1);
+    }
   }
 }
 
@@ -513,10 +583,23 @@ int skge_rank_rescore(int op, const float *Efull, int d, const double *q64, cons
   SKGE_REQUIRE(Efull && q64 && tscore && pair_q && pair_e && cnt, "null argument");
   SKGE_REQUIRE((op == SKGE_RANK_L1 || op == SKGE_RANK_DOT) && d > 0 && npairs >= 0, "bad sizes");
   if (npairs == 0) return 0;
-  int64_t blocks = (npairs + 7) / 8;
+  int64_t blocks = (npairs + 31) / 32;  // 8 warps x 4 pairs
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  rank_rescore_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(op, Efull, d, q64, tscore, pair_q, pair_e,
-                                                                 npairs, npairs_dev, target, cnt);
+#define SKGE_RESCORE(NC)                                                                                   \
+  rank_rescore_kernel<NC><<<(int)blocks, 256, 0, as_stream(stream)>>>(op, Efull, d, q64, tscore, pair_q, pair_e, \
+                                                                     npairs, npairs_dev, target, cnt)
+  switch (d % 32 == 0 && d <= 256 ? d / 32 : 0) {
+    case 1: SKGE_RESCORE(1); break;
+    case 2: SKGE_RESCORE(2); break;
+    case 3: SKGE_RESCORE(3); break;
+    case 4: SKGE_RESCORE(4); break;
+    case 5: SKGE_RESCORE(5); break;
+    case 6: SKGE_RESCORE(6); break;
+    case 7: SKGE_RESCORE(7); break;
+    case 8: SKGE_RESCORE(8); break;
+    default: SKGE_RESCORE(0); break;
+  }
+#undef SKGE_RESCORE
   SKGE_LAUNCH_CHECK();
   return 0;
 }
