@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256) hole_spectra_kernel(const float *__restri
   }
 }
 
-__global__ void __launch_bounds__(256) hole_pair_spec_kernel(const float *__restrict__ Ehat,
+__global__ void __launch_bounds__(256, 4) hole_pair_spec_kernel(const float *__restrict__ Ehat,
                                                              const float *__restrict__ Rhat, PairIdx ix, int64_t P,
                                                              int d, int af, float margin,
                                                              uint8_t *__restrict__ flags, float *__restrict__ G,

@@ -292,7 +292,7 @@ __device__ __forceinline__ int accumulate_rows(const SegArgs &a, int beg, int en
 
 // acc holds the SUM over the n occurrences of segment seg: take the mean and either apply
 // the optimiser step in place or emit (gradient row, row id).
-template <int VEC, int MAXC, bool UPDATE>
+template <int VEC, int MAXC, bool UPDATE, bool SPEC>
 __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, int n, int lane,
                                            float (&acc)[MAXC][VEC], float *spec_smem = nullptr, int warp_in_cta = 0) {
   const int d = a.d;
@@ -301,7 +301,7 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
   int64_t row = which ? key - a.N : key;
   const float inv_n = 1.0f / (float)n;
   float2 *tw = nullptr, *b0 = nullptr, *b1 = nullptr;
-  if (UPDATE && a.spec_logd > 0) {
+  if (UPDATE && SPEC) {
     // acc is a summed packed spectrum: back to the time domain
     const int h = d / 2;
     tw = reinterpret_cast<float2 *>(spec_smem);
@@ -335,7 +335,7 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
     row_update<VEC, MAXC>(pd.param + row * d, pd.p2 ? pd.p2 + row * d : nullptr, acc, d, lane, a.opt, a.lr,
                           pd.post, pd.rparam, x);
     if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
-    if (a.spec_logd > 0 && pd.hat) {
+    if (SPEC && pd.hat) {
       // refresh the row's packed spectrum from the updated time-domain row
       const int h = d / 2;
       __syncwarp();
@@ -370,10 +370,10 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
 
 // Pass 1: one warp per segment.  Short segments are finished here; long ones are registered
 // (segment, chunk range) for passes 2 and 3.
-template <int VEC, int MAXC, bool UPDATE, int BATCH>
-__global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
+template <int VEC, int MAXC, bool UPDATE, int BATCH, bool SPEC>
+__global__ void __launch_bounds__(256, (BATCH > 1 || MAXC > 2) ? 1 : 4) seg_reduce_kernel(SegArgs a) {
   extern __shared__ __align__(16) float spec_smem[];
-  if (UPDATE && a.spec_logd > 0) {
+  if (UPDATE && SPEC) {
     fill_twiddles(reinterpret_cast<float2 *>(spec_smem), a.d, threadIdx.x, blockDim.x);
     __syncthreads();
   }
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(SegArgs a) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
     const int occ = accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
-    finish_row<VEC, MAXC, UPDATE>(a, seg, key, occ, lane, acc, spec_smem, threadIdx.x >> 5);
+    finish_row<VEC, MAXC, UPDATE, SPEC>(a, seg, key, occ, lane, acc, spec_smem, threadIdx.x >> 5);
   }
 }
 
@@ -449,14 +449,14 @@ __global__ void __launch_bounds__(256) seg_long_chunks_kernel(SegArgs a) {
 
 // Pass 3: one CTA per long segment: warp w sums partials w, w + 8, ...; the eight warp sums are
 // combined through shared memory in warp order, then warp 0 finishes the row.
-template <int VEC, int MAXC, bool UPDATE>
+template <int VEC, int MAXC, bool UPDATE, bool SPEC>
 __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
   extern __shared__ __align__(16) float red[];  // [8][d], then the spectral scratch
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nlong = a.long_meta[0];
   const int d = a.d;
   float *spec_smem = red + 8 * d;
-  if (UPDATE && a.spec_logd > 0) {
+  if (UPDATE && SPEC) {
     fill_twiddles(reinterpret_cast<float2 *>(spec_smem), d, threadIdx.x, blockDim.x);
     __syncthreads();
   }
@@ -504,36 +504,43 @@ __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
       for (int k = lane; k < nch; k += 32) n += a.partial_occ[first + k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
-      finish_row<VEC, MAXC, UPDATE>(a, seg, a.seg_key[seg], n, lane, acc, spec_smem, 0);
+      finish_row<VEC, MAXC, UPDATE, SPEC>(a, seg, a.seg_key[seg], n, lane, acc, spec_smem, 0);
     }
   }
 }
 
-template <int VEC, int MAXC, int BATCH>
-static void launch_seg_reduce_b(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
-  const bool spec = update && a.spec_logd > 0;
-  size_t sm1 = spec ? spec_smem_bytes(a.d, 8) : 0;
+template <int VEC, int MAXC, int BATCH, bool SPEC>
+static void launch_seg_reduce_s(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
+  size_t sm1 = SPEC ? spec_smem_bytes(a.d, 8) : 0;
   if (update) {
     if (sm1 > 48 * 1024)
-      cudaFuncSetAttribute(seg_reduce_kernel<VEC, MAXC, true, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sm1);
-    seg_reduce_kernel<VEC, MAXC, true, BATCH><<<blocks, 256, sm1, st>>>(a);
+      cudaFuncSetAttribute(seg_reduce_kernel<VEC, MAXC, true, BATCH, SPEC>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    seg_reduce_kernel<VEC, MAXC, true, BATCH, SPEC><<<blocks, 256, sm1, st>>>(a);
   } else {
-    seg_reduce_kernel<VEC, MAXC, false, BATCH><<<blocks, 256, 0, st>>>(a);
+    seg_reduce_kernel<VEC, MAXC, false, BATCH, false><<<blocks, 256, 0, st>>>(a);
   }
   int cb = (a.long_chunk_cap + 7) / 8;
   if (cb > kNumSMs * 8) cb = kNumSMs * 8;
   seg_long_chunks_kernel<VEC, MAXC, BATCH><<<cb, 256, 0, st>>>(a);
   int sb = a.long_seg_cap < kNumSMs * 4 ? a.long_seg_cap : kNumSMs * 4;
-  size_t smem = (size_t)8 * a.d * sizeof(float) + (spec ? spec_smem_bytes(a.d, 8) : 0);
+  size_t smem = (size_t)8 * a.d * sizeof(float) + sm1;
   if (update) {
     if (smem > 48 * 1024)
-      cudaFuncSetAttribute(seg_long_finish_kernel<VEC, MAXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(seg_long_finish_kernel<VEC, MAXC, true, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)smem);
-    seg_long_finish_kernel<VEC, MAXC, true><<<sb, 256, smem, st>>>(a);
+    seg_long_finish_kernel<VEC, MAXC, true, SPEC><<<sb, 256, smem, st>>>(a);
   } else {
-    seg_long_finish_kernel<VEC, MAXC, false><<<sb, 256, smem, st>>>(a);
+    seg_long_finish_kernel<VEC, MAXC, false, false><<<sb, 256, smem, st>>>(a);
   }
+}
+
+// The spectral (HolE, frequency-domain) variant carries the warp FFTs; keeping it a separate
+// instantiation leaves the plain update kernel with fewer registers.
+template <int VEC, int MAXC, int BATCH>
+static void launch_seg_reduce_b(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
+  if (update && a.spec_logd > 0) launch_seg_reduce_s<VEC, MAXC, BATCH, true>(a, update, blocks, st);
+  else launch_seg_reduce_s<VEC, MAXC, BATCH, false>(a, update, blocks, st);
 }
 
 template <int VEC, int MAXC>
