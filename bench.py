@@ -56,6 +56,8 @@ def parse():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--train-batches', type=int, default=6)
     ap.add_argument('--engine', default='auto', choices=['auto', 'sweep', 'umma'])
+    ap.add_argument('--nsplit', type=int, default=0, choices=[0, 1, 2, 3],
+                    help='tcgen05 engine: fp16 products on the tensor cores (0 = the evaluator default)')
     return ap.parse_args()
 
 
@@ -223,6 +225,8 @@ def run_b200(args):
     ev = Ev(test, true)
     if args.engine != 'auto':
         ev.engine = args.engine
+    if args.nsplit:
+        ev.nsplit = args.nsplit
     del true, g
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup

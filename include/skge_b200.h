@@ -260,16 +260,27 @@ SKGE_API int skge_rank_scores_one(int op, const float *E, int64_t N, int d, cons
  * cores with fp32 accumulation in TMEM; the epilogue compares against the
  * per-query thresholds straight out of TMEM and never stores a score. */
 SKGE_API size_t skge_rank_packed_bytes(int64_t rows, int d); /* bytes of ONE (hi or lo) packed array */
+/* lo_rowmajor (nullable): a second, row-major copy of the lo parts, [rows padded to 128][64 * ceil(d / 64)]
+ * halfs -- the entity-side `Elo` argument of skge_rank_gemm_count when nsplit == 2.
+ * lo_norm2 (nullable, [rows], zeroed by the caller): += squared L2 norm of each row's lo part. */
 SKGE_API int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_scale,
-                       float scalar_scale, void *hi, void *lo, skge_stream_t stream);
+                       float scalar_scale, void *hi, void *lo, void *lo_rowmajor, float *lo_norm2,
+                       skge_stream_t stream);
 /* Per-query power-of-two scale (max|q| * qscale in [2^11, 2^12)) and the scaled
  * thresholds thr = (tscore -+ eps) * qscale * escale, rounded outwards. */
 SKGE_API int skge_rank_query_scale(const float *q32, const double *tscore, const float *eps, int64_t Q, int d,
                           float escale, float *qscale, float *thr_lo, float *thr_hi,
                           skge_stream_t stream);
+/* nsplit: 1 = hi*hi only (fp16 accuracy), 3 = hi*hi + hi*lo + lo*hi on the tensor cores,
+ * 2 = q_hi*e_hi + q_lo*e_hi on the tensor cores; the accumulator is then tested against
+ * thr_*_wide (the tight thresholds widened by >= ||q|| max_e ||e_lo|| in scaled units), and
+ * pairs inside the wide band get (q_hi + q_lo) . e_lo added in the epilogue before the tight
+ * test; Elo must then be the row-major lo array of skge_rank_pack_f16.  thr_*_wide may be NULL
+ * unless nsplit == 2. */
 SKGE_API int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
                          const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
-                         const float *thr_lo, const float *thr_hi, int32_t *cnt_gt,
+                         const float *thr_lo, const float *thr_hi, const float *thr_lo_wide,
+                         const float *thr_hi_wide, int32_t *cnt_gt,
                          int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                          unsigned long long *cand_count, skge_stream_t stream);
 

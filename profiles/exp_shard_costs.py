@@ -34,6 +34,8 @@ def main(worlds=(1, 2, 4, 8)):
     mdl.E.data.copy_(E)
     mdl.R.data.copy_(R)
     ev = ranking.HolEEval(g['test'], true)
+    ev.nsplit = int(os.environ.get('SKGE_NSPLIT', ev.nsplit))
+    print('nsplit', ev.nsplit, flush=True)
     del true, g
     st = ev._device_state()
     Q = 2 * Te

@@ -14,6 +14,17 @@
 // the same TMEM tile, which reproduces the fp32 inputs to ~2^-21 relative.  The
 // thresholds already contain the (power-of-two) scales.
 //
+// nsplit = 2 ("refine" mode) issues only the two products that share the entity operand,
+// q_hi*e_hi + q_lo*e_hi.  What is missing, (q_hi + q_lo) . e_lo, is bounded by
+// ||q|| max_e ||e_lo|| ~ 2^-13 ||q|| ||e||, so the epilogue first tests against thresholds
+// widened by that bound; the ~0.2 % of pairs that fall into the wide band get the missing
+// term added by their epilogue warp (32 lanes x 8 k each: q from the resident shared-memory
+// tile, e_lo straight from the L2-resident slice) and are then tested against the tight
+// thresholds exactly like an nsplit = 3 accumulator.  A third of the tensor-core work and half
+// of the shared-memory fill traffic are gone; counts and candidates are identical in meaning.
+// In this mode GemmArgs::Elo is the ROW-MAJOR copy of the lo parts ([rows padded to 128][kch * 64],
+// skge_rank_pack_f16's optional third output): a gathered row is 4 contiguous lines.
+//
 // Memory layout (produced by skge_rank_pack_f16): rows are grouped in tiles of
 // 128, k in chunks of 64; one (tile, chunk) block is 16 KB laid out as UMMA
 // K-major, no-swizzle core matrices:  [kcore 8][rowgroup 16][row 8][8 halfs],
@@ -32,7 +43,10 @@ static constexpr int KCHUNK = 64;                      // k per block
 static constexpr int BLOCK_HALFS = TILE * KCHUNK;      // 8192 halfs = 16 KB
 static constexpr int BLOCK_BYTES = BLOCK_HALFS * 2;
 static constexpr int MAX_KCH = 4;                      // d <= 256
-static constexpr int B_STAGES = 3;
+static constexpr int B_STAGES = 3;                     // stages of (hi, lo) entity blocks
+static constexpr int B_STAGES_REFINE = 5;              // refine mode: stages of hi blocks only
+static constexpr int MAX_B_STAGES = 5;
+static constexpr int LIST_CAP = 32;                    // refine mode: wide-band pairs per warp and tile
 static constexpr int ACC_STAGES = 4;                   // 4 x 128 TMEM columns
 static constexpr int STAGING = 192;                    // candidate staging entries in smem
 static constexpr uint32_t LBO_BYTES = 2048, SBO_BYTES = 128;
@@ -110,12 +124,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- shared-memory plan ----------------------------------------------------------
 struct __align__(8) Ctrl {
   uint64_t a_full, a_empty;
-  uint64_t b_full[B_STAGES], b_empty[B_STAGES];
+  uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
   uint64_t acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
   uint32_t tmem_base;
   int stage_count;
   unsigned long long base_slot;
   int stage_q[STAGING], stage_e[STAGING];
+};
+// refine mode only (carved after Ctrl): per epilogue warp, the wide-band pairs of the current tile
+struct WideLists {
+  float score[16][LIST_CAP];   // coarse score
+  int rc[16][LIST_CAP];        // lane << 8 | column in tile
+  int count[16];
 };
 
 struct GemmArgs {
@@ -123,6 +143,7 @@ struct GemmArgs {
   int64_t n_shard, shard_base, Q;
   int kch, nsplit;
   const float *thr_lo, *thr_hi;
+  const float *thr_lo_wide, *thr_hi_wide;   // refine mode
   int32_t *cnt_gt, *cand_q, *cand_e;
   int64_t cand_cap;
   unsigned long long *cand_count;
@@ -187,27 +208,89 @@ __device__ __forceinline__ void push_band(Ctrl *ctrl, const GemmArgs &a, int q, 
   }
 }
 
-__global__ void __launch_bounds__(384, 1) rank_gemm_kernel(GemmArgs a) {
+__device__ __forceinline__ void push_one(Ctrl *ctrl, const GemmArgs &a, int q, int e) {
+  int pos = atomicAdd(&ctrl->stage_count, 1);
+  if (pos < STAGING) {
+    ctrl->stage_q[pos] = q;
+    ctrl->stage_e[pos] = e;
+  } else {
+    unsigned long long slot = atomicAdd(a.cand_count, 1ull);
+    if ((int64_t)slot < a.cand_cap) {
+      a.cand_q[slot] = q;
+      a.cand_e[slot] = e;
+    }
+  }
+}
+
+// refine mode: the few pairs that stay undecided after the refinement go straight to the global
+// list (no staging, so the epilogue warps never meet at a barrier)
+__device__ __forceinline__ void push_global(const GemmArgs &a, int q, int e) {
+  unsigned long long slot = atomicAdd(a.cand_count, 1ull);
+  if ((int64_t)slot < a.cand_cap) {
+    a.cand_q[slot] = q;
+    a.cand_e[slot] = e;
+  }
+}
+
+// r[j] for a run-time j without spilling the array: a 5-level multiplexer
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int j) {
+  uint32_t a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+  const uint32_t d0 = (j & 8) ? c[1] : c[0], d1 = (j & 8) ? c[3] : c[2];
+  return (j & 16) ? d1 : d0;
+}
+
+// sum over 8 k of (q_hi + q_lo) * e_lo for one 16-byte chunk of each operand.  The term is a
+// correction of relative size 2^-12, so packed fp16 arithmetic is enough: |q_hi| < 2^12 and
+// |e_lo| <= 1 in scaled units, four products per half2 lane stay below 2^14, and the fp16
+// roundings contribute < 2^-21 ||q|| ||e|| (covered by the 2^-17 band).
+__device__ __forceinline__ float chunk_dot(const uint4 &qh, const uint4 &ql, const uint4 &el) {
+  const __half2 *h = reinterpret_cast<const __half2 *>(&qh), *l = reinterpret_cast<const __half2 *>(&ql);
+  const __half2 *e = reinterpret_cast<const __half2 *>(&el);
+  __half2 acc = __hmul2(h[0], e[0]);
+  acc = __hfma2(h[1], e[1], acc);
+  acc = __hfma2(h[2], e[2], acc);
+  acc = __hfma2(h[3], e[3], acc);
+  __half2 acl = __hmul2(l[0], e[0]);
+  acl = __hfma2(l[1], e[1], acl);
+  acl = __hfma2(l[2], e[2], acl);
+  acl = __hfma2(l[3], e[3], acl);
+  const float2 a = __half22float2(acc), b = __half22float2(acl);
+  return (a.x + a.y) + (b.x + b.y);
+}
+
+template <bool REFINE>
+__global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // carve: A (kch blocks hi, kch blocks lo), B stages (hi, lo), control.  No-swizzle
   // descriptors and bulk copies only need 16-byte alignment.
   uint8_t *sA_hi = smem_raw;
   uint8_t *sA_lo = sA_hi + a.kch * BLOCK_BYTES;
-  uint8_t *sB = sA_lo + a.kch * BLOCK_BYTES;  // stage s: hi at s*2*BLOCK, lo right after
-  Ctrl *ctrl = reinterpret_cast<Ctrl *>(sB + B_STAGES * 2 * BLOCK_BYTES);
+  uint8_t *sB = sA_lo + a.kch * BLOCK_BYTES;  // stage s: hi at s*BSTRIDE, lo right after (not in refine mode)
+  constexpr int NB = REFINE ? B_STAGES_REFINE : B_STAGES;
+  constexpr int BSTRIDE = REFINE ? BLOCK_BYTES : 2 * BLOCK_BYTES;
+  Ctrl *ctrl = reinterpret_cast<Ctrl *>(sB + NB * BSTRIDE);
+  WideLists *wl = reinterpret_cast<WideLists *>(ctrl + 1);   // refine mode only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kch = a.kch;
   const int nitems = a.qtiles * a.nslices;
-  const int nprod = a.nsplit == 1 ? 1 : 3;
-  const bool use_lo = nprod == 3;
+  const bool use_lo = REFINE || a.nsplit == 3;   // q_lo resident / multiplied
+  const bool use_b_lo = !REFINE && a.nsplit == 3; // e_lo streamed through shared memory
 
   if (threadIdx.x == 0) {
     mbar_init(&ctrl->a_full, 1);
-    mbar_init(&ctrl->a_empty, 1);
-    for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ctrl->b_full[s], 1); mbar_init(&ctrl->b_empty[s], 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&ctrl->acc_full[s], 1); mbar_init(&ctrl->acc_empty[s], 8); }
+    // refine mode: the epilogue warps read the query tile too, so they release it as well
+    mbar_init(&ctrl->a_empty, REFINE ? 17 : 1);
+    for (int s = 0; s < NB; ++s) { mbar_init(&ctrl->b_full[s], 1); mbar_init(&ctrl->b_empty[s], 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&ctrl->acc_full[s], 1); mbar_init(&ctrl->acc_empty[s], REFINE ? 4 : 8); }
     ctrl->stage_count = 0;
+    if (REFINE) for (int w = 0; w < 16; ++w) wl->count[w] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -227,7 +310,7 @@ __global__ void __launch_bounds__(384, 1) rank_gemm_kernel(GemmArgs a) {
     if (lane == 0) {
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       const uint32_t a_bytes = (uint32_t)kch * BLOCK_BYTES * (use_lo ? 2 : 1);
-      const uint32_t b_bytes = (uint32_t)BLOCK_BYTES * (use_lo ? 2 : 1);
+      const uint32_t b_bytes = (uint32_t)BLOCK_BYTES * (use_b_lo ? 2 : 1);
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const Item it = get_item(a, item);
         mbar_wait(&ctrl->a_empty, aphase ^ 1);  // previous item's MMAs retired
@@ -243,11 +326,11 @@ __global__ void __launch_bounds__(384, 1) rank_gemm_kernel(GemmArgs a) {
           for (int c = 0; c < kch; ++c) {
             mbar_wait(&ctrl->b_empty[bstage], bphase ^ 1);
             mbar_expect_tx(&ctrl->b_full[bstage], b_bytes);
-            uint8_t *dst = sB + bstage * 2 * BLOCK_BYTES;
+            uint8_t *dst = sB + bstage * BSTRIDE;
             int64_t off = ((int64_t)et * kch + c) * BLOCK_HALFS;
             bulk_g2s(dst, a.Ehi + off, BLOCK_BYTES, &ctrl->b_full[bstage]);
-            if (use_lo) bulk_g2s(dst + BLOCK_BYTES, a.Elo + off, BLOCK_BYTES, &ctrl->b_full[bstage]);
-            if (++bstage == B_STAGES) { bstage = 0; bphase ^= 1; }
+            if (use_b_lo) bulk_g2s(dst + BLOCK_BYTES, a.Elo + off, BLOCK_BYTES, &ctrl->b_full[bstage]);
+            if (++bstage == NB) { bstage = 0; bphase ^= 1; }
           }
         }
       }
@@ -269,19 +352,17 @@ __global__ void __launch_bounds__(384, 1) rank_gemm_kernel(GemmArgs a) {
             mbar_wait(&ctrl->b_full[bstage], bphase);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(sA_hi + c * BLOCK_BYTES), a_lo = smem_u32(sA_lo + c * BLOCK_BYTES);
-            const uint32_t b_hi = smem_u32(sB + bstage * 2 * BLOCK_BYTES), b_lo = b_hi + BLOCK_BYTES;
+            const uint32_t b_hi = smem_u32(sB + bstage * BSTRIDE), b_lo = b_hi + BLOCK_BYTES;
 #pragma unroll
             for (int ks = 0; ks < KCHUNK / 16; ++ks) {
               const uint32_t koff = ks * 2 * LBO_BYTES;  // one MMA consumes two k core matrices
               umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), IDESC, acc_on);
               acc_on = 1;
-              if (use_lo) {
-                umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), IDESC, 1);
-                umma_f16(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), IDESC, 1);
-              }
+              if (use_b_lo) umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), IDESC, 1);
+              if (use_lo) umma_f16(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), IDESC, 1);
             }
             tc_commit(&ctrl->b_empty[bstage]);  // frees the stage once these MMAs have read it
-            if (++bstage == B_STAGES) { bstage = 0; bphase ^= 1; }
+            if (++bstage == NB) { bstage = 0; bphase ^= 1; }
           }
           tc_commit(&ctrl->acc_full[accs]);  // accumulator complete -> epilogue
           if (++accs == ACC_STAGES) { accs = 0; accphase ^= 1; }
@@ -291,57 +372,168 @@ __global__ void __launch_bounds__(384, 1) rank_gemm_kernel(GemmArgs a) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> compare -> count / candidates =====================
-    // 8 warps: warp % 4 is the TMEM lane quarter a warp may read, (warp - 4) / 4 the column half
-    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int quarter = warp & 3, cpart = (warp - 4) >> 2, w16 = warp - 4;   // cpart: column half / quad
     const int row = quarter * 32 + lane;  // query row inside the tile
     const int tid256 = threadIdx.x - 128;
-    uint32_t accs = 0, accphase = 0;
+    uint32_t accs = 0, accphase = 0, tseq = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const Item it = get_item(a, item);
       const int64_t q = (int64_t)it.qt * TILE + row;
-      float thi = INFINITY, tlo = INFINITY;
-      if (q < a.Q) { thi = a.thr_hi[q]; tlo = a.thr_lo[q]; }
+      float thi = INFINITY, tlo = INFINITY;       // tight thresholds: t +- eps
+      float whi = INFINITY, wlo = INFINITY;       // refine mode: widened by the missing-product bound
+      if (q < a.Q) {
+        thi = a.thr_hi[q];
+        tlo = a.thr_lo[q];
+        if (REFINE) { whi = a.thr_hi_wide[q]; wlo = a.thr_lo_wide[q]; }
+      }
       int cnt = 0;
       for (int et = it.et_beg; et < it.et_end; ++et) {
-        mbar_wait(&ctrl->acc_full[accs], accphase);
-        tc_fence_after();
         const int64_t e0 = (int64_t)et * TILE;
         const int nvalid = (int)min((int64_t)TILE, a.n_shard - e0);
-        const int col0 = half * 64;
-        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + accs * TILE + col0;
-        uint32_t r0[32], r1[32];
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 32, r1);
-        tmem_ld_wait();
-        // the accumulator is in registers: hand the TMEM stage back before the compare work
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->acc_empty[accs]);
-        if (++accs == ACC_STAGES) { accs = 0; accphase ^= 1; }
+        if (!REFINE) {
+          mbar_wait(&ctrl->acc_full[accs], accphase);
+          tc_fence_after();
+          const int col0 = cpart * 64;
+          const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + accs * TILE + col0;
+          uint32_t r[2][32];
+          tmem_ld32(taddr, r[0]);
+          tmem_ld32(taddr + 32, r[1]);
+          tmem_ld_wait();
+          // the accumulator is in registers: hand the TMEM stage back before the compare work
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctrl->acc_empty[accs]);
+          if (++accs == ACC_STAGES) { accs = 0; accphase ^= 1; }
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          // bit j of mhi / mlo: column j beats thr_hi / reaches thr_lo (4 partial masks keep the
-          // dependency chains short)
-          uint32_t mh[4] = {0u, 0u, 0u, 0u}, ml[4] = {0u, 0u, 0u, 0u};
+          for (int c2 = 0; c2 < 2; ++c2) {
+            // bit j of mhi / mlo: column j beats thr_hi / reaches thr_lo (4 partial masks keep
+            // the dependency chains short)
+            uint32_t mh[4] = {0u, 0u, 0u, 0u}, ml[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(c2 == 0 ? r0[j] : r1[j]);
-            if (v > thi) mh[j & 3] |= 1u << j;
-            if (v >= tlo) ml[j & 3] |= 1u << j;
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[c2][j]);
+              if (v > thi) mh[j & 3] |= 1u << j;
+              if (v >= tlo) ml[j & 3] |= 1u << j;
+            }
+            uint32_t mhi = (mh[0] | mh[1]) | (mh[2] | mh[3]), mlo = (ml[0] | ml[1]) | (ml[2] | ml[3]);
+            const int left = nvalid - (col0 + c2 * 32);
+            if (left < 32) {  // last, partial entity tile
+              uint32_t vm = left <= 0 ? 0u : (0xFFFFFFFFu >> (32 - left));
+              mhi &= vm;
+              mlo &= vm;
+            }
+            cnt += __popc(mhi);
+            uint32_t band = mlo & ~mhi;  // inside [thr_lo, thr_hi]: settle in fp64 later
+            if (band) push_band(ctrl, a, (int)q, (int)(a.shard_base + e0 + col0 + c2 * 32), band);
           }
-          uint32_t mhi = (mh[0] | mh[1]) | (mh[2] | mh[3]), mlo = (ml[0] | ml[1]) | (ml[2] | ml[3]);
-          const int left = nvalid - (col0 + c2 * 32);
-          if (left < 32) {  // last, partial entity tile
-            uint32_t vm = left <= 0 ? 0u : (0xFFFFFFFFu >> (32 - left));
-            mhi &= vm;
-            mlo &= vm;
+          // the flush decision must be uniform across the 256 epilogue threads: take it at fixed points
+          if (((et - it.et_beg) & 15) == 15 || et == it.et_end - 1) flush_staging(ctrl, a, tid256);
+        } else {
+          const uint32_t my = tseq++;
+          if ((int)(my & 3u) != cpart) continue;    // another quad's tile
+          const uint32_t stage = my & 3u;
+          mbar_wait(&ctrl->acc_full[stage], (my >> 2) & 1u);
+          tc_fence_after();
+          const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + stage * TILE;
+          for (int c2 = 0; c2 < 4; ++c2) {
+            uint32_t r[32];
+            tmem_ld32(taddr + 32 * c2, r);
+            tmem_ld_wait();
+            if (c2 == 3) {  // all 128 columns are in flight or consumed: hand the TMEM stage back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ctrl->acc_empty[stage]);
+            }
+            uint32_t mh[4] = {0u, 0u, 0u, 0u}, ml[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]);
+              if (v > whi) mh[j & 3] |= 1u << j;
+              if (v >= wlo) ml[j & 3] |= 1u << j;
+            }
+            uint32_t mhi = (mh[0] | mh[1]) | (mh[2] | mh[3]), mlo = (ml[0] | ml[1]) | (ml[2] | ml[3]);
+            const int left = nvalid - c2 * 32;
+            if (left < 32) {
+              uint32_t vm = left <= 0 ? 0u : (0xFFFFFFFFu >> (32 - left));
+              mhi &= vm;
+              mlo &= vm;
+            }
+            cnt += __popc(mhi);
+            uint32_t band = mlo & ~mhi;  // inside the WIDE band: needs the missing product
+            // every lane walks its own bits and appends (lane, column, coarse score) to the warp's
+            // list; the accumulator registers are read through a multiplexer
+            while (band) {
+              const int j = __ffs(band) - 1;
+              band &= band - 1;
+              const int idx = atomicAdd(&wl->count[w16], 1);
+              if (idx < LIST_CAP) {
+                wl->score[w16][idx] = __uint_as_float(pick32(r, j));
+                wl->rc[w16][idx] = (lane << 8) | (c2 * 32 + j);
+              } else {
+                // list full (rare): let the fp64 pass settle this pair
+                push_global(a, (int)q, (int)(a.shard_base + e0 + c2 * 32 + j));
+              }
+            }
           }
-          cnt += __popc(mhi);
-          uint32_t band = mlo & ~mhi;  // inside [thr_lo, thr_hi]: settle in fp64 later
-          if (band) push_band(ctrl, a, (int)q, (int)(a.shard_base + e0 + col0 + c2 * 32), band);
+          __syncwarp();
+          // Add (q_hi + q_lo) . e_lo to the coarse score of every listed pair.  Eight pairs per
+          // batch, four lanes per pair: lane 8 p + s takes the 16-byte k-chunks p, p + 4, ... of
+          // pair s (chunk c = block c / 8, core matrix c % 8).  In the K-major core-matrix layout
+          // all chunks of one query row live in the same four banks, and a 128-bit shared load is
+          // served per quarter-warp: lanes 8 p .. 8 p + 7 belong to eight different pairs, so they
+          // collide only where two rows agree modulo 8 (bucketing the list by row & 7 made the
+          // loads conflict-free but doubled the number of half-empty batches: slower).
+          const int slot = lane & 7, part = lane >> 3;
+          const int n = min(wl->count[w16], LIST_CAP);
+          if (n) {
+            __syncwarp();
+            if (lane == 0) wl->count[w16] = 0;
+            for (int b = 0; b < n; b += 8) {
+              const bool mine = b + slot < n;
+              const float sc = mine ? wl->score[w16][b + slot] : 0.f;
+              const int rc = mine ? wl->rc[w16][b + slot] : 0;
+              const int qr = quarter * 32 + (rc >> 8), col = rc & 255;
+              const uint32_t qbase = (qr >> 3) * SBO_BYTES + (qr & 7) * 16;
+              const __half *ebase = a.Elo + (e0 + col) * (int64_t)(kch * KCHUNK);   // row-major lo rows
+              uint4 el[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const int ch = part + 4 * t;          // k-chunk 0 .. 31
+                if (mine && ch < kch * 8)
+                  el[t] = __ldg(reinterpret_cast<const uint4 *>(ebase + ch * 8));
+              }
+              float acc = 0.f;
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const int ch = part + 4 * t;
+                if (mine && ch < kch * 8) {
+                  const uint32_t qoff = (ch >> 3) * BLOCK_BYTES + (ch & 7) * LBO_BYTES + qbase;
+                  acc += chunk_dot(*reinterpret_cast<const uint4 *>(sA_hi + qoff),
+                                   *reinterpret_cast<const uint4 *>(sA_lo + qoff), el[t]);
+                }
+              }
+              acc += __shfl_xor_sync(kFull, acc, 8);
+              acc += __shfl_xor_sync(kFull, acc, 16);
+              const float s2 = sc + acc;
+              // deliver each pair's refined score to the lane that owns its query row
+              const uint32_t have = __ballot_sync(kFull, mine);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float su = __shfl_sync(kFull, s2, u);
+                const int ru = __shfl_sync(kFull, rc, u);
+                if (((have >> u) & 1u) && lane == (ru >> 8)) {
+                  if (su > thi) ++cnt;
+                  else if (su >= tlo) push_global(a, (int)q, (int)(a.shard_base + e0 + (ru & 255)));
+                }
+              }
+            }
+            __syncwarp();
+          }
         }
-        // the flush decision must be uniform across the 256 epilogue threads: take it at fixed points
-        if (((et - it.et_beg) & 15) == 15 || et == it.et_end - 1) flush_staging(ctrl, a, tid256);
+      }
+      if (REFINE) {  // this warp no longer reads the resident query tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->a_empty);
       }
       if (q < a.Q && cnt) atomicAdd(a.cnt_gt + q, cnt);
     }
@@ -359,8 +551,9 @@ __global__ void __launch_bounds__(384, 1) rank_gemm_kernel(GemmArgs a) {
 // (row, group of 8 k): two 16-byte stores.
 __global__ void __launch_bounds__(256) pack_f16_kernel(const float *__restrict__ X, int64_t rows, int d,
                                                        const float *__restrict__ row_scale, float scalar_scale,
-                                                       __half *__restrict__ hi, __half *__restrict__ lo, int kch,
-                                                       int64_t rows_padded) {
+                                                       __half *__restrict__ hi, __half *__restrict__ lo,
+                                                       __half *__restrict__ lo_rm, float *__restrict__ lo_norm2,
+                                                       int kch, int64_t rows_padded) {
   const int groups = kch * (KCHUNK / 8);
   int64_t total = rows_padded * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -382,6 +575,18 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const float *__restrict__
     int64_t off = (tile * kch + c) * (int64_t)BLOCK_HALFS + (int64_t)kcore * (16 * 64) + (rr >> 3) * 64 + (rr & 7) * 8;
     *reinterpret_cast<uint4 *>(hi + off) = *reinterpret_cast<const uint4 *>(h);
     *reinterpret_cast<uint4 *>(lo + off) = *reinterpret_cast<const uint4 *>(l);
+    // optional row-major copy of the lo part ([rows_padded][kch * 64]): what the refine-mode
+    // epilogue gathers (a row's chunks are contiguous here, 2 KB apart in the blocked layout)
+    if (lo_rm) *reinterpret_cast<uint4 *>(lo_rm + r * (int64_t)(kch * KCHUNK) + g * 8) = *reinterpret_cast<const uint4 *>(l);
+    if (lo_norm2) {  // squared norm of the row's lo part (pre-zeroed by the caller): bounds the product refine mode defers
+      float p2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = __half2float(l[i]);
+        p2 = fmaf(x, x, p2);
+      }
+      if (r < rows && p2 != 0.f) atomicAdd(lo_norm2 + r, p2);
+    }
   }
 }
 
@@ -426,7 +631,7 @@ size_t skge_rank_packed_bytes(int64_t rows, int d) {
 }
 
 int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_scale, float scalar_scale,
-                       void *hi, void *lo, skge_stream_t stream) {
+                       void *hi, void *lo, void *lo_rowmajor, float *lo_norm2, skge_stream_t stream) {
   SKGE_REQUIRE(X && hi && lo && rows > 0 && d > 0, "bad arguments");
   int kch = (d + KCHUNK - 1) / KCHUNK;
   int64_t rp = round_up(rows, TILE);
@@ -435,7 +640,7 @@ int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_sca
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   pack_f16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(X, rows, d, row_scale, scalar_scale,
                                                              static_cast<__half *>(hi), static_cast<__half *>(lo),
-                                                             kch, rp);
+                                                             static_cast<__half *>(lo_rowmajor), lo_norm2, kch, rp);
   SKGE_LAUNCH_CHECK();
   return 0;
 }
@@ -454,13 +659,15 @@ int skge_rank_query_scale(const float *q32, const double *tscore, const float *e
 
 int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
                          const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
-                         const float *thr_lo, const float *thr_hi, int32_t *cnt_gt,
+                         const float *thr_lo, const float *thr_hi, const float *thr_lo_wide,
+                         const float *thr_hi_wide, int32_t *cnt_gt,
                          int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                          unsigned long long *cand_count, skge_stream_t stream) {
   SKGE_REQUIRE(Ehi && Elo && Qhi && Qlo && thr_lo && thr_hi && cnt_gt && cand_q && cand_e && cand_count,
                "null argument");
   SKGE_REQUIRE(d > 0 && d <= MAX_KCH * KCHUNK, "the tcgen05 ranking kernel supports d <= 256");
-  SKGE_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
+  SKGE_REQUIRE(nsplit >= 1 && nsplit <= 3, "nsplit must be 1, 2 or 3");
+  SKGE_REQUIRE(nsplit != 2 || (thr_lo_wide && thr_hi_wide), "nsplit = 2 needs the widened thresholds");
   SKGE_REQUIRE(n_shard >= 0 && Q >= 0, "bad sizes");
   if (Q == 0 || n_shard == 0) return 0;
   GemmArgs a;
@@ -475,6 +682,8 @@ int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int6
   a.nsplit = nsplit;
   a.thr_lo = thr_lo;
   a.thr_hi = thr_hi;
+  a.thr_lo_wide = thr_lo_wide;
+  a.thr_hi_wide = thr_hi_wide;
   a.cnt_gt = cnt_gt;
   a.cand_q = cand_q;
   a.cand_e = cand_e;
@@ -482,8 +691,14 @@ int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int6
   a.cand_count = cand_count;
   a.qtiles = (int)((Q + TILE - 1) / TILE);
   a.etiles = (int)((n_shard + TILE - 1) / TILE);
-  size_t smem = (size_t)2 * a.kch * BLOCK_BYTES + (size_t)B_STAGES * 2 * BLOCK_BYTES + sizeof(Ctrl);
-  SKGE_CUDA(cudaFuncSetAttribute(rank_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool refine = nsplit == 2;
+  size_t smem = (size_t)2 * a.kch * BLOCK_BYTES +
+                (refine ? (size_t)B_STAGES_REFINE * BLOCK_BYTES + sizeof(WideLists) : (size_t)B_STAGES * 2 * BLOCK_BYTES) +
+                sizeof(Ctrl);
+  if (refine)
+    SKGE_CUDA(cudaFuncSetAttribute(rank_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    SKGE_CUDA(cudaFuncSetAttribute(rank_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // slices of at most ~48 MB (hi + lo) so a slice stays L2-resident while every query tile
   // sweeps it; more slices when there are too few query tiles to fill the machine
   int tps = (48 << 20) / (a.kch * 2 * BLOCK_BYTES);
@@ -493,7 +708,8 @@ int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int6
   a.nslices = (a.etiles + tps - 1) / tps;
   int64_t nitems = (int64_t)a.qtiles * a.nslices;
   int grid = nitems < kNumSMs ? (int)nitems : kNumSMs;
-  rank_gemm_kernel<<<grid, 384, smem, as_stream(stream)>>>(a);
+  if (refine) rank_gemm_kernel<true><<<grid, 640, smem, as_stream(stream)>>>(a);
+  else rank_gemm_kernel<false><<<grid, 384, smem, as_stream(stream)>>>(a);
   SKGE_LAUNCH_CHECK();
   return 0;
 }

@@ -235,16 +235,19 @@ def rank_scores_one(op, E, q64_row):
     return out
 
 
-def pack_f16(X, row_scale, scalar_scale):
-    """fp32 [rows, d] -> (hi, lo) fp16 UMMA blocks (uint8 tensors)."""
+def pack_f16(X, row_scale, scalar_scale, lo_rowmajor=False):
+    """fp32 [rows, d] -> (hi, lo) fp16 UMMA blocks (uint8 tensors); with ``lo_rowmajor`` also the
+    row-major copy of the lo parts (the refine-mode gather operand) and each row's squared lo norm."""
     rows, d = X.shape
     nbytes = lib().skge_rank_packed_bytes(rows, d)
     hi = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
     lo = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
+    lo_rm = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device()) if lo_rowmajor else None
+    lo_n2 = torch.zeros(rows, dtype=torch.float32, device=_ext.device()) if lo_rowmajor else None
     _count('pack')
     check(lib().skge_rank_pack_f16(ptr(X), rows, d, ptr(row_scale), float(scalar_scale), ptr(hi), ptr(lo),
-                                   stream()))
-    return hi, lo
+                                   ptr(lo_rm), ptr(lo_n2), stream()))
+    return (hi, lo, lo_rm, lo_n2) if lo_rowmajor else (hi, lo)
 
 
 def query_scale(q, escale):
@@ -257,8 +260,8 @@ def query_scale(q, escale):
 
 
 def rank_gemm_count(Ehi, Elo, n_shard, shard_base, Qhi, Qlo, Q, d, nsplit, tlo, thi, cnt_gt, cand_q, cand_e,
-                    cand_count):
+                    cand_count, tlo_wide=None, thi_wide=None):
     _count('gemm')
     check(lib().skge_rank_gemm_count(ptr(Ehi), ptr(Elo), n_shard, shard_base, ptr(Qhi), ptr(Qlo), Q, d, nsplit,
-                                     ptr(tlo), ptr(thi), ptr(cnt_gt), ptr(cand_q), ptr(cand_e), cand_q.numel(),
-                                     ptr(cand_count), stream()))
+                                     ptr(tlo), ptr(thi), ptr(tlo_wide), ptr(thi_wide), ptr(cnt_gt), ptr(cand_q),
+                                     ptr(cand_e), cand_q.numel(), ptr(cand_count), stream()))

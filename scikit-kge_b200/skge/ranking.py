@@ -297,7 +297,7 @@ class FilteredRankingEval(object):
         return hit
 
     engine = 'auto'             # 'auto' | 'sweep' (fp32 CUDA cores) | 'umma' (tcgen05, DOT models, d <= 256)
-    nsplit = 3                  # fp16 hi/lo products accumulated by the tcgen05 engine (1 or 3)
+    nsplit = 3                  # fp16 hi/lo products on the tensor cores: 3, 2 (third product in the epilogue), 1
 
     def _coarse_engine(self, E, lo, hi, enorm):
         """The coarse-pass engine for this shard.  The object (and its candidate
@@ -417,7 +417,7 @@ class _UmmaEngine(_SweepEngine):
         self.nsplit = nsplit
         self.name = 'tcgen05-f16x%d' % nsplit
         self.dtype = 'f16x%d split (tcgen05, fp32 accumulate) + f64 settle' % nsplit
-        if nsplit != 3:
+        if nsplit == 1:
             self.cands_per_query = 4096
 
     def bind(self, E, lo, hi):
@@ -425,7 +425,14 @@ class _UmmaEngine(_SweepEngine):
         if hi > lo:
             emax = float(self.shard.abs().max().item())
             self.escale = 2.0 ** (12 - math.ceil(math.log2(emax))) if emax > 0 else 1.0
-            self.Ehi, self.Elo = kernels.pack_f16(self.shard, None, self.escale)
+            if self.nsplit == 2:
+                # refine mode gathers lo rows in the epilogue: it wants them row-major
+                # and the largest ||e_lo||_2 (scaled units) bounds the product they defer:
+                # |(q_hi + q_lo) . e_lo| <= ||q|| ||e_lo||  (1e-3 covers the fp32 atomics' rounding)
+                self.Ehi, _, self.Elo, n2 = kernels.pack_f16(self.shard, None, self.escale, lo_rowmajor=True)
+                self.elo_max = math.sqrt(float(n2.max().item())) * 1.001
+            else:
+                self.Ehi, self.Elo = kernels.pack_f16(self.shard, None, self.escale)
 
     def coarse_rel(self, d):
         # Error model, relative to sum|q_i e_i| <= |q||e|: split residual 3*2^-22, fp32 rounding
@@ -433,16 +440,22 @@ class _UmmaEngine(_SweepEngine):
         # (worst case, all one-sided): 6.2e-6 at d = 256.  2^-17 = 7.6e-6 covers it; the error
         # measured on the B200 (profiles/exp_gemm.py probe) is 1.1e-7 = 2^-23.1, 70x smaller.
         # nsplit = 1 keeps only hi*hi: fp16 rounding of both operands, 2^-10 worst case.
-        return 2.0 ** -17 if self.nsplit == 3 else 2.0 ** -9
+        # nsplit = 2 adds the third product in the epilogue (fp32 FMAs): same bound, fewer MMA steps.
+        return 2.0 ** -9 if self.nsplit == 1 else 2.0 ** -17
 
     def _coarse(self, op, q, cnt_gt):
         Q, d = q['q32'].shape
         qscale, tlo, thi = kernels.query_scale(q, self.escale)
         Qhi, Qlo = kernels.pack_f16(q['q32'], qscale, 1.0)
+        wlo = whi = None
+        if self.nsplit == 2:
+            # widen by ||q|| max||e_lo|| (scaled units); 1 % covers the fp32 roundings of the norms
+            w = q['qnorm'] * qscale * (self.elo_max * 1.01)
+            wlo, whi = (tlo - w).contiguous(), (thi + w).contiguous()
         work = 2.0 * (self.hi - self.lo) * d * Q
         self._timed(lambda: kernels.rank_gemm_count(self.Ehi, self.Elo, self.hi - self.lo, self.lo, Qhi, Qlo, Q, d,
                                                     self.nsplit, tlo, thi, cnt_gt, self.cand_q, self.cand_e,
-                                                    self.count), work)
+                                                    self.count, wlo, whi), work)
 
 
 class TransEEval(FilteredRankingEval):

@@ -127,6 +127,13 @@ def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te):
     got1 = ev.count_pass(m)
     assert torch.equal(got1, ref)
     assert ev.last_stats['candidates'] > c3 and ev.last_stats['engine'] == 'tcgen05-f16x1'
+    # two products on the tensor cores, the third added in the epilogue for the wide-band pairs:
+    # the refined scores are tested against the same tight band, so the fp64 workload stays small
+    ev.nsplit = 2
+    got2 = ev.count_pass(m)
+    assert torch.equal(got2, ref)
+    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert ev.last_stats['candidates'] < 4 * max(c3, 64)
 
 
 @pytest.mark.parametrize('kind', ['transe', 'hole'])
