@@ -43,6 +43,11 @@ WORKLOADS = {
 }
 
 
+# per-launch DRAM bytes (read + write) and tensor-pipe active % of the coarse kernel at the full
+# config-5 size on one GPU, from the committed ncu --set full captures
+NCU_GEMM = {'tcgen05-f16x3': (12.875e9 + 0.180e9, 69.2)}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -297,13 +302,18 @@ def run_b200(args):
         if tensor:
             achieved = work / (avg_ms * 1e-3) / 1e12
             peak = pk['tf_sust']
-            traffic = None
-            if args.workload == 'cfg5' and world == 1 and te == Te and str(stats.get('engine', '')).startswith('tcgen05'):
-                traffic = 12.875e9 + 0.180e9   # dram read + write of one launch: profiles/r01_rank_cfg5_tcgen05_v2.txt
+            traffic = pipe_pct = None
+            eng = str(stats.get('engine', ''))
+            if args.workload == 'cfg5' and world == 1 and te == Te:
+                # dram read + write of one launch and tensor-pipe activity from ncu --set full
+                # (profiles/r01_rank_cfg5_tcgen05_v2.txt, profiles/r01_rank_cfg5_tcgen05_refine.txt)
+                traffic, pipe_pct = NCU_GEMM.get(eng, (None, None))
+            nprod = {'tcgen05-f16x3': 3, 'tcgen05-f16x2': 2}.get(eng, 1)
             roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak, 'traffic': traffic, 'kernel': stats.get('engine'),
-                    'executed_tflops': achieved * (3 if 'x3' in str(stats.get('engine')) else 1),
-                    'tensor_pipe_active_pct_ncu': 69.2 if traffic else None,
+                    'frac': achieved / peak, 'traffic': traffic, 'kernel': eng,
+                    'mma_products_per_algorithmic_mac': nprod,
+                    'executed_tflops': achieved * nprod,
+                    'tensor_pipe_active_pct_ncu': pipe_pct,
                     'launch_ms': avg_ms, 'launches_timed': len(kt), 'peak_source': pk['src'] + ' bf16 sustained',
                     'algorithmic_flops_per_launch': work,
                     'kernel_share_of_step': sum(t for t, _ in kt) / max(ms, 1e-9)}

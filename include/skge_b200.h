@@ -274,7 +274,7 @@ SKGE_API int skge_rank_query_scale(const float *q32, const double *tscore, const
 /* nsplit: 1 = hi*hi only (fp16 accuracy), 3 = hi*hi + hi*lo + lo*hi on the tensor cores,
  * 2 = q_hi*e_hi + q_lo*e_hi on the tensor cores; the accumulator is then tested against
  * thr_*_wide (the tight thresholds widened by >= ||q|| max_e ||e_lo|| in scaled units), and
- * pairs inside the wide band get (q_hi + q_lo) . e_lo added in the epilogue before the tight
+ * pairs inside the wide band get q_hi . e_lo added in the epilogue before the tight
  * test; Elo must then be the row-major lo array of skge_rank_pack_f16.  thr_*_wide may be NULL
  * unless nsplit == 2. */
 SKGE_API int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,

@@ -15,7 +15,7 @@
 // thresholds already contain the (power-of-two) scales.
 //
 // nsplit = 2 ("refine" mode) issues only the two products that share the entity operand,
-// q_hi*e_hi + q_lo*e_hi.  What is missing, (q_hi + q_lo) . e_lo, is bounded by
+// q_hi*e_hi + q_lo*e_hi.  What is missing, q_hi . e_lo (+ the negligible q_lo . e_lo), is bounded by
 // ||q|| max_e ||e_lo|| ~ 2^-13 ||q|| ||e||, so the epilogue first tests against thresholds
 // widened by that bound; the ~0.2 % of pairs that fall into the wide band get the missing
 // term added by their epilogue warp (32 lanes x 8 k each: q from the resident shared-memory
@@ -245,23 +245,21 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int j) {
   return (j & 16) ? d1 : d0;
 }
 
-// sum over 8 k of (q_hi + q_lo) * e_lo for one 16-byte chunk of each operand.  The term is a
-// correction of relative size 2^-12, so packed fp16 arithmetic is enough: |q_hi| < 2^12 and
-// |e_lo| <= 1 in scaled units, four products per half2 lane stay below 2^14, and the fp16
-// roundings contribute < 2^-21 ||q|| ||e|| (covered by the 2^-17 band).
-__device__ __forceinline__ float chunk_dot(const uint4 &qh, const uint4 &ql, const uint4 &el) {
-  const __half2 *h = reinterpret_cast<const __half2 *>(&qh), *l = reinterpret_cast<const __half2 *>(&ql);
+// sum over 8 k of q_hi * e_lo for one 16-byte chunk of each operand.  The term is a correction
+// of relative size 2^-12, so packed fp16 arithmetic is enough (|q_hi| < 2^12 and |e_lo| <= 1 in
+// scaled units: four products per half2 lane stay below 2^14, and the fp16 roundings contribute
+// < 2^-21 ||q|| ||e||), and q_lo * e_lo (< 2^-23 ||q|| ||e||) is dropped like in the three-product
+// mode.  Both are covered by the 2^-17 band.  Reading q_hi only also halves the shared-memory
+// traffic of the refinement, which is what bounds it.
+__device__ __forceinline__ float chunk_dot(const uint4 &qh, const uint4 &el) {
+  const __half2 *h = reinterpret_cast<const __half2 *>(&qh);
   const __half2 *e = reinterpret_cast<const __half2 *>(&el);
   __half2 acc = __hmul2(h[0], e[0]);
   acc = __hfma2(h[1], e[1], acc);
   acc = __hfma2(h[2], e[2], acc);
   acc = __hfma2(h[3], e[3], acc);
-  __half2 acl = __hmul2(l[0], e[0]);
-  acl = __hfma2(l[1], e[1], acl);
-  acl = __hfma2(l[2], e[2], acl);
-  acl = __hfma2(l[3], e[3], acl);
-  const float2 a = __half22float2(acc), b = __half22float2(acl);
-  return (a.x + a.y) + (b.x + b.y);
+  const float2 a = __half22float2(acc);
+  return a.x + a.y;
 }
 
 template <bool REFINE>
@@ -476,7 +474,7 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
             }
           }
           __syncwarp();
-          // Add (q_hi + q_lo) . e_lo to the coarse score of every listed pair.  Eight pairs per
+          // Add q_hi . e_lo to the coarse score of every listed pair.  Eight pairs per
           // batch, four lanes per pair: lane 8 p + s takes the 16-byte k-chunks p, p + 4, ... of
           // pair s (chunk c = block c / 8, core matrix c % 8).  In the K-major core-matrix layout
           // all chunks of one query row live in the same four banks, and a 128-bit shared load is
@@ -508,8 +506,7 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
                 const int ch = part + 4 * t;
                 if (mine && ch < kch * 8) {
                   const uint32_t qoff = (ch >> 3) * BLOCK_BYTES + (ch & 7) * LBO_BYTES + qbase;
-                  acc += chunk_dot(*reinterpret_cast<const uint4 *>(sA_hi + qoff),
-                                   *reinterpret_cast<const uint4 *>(sA_lo + qoff), el[t]);
+                  acc += chunk_dot(*reinterpret_cast<const uint4 *>(sA_hi + qoff), el[t]);
                 }
               }
               acc += __shfl_xor_sync(kFull, acc, 8);

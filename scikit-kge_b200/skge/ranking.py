@@ -20,6 +20,7 @@ rank and for every world size.
 """
 import logging
 import gc
+import os
 import math
 
 import numpy as np
@@ -261,7 +262,7 @@ class FilteredRankingEval(object):
         enorm = float(torch.linalg.vector_norm(E, dim=1).max().item()) if op == _ext.RANK_DOT else 1.0
         # filter entries are settled by the rank that owns the entity
         pq, pe, pair_bounds = self._shard_pairs(st, lo, hi, world, Q)
-        engine = self._coarse_engine(E, lo, hi, enorm)
+        engine = self._coarse_engine(E, lo, hi, enorm, min(Q, self.chunk_queries))
         engine.reserve(min(Q, self.chunk_queries))
         ncand = 0
         for ci, q0 in enumerate(range(0, Q, self.chunk_queries)):
@@ -297,9 +298,12 @@ class FilteredRankingEval(object):
         return hit
 
     engine = 'auto'             # 'auto' | 'sweep' (fp32 CUDA cores) | 'umma' (tcgen05, DOT models, d <= 256)
-    nsplit = 3                  # fp16 hi/lo products on the tensor cores: 3, 2 (third product in the epilogue), 1
+    # fp16 hi/lo products on the tensor cores: 3, 2 (third product added in the epilogue), 1 (fp16 only);
+    # 0 = choose: 2 for large sweeps (the saved MMA work outweighs the heavier epilogue), else 3
+    nsplit = int(os.environ.get('SKGE_RANK_NSPLIT', '0'))
+    refine_min_pairs = 1 << 33  # queries x shard rows per coarse launch above which nsplit = 2 pays off
 
-    def _coarse_engine(self, E, lo, hi, enorm):
+    def _coarse_engine(self, E, lo, hi, enorm, nqueries=0):
         """The coarse-pass engine for this shard.  The object (and its candidate
         buffers) is cached across calls; the fp16 shadow of the shard is rebuilt on
         every call because the model may have been trained in between."""
@@ -309,11 +313,12 @@ class FilteredRankingEval(object):
             want = 'umma' if (dot and self.use_tensor_cores and E.shape[1] <= 256) else 'sweep'
         if want == 'umma' and (not dot or E.shape[1] > 256):
             raise ValueError('the tcgen05 engine needs a dot-product model with d <= 256')
-        key = (want, self.nsplit if want == 'umma' else 0)
+        nsplit = self.nsplit or (2 if nqueries * (hi - lo) >= self.refine_min_pairs else 3)
+        key = (want, nsplit if want == 'umma' else 0)
         cache = self.__dict__.setdefault('_engines', {})
         eng = cache.get(key)
         if eng is None:
-            eng = cache[key] = _UmmaEngine(self.nsplit) if want == 'umma' else _SweepEngine()
+            eng = cache[key] = _UmmaEngine(nsplit) if want == 'umma' else _SweepEngine()
         eng.bind(E, lo, hi)
         return eng
 
@@ -428,7 +433,7 @@ class _UmmaEngine(_SweepEngine):
             if self.nsplit == 2:
                 # refine mode gathers lo rows in the epilogue: it wants them row-major
                 # and the largest ||e_lo||_2 (scaled units) bounds the product they defer:
-                # |(q_hi + q_lo) . e_lo| <= ||q|| ||e_lo||  (1e-3 covers the fp32 atomics' rounding)
+                # |q . e_lo| <= ||q|| ||e_lo||  (1e-3 covers the fp32 atomics' rounding)
                 self.Ehi, _, self.Elo, n2 = kernels.pack_f16(self.shard, None, self.escale, lo_rowmajor=True)
                 self.elo_max = math.sqrt(float(n2.max().item())) * 1.001
             else:

@@ -120,6 +120,7 @@ def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te):
     ev.engine = 'sweep'
     ref = ev.count_pass(m)
     ev.engine = 'umma'
+    ev.nsplit = 3
     got = ev.count_pass(m)
     c3 = ev.last_stats['candidates']
     assert torch.equal(got, ref)
