@@ -302,6 +302,7 @@ class FilteredRankingEval(object):
     # 0 = choose: 2 for large sweeps (the saved MMA work outweighs the heavier epilogue), else 3
     nsplit = int(os.environ.get('SKGE_RANK_NSPLIT', '0'))
     refine_min_pairs = 1 << 33  # queries x shard rows per coarse launch above which nsplit = 2 pays off
+    refine_max_norm_spread = 2.0  # ... provided max row norm <= this x the median row norm of the shard
 
     def _coarse_engine(self, E, lo, hi, enorm, nqueries=0):
         """The coarse-pass engine for this shard.  The object (and its candidate
@@ -313,7 +314,16 @@ class FilteredRankingEval(object):
             want = 'umma' if (dot and self.use_tensor_cores and E.shape[1] <= 256) else 'sweep'
         if want == 'umma' and (not dot or E.shape[1] > 256):
             raise ValueError('the tcgen05 engine needs a dot-product model with d <= 256')
-        nsplit = self.nsplit or (2 if nqueries * (hi - lo) >= self.refine_min_pairs else 3)
+        nsplit = self.nsplit
+        if not nsplit:
+            nsplit = 3
+            if want == 'umma' and nqueries * (hi - lo) >= self.refine_min_pairs:
+                # Refine mode widens the band by ||q|| * max_e ||e_lo||, one number for the whole shard.
+                # If a few rows are much longer than the typical row, that band is far too wide for
+                # the short ones (many wide-band pairs, a slow epilogue): keep the three-product mode.
+                rn = torch.linalg.vector_norm(E[lo:hi], dim=1)
+                if float(rn.max().item()) <= self.refine_max_norm_spread * float(rn.median().item()):
+                    nsplit = 2
         key = (want, nsplit if want == 'umma' else 0)
         cache = self.__dict__.setdefault('_engines', {})
         eng = cache.get(key)
