@@ -272,15 +272,18 @@ SKGE_API int skge_rank_query_scale(const float *q32, const double *tscore, const
                           float escale, float *qscale, float *thr_lo, float *thr_hi,
                           skge_stream_t stream);
 /* nsplit: 1 = hi*hi only (fp16 accuracy), 3 = hi*hi + hi*lo + lo*hi on the tensor cores,
- * 2 = q_hi*e_hi + q_lo*e_hi on the tensor cores; the accumulator is then tested against
- * thr_*_wide (the tight thresholds widened by >= ||q|| max_e ||e_lo|| in scaled units), and
- * pairs inside the wide band get q_hi . e_lo added in the epilogue before the tight
- * test; Elo must then be the row-major lo array of skge_rank_pack_f16.  thr_*_wide may be NULL
- * unless nsplit == 2. */
+ * 2 = q_hi*e_hi + q_lo*e_hi on the tensor cores ("refine" mode): the accumulator of entity tile t
+ * (128 packed rows) is tested against the tight thresholds widened by qwidth[q] * tile_w[t], which
+ * must bound ||q|| * max ||e_lo|| over the tile in scaled units; pairs inside the wide band get
+ * q_hi . e_lo added in the epilogue before the tight test.  Elo must then be the row-major lo
+ * array of skge_rank_pack_f16.  perm (nullable) maps packed shard row -> shard-local entity id, so
+ * the caller may pack the shard in any order (e.g. by row norm, which makes tile_w tight);
+ * candidates always carry shard_base + entity id.  qwidth, tile_w, perm may be NULL unless
+ * nsplit == 2. */
 SKGE_API int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
                          const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
-                         const float *thr_lo, const float *thr_hi, const float *thr_lo_wide,
-                         const float *thr_hi_wide, int32_t *cnt_gt,
+                         const float *thr_lo, const float *thr_hi, const float *qwidth,
+                         const float *tile_w, const int32_t *perm, int32_t *cnt_gt,
                          int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                          unsigned long long *cand_count, skge_stream_t stream);
 

@@ -62,8 +62,12 @@ def main(worlds=(1, 2, 4, 8)):
         return fn
     names = ['make_queries', 'rank_rescore', 'rank_gemm_count', 'pack_f16', 'query_scale', 'rank_sweep']
     saved = {n: wrap(n) for n in names if hasattr(kernels, n)}
-    ev.count_pass(mdl, world=(0, 1))
+    bw = int(os.environ.get('SKGE_BREAKDOWN_WORLD', '1'))
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev.count_pass(mdl, world=(0, bw))
+    torch.cuda.synchronize()
+    print('breakdown pass (world %d): %.1f ms wall' % (bw, (time.perf_counter() - t0) * 1e3))
     for n, fn in saved.items():
         setattr(kernels, n, fn)
     print('one pass: ' + ', '.join('%s %.2f ms x%d' % (n, sum(a.elapsed_time(b) for a, b in v), len(v))

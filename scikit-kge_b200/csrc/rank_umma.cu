@@ -16,8 +16,9 @@
 //
 // nsplit = 2 ("refine" mode) issues only the two products that share the entity operand,
 // q_hi*e_hi + q_lo*e_hi.  What is missing, q_hi . e_lo (+ the negligible q_lo . e_lo), is bounded by
-// ||q|| max_e ||e_lo|| ~ 2^-13 ||q|| ||e||, so the epilogue first tests against thresholds
-// widened by that bound; the ~0.2 % of pairs that fall into the wide band get the missing
+// ||q|| max ||e_lo|| ~ 2^-13 ||q|| ||e|| (the maximum over the 128 rows of the entity tile; the
+// caller packs the shard ordered by row norm so that a tile's rows are alike), so the epilogue first
+// tests against thresholds widened by that bound; the ~0.3 % of pairs that fall into the wide band get the missing
 // term added by their epilogue warp (32 lanes x 8 k each: q from the resident shared-memory
 // tile, e_lo straight from the L2-resident slice) and are then tested against the tight
 // thresholds exactly like an nsplit = 3 accumulator.  A third of the tensor-core work and half
@@ -143,7 +144,10 @@ struct GemmArgs {
   int64_t n_shard, shard_base, Q;
   int kch, nsplit;
   const float *thr_lo, *thr_hi;
-  const float *thr_lo_wide, *thr_hi_wide;   // refine mode
+  // refine mode: the band is widened by qwidth[q] * tile_w[tile] >= ||q|| * max ||e_lo|| over the tile
+  // (scaled units); perm (nullable) maps a packed shard row to its shard-local entity id
+  const float *qwidth, *tile_w;
+  const int32_t *perm;
   int32_t *cnt_gt, *cand_q, *cand_e;
   int64_t cand_cap;
   unsigned long long *cand_count;
@@ -231,6 +235,9 @@ __device__ __forceinline__ void push_global(const GemmArgs &a, int q, int e) {
     a.cand_e[slot] = e;
   }
 }
+
+// shard-local entity id of packed row `r` (refine mode may pack the shard in another order)
+__device__ __forceinline__ int64_t entity_of(const GemmArgs &a, int64_t r) { return a.perm ? (int64_t)__ldg(a.perm + r) : r; }
 
 // r[j] for a run-time j without spilling the array: a 5-level multiplexer
 __device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int j) {
@@ -378,11 +385,11 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
       const Item it = get_item(a, item);
       const int64_t q = (int64_t)it.qt * TILE + row;
       float thi = INFINITY, tlo = INFINITY;       // tight thresholds: t +- eps
-      float whi = INFINITY, wlo = INFINITY;       // refine mode: widened by the missing-product bound
+      float qw = 0.f;                             // refine mode: ||q|| (scaled, rounded up)
       if (q < a.Q) {
         thi = a.thr_hi[q];
         tlo = a.thr_lo[q];
-        if (REFINE) { whi = a.thr_hi_wide[q]; wlo = a.thr_lo_wide[q]; }
+        if (REFINE) qw = a.qwidth[q];
       }
       int cnt = 0;
       for (int et = it.et_beg; et < it.et_end; ++et) {
@@ -430,6 +437,9 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
           const uint32_t my = tseq++;
           if ((int)(my & 3u) != cpart) continue;    // another quad's tile
           const uint32_t stage = my & 3u;
+          // this tile's wide band: the missing product is at most ||q|| * max ||e_lo|| over its rows
+          const float tw = __ldg(a.tile_w + et);
+          const float whi = __fmaf_ru(qw, tw, thi), wlo = __fmaf_rd(-qw, tw, tlo);
           mbar_wait(&ctrl->acc_full[stage], (my >> 2) & 1u);
           tc_fence_after();
           const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + stage * TILE;
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
                 wl->rc[w16][idx] = (lane << 8) | (c2 * 32 + j);
               } else {
                 // list full (rare): let the fp64 pass settle this pair
-                push_global(a, (int)q, (int)(a.shard_base + e0 + c2 * 32 + j));
+                push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + c2 * 32 + j)));
               }
             }
           }
@@ -520,7 +530,7 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
                 const int ru = __shfl_sync(kFull, rc, u);
                 if (((have >> u) & 1u) && lane == (ru >> 8)) {
                   if (su > thi) ++cnt;
-                  else if (su >= tlo) push_global(a, (int)q, (int)(a.shard_base + e0 + (ru & 255)));
+                  else if (su >= tlo) push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + (ru & 255))));
                 }
               }
             }
@@ -656,15 +666,15 @@ int skge_rank_query_scale(const float *q32, const double *tscore, const float *e
 
 int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
                          const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
-                         const float *thr_lo, const float *thr_hi, const float *thr_lo_wide,
-                         const float *thr_hi_wide, int32_t *cnt_gt,
+                         const float *thr_lo, const float *thr_hi, const float *qwidth,
+                         const float *tile_w, const int32_t *perm, int32_t *cnt_gt,
                          int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                          unsigned long long *cand_count, skge_stream_t stream) {
   SKGE_REQUIRE(Ehi && Elo && Qhi && Qlo && thr_lo && thr_hi && cnt_gt && cand_q && cand_e && cand_count,
                "null argument");
   SKGE_REQUIRE(d > 0 && d <= MAX_KCH * KCHUNK, "the tcgen05 ranking kernel supports d <= 256");
   SKGE_REQUIRE(nsplit >= 1 && nsplit <= 3, "nsplit must be 1, 2 or 3");
-  SKGE_REQUIRE(nsplit != 2 || (thr_lo_wide && thr_hi_wide), "nsplit = 2 needs the widened thresholds");
+  SKGE_REQUIRE(nsplit != 2 || (qwidth && tile_w), "nsplit = 2 needs qwidth and tile_w");
   SKGE_REQUIRE(n_shard >= 0 && Q >= 0, "bad sizes");
   if (Q == 0 || n_shard == 0) return 0;
   GemmArgs a;
@@ -679,8 +689,9 @@ int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int6
   a.nsplit = nsplit;
   a.thr_lo = thr_lo;
   a.thr_hi = thr_hi;
-  a.thr_lo_wide = thr_lo_wide;
-  a.thr_hi_wide = thr_hi_wide;
+  a.qwidth = qwidth;
+  a.tile_w = tile_w;
+  a.perm = perm;
   a.cnt_gt = cnt_gt;
   a.cand_q = cand_q;
   a.cand_e = cand_e;

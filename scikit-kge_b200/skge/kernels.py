@@ -260,8 +260,8 @@ def query_scale(q, escale):
 
 
 def rank_gemm_count(Ehi, Elo, n_shard, shard_base, Qhi, Qlo, Q, d, nsplit, tlo, thi, cnt_gt, cand_q, cand_e,
-                    cand_count, tlo_wide=None, thi_wide=None):
+                    cand_count, qwidth=None, tile_w=None, perm=None):
     _count('gemm')
     check(lib().skge_rank_gemm_count(ptr(Ehi), ptr(Elo), n_shard, shard_base, ptr(Qhi), ptr(Qlo), Q, d, nsplit,
-                                     ptr(tlo), ptr(thi), ptr(tlo_wide), ptr(thi_wide), ptr(cnt_gt), ptr(cand_q),
-                                     ptr(cand_e), cand_q.numel(), ptr(cand_count), stream()))
+                                     ptr(tlo), ptr(thi), ptr(qwidth), ptr(tile_w), ptr(perm), ptr(cnt_gt),
+                                     ptr(cand_q), ptr(cand_e), cand_q.numel(), ptr(cand_count), stream()))

@@ -302,7 +302,6 @@ class FilteredRankingEval(object):
     # 0 = choose: 2 for large sweeps (the saved MMA work outweighs the heavier epilogue), else 3
     nsplit = int(os.environ.get('SKGE_RANK_NSPLIT', '0'))
     refine_min_pairs = 1 << 33  # queries x shard rows per coarse launch above which nsplit = 2 pays off
-    refine_max_norm_spread = 2.0  # ... provided max row norm <= this x the median row norm of the shard
 
     def _coarse_engine(self, E, lo, hi, enorm, nqueries=0):
         """The coarse-pass engine for this shard.  The object (and its candidate
@@ -318,12 +317,7 @@ class FilteredRankingEval(object):
         if not nsplit:
             nsplit = 3
             if want == 'umma' and nqueries * (hi - lo) >= self.refine_min_pairs:
-                # Refine mode widens the band by ||q|| * max_e ||e_lo||, one number for the whole shard.
-                # If a few rows are much longer than the typical row, that band is far too wide for
-                # the short ones (many wide-band pairs, a slow epilogue): keep the three-product mode.
-                rn = torch.linalg.vector_norm(E[lo:hi], dim=1)
-                if float(rn.max().item()) <= self.refine_max_norm_spread * float(rn.median().item()):
-                    nsplit = 2
+                nsplit = 2
         key = (want, nsplit if want == 'umma' else 0)
         cache = self.__dict__.setdefault('_engines', {})
         eng = cache.get(key)
@@ -441,11 +435,21 @@ class _UmmaEngine(_SweepEngine):
             emax = float(self.shard.abs().max().item())
             self.escale = 2.0 ** (12 - math.ceil(math.log2(emax))) if emax > 0 else 1.0
             if self.nsplit == 2:
-                # refine mode gathers lo rows in the epilogue: it wants them row-major
-                # and the largest ||e_lo||_2 (scaled units) bounds the product they defer:
-                # |q . e_lo| <= ||q|| ||e_lo||  (1e-3 covers the fp32 atomics' rounding)
-                self.Ehi, _, self.Elo, n2 = kernels.pack_f16(self.shard, None, self.escale, lo_rowmajor=True)
-                self.elo_max = math.sqrt(float(n2.max().item())) * 1.001
+                # Refine mode: the epilogue gathers lo rows (row-major copy) and widens the band of
+                # entity tile t by ||q|| * max ||e_lo|| over the tile's 128 rows.  Counting does not
+                # care about the order of the entities, so the shard is packed by decreasing row norm:
+                # the rows of a tile are then alike and the per-tile bound is tight even when the
+                # table mixes long and short rows.
+                rn = torch.linalg.vector_norm(self.shard, dim=1)
+                self.perm = torch.argsort(rn, descending=True).to(torch.int32)
+                ordered = self.shard.index_select(0, self.perm.to(torch.int64))
+                self.Ehi, _, self.Elo, n2 = kernels.pack_f16(ordered, None, self.escale, lo_rowmajor=True)
+                del ordered
+                pad = (-n2.numel()) % 128
+                if pad:
+                    n2 = torch.cat([n2, n2.new_zeros(pad)])
+                # 1e-3: fp32 atomics' rounding in the squared norms
+                self.tile_w = (n2.view(-1, 128).max(dim=1).values.sqrt() * 1.001).contiguous()
             else:
                 self.Ehi, self.Elo = kernels.pack_f16(self.shard, None, self.escale)
 
@@ -462,15 +466,15 @@ class _UmmaEngine(_SweepEngine):
         Q, d = q['q32'].shape
         qscale, tlo, thi = kernels.query_scale(q, self.escale)
         Qhi, Qlo = kernels.pack_f16(q['q32'], qscale, 1.0)
-        wlo = whi = None
+        qwidth = tile_w = perm = None
         if self.nsplit == 2:
-            # widen by ||q|| max||e_lo|| (scaled units); 1 % covers the fp32 roundings of the norms
-            w = q['qnorm'] * qscale * (self.elo_max * 1.01)
-            wlo, whi = (tlo - w).contiguous(), (thi + w).contiguous()
+            # ||q|| in scaled units; 1 % covers the fp32 roundings of the norm and of q itself
+            qwidth = (q['qnorm'] * qscale * 1.01).contiguous()
+            tile_w, perm = self.tile_w, self.perm
         work = 2.0 * (self.hi - self.lo) * d * Q
         self._timed(lambda: kernels.rank_gemm_count(self.Ehi, self.Elo, self.hi - self.lo, self.lo, Qhi, Qlo, Q, d,
                                                     self.nsplit, tlo, thi, cnt_gt, self.cand_q, self.cand_e,
-                                                    self.count, wlo, whi), work)
+                                                    self.count, qwidth, tile_w, perm), work)
 
 
 class TransEEval(FilteredRankingEval):

@@ -137,6 +137,28 @@ def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te):
     assert ev.last_stats['candidates'] < 4 * max(c3, 64)
 
 
+@pytest.mark.parametrize('N,d', [(7777, 256), (3001, 96)])
+def test_refine_mode_with_mixed_row_norms(N, d):
+    """nsplit = 2 packs the shard by decreasing row norm and widens the band per 128-row tile.
+    Rows spanning a factor 50 in norm, a ragged last tile and emulated shards must still give the
+    fp32 engine's counts bit for bit, with candidates reported under their original ids."""
+    M = 11
+    rng, true, test = _graph(N, N, M, 3 * N, 400)
+    E0 = (rng.normal(size=(N, d)) / np.sqrt(d) * 10.0 ** rng.uniform(-1.7, 0.0, size=(N, 1))).astype(np.float32)
+    R0 = (rng.normal(size=(M, d)) / np.sqrt(d)).astype(np.float32)
+    m = _model('hole', E0, R0)
+    ev = _evaluator('hole')(test, true)
+    ev.engine = 'sweep'
+    ref = ev.count_pass(m)
+    ev.engine = 'umma'
+    ev.nsplit = 2
+    got = ev.count_pass(m)
+    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert torch.equal(got, ref)
+    parts = sum(ev.count_pass(m, world=(r, 3)) for r in range(3))
+    assert torch.equal(parts, ref)
+
+
 @pytest.mark.parametrize('kind', ['transe', 'hole'])
 @pytest.mark.parametrize('world', [2, 3, 8])
 def test_emulated_entity_shards_sum_to_the_single_gpu_counts(kind, world):
