@@ -122,37 +122,45 @@ def ranks_from_counts(cnt):
     return raw, raw - cnt[1]
 
 
-def regroup(test, raw, filt):
-    """Flat rank arrays (tail queries then head queries) -> the reference's
-    ``pos`` / ``fpos`` dicts ``{p: {'head': [...], 'tail': [...]}}`` with
-    relations and triples in insertion order (skge/base.py:743, 921, 1027-1028)."""
+def regroup_plan(test):
+    """The part of ``regroup`` that depends on the test triples only (computed once per
+    evaluator): the permutation that groups triples by relation, the group boundaries, and the
+    relations in order of first appearance."""
     t = np.asarray(test, dtype=np.int64).reshape(-1, 3)
     te = t.shape[0]
-    raw, filt = np.asarray(raw), np.asarray(filt)
-    pos, fpos = {}, {}
     if te == 0:
-        return pos, fpos
+        return None
     rel = t[:, 2]
     if rel.max() < 65536:
         rel = rel.astype(np.uint16)                     # numpy's stable sort is a radix sort for 16-bit keys
     order = np.argsort(rel, kind='stable')              # triples of one relation stay in test order
     ps = t[order, 2]
     bounds = np.concatenate([[0], np.nonzero(np.diff(ps))[0] + 1, [te]]).tolist()
+    first = order[bounds[:-1]]                          # first test position of each relation
+    groups = [(int(ps[bounds[g]]), bounds[g], bounds[g + 1]) for g in np.argsort(first, kind='stable').tolist()]
+    return te, np.concatenate([order, te + order]), groups
+
+
+def regroup(test, raw, filt, plan=None):
+    """Flat rank arrays (tail queries then head queries) -> the reference's
+    ``pos`` / ``fpos`` dicts ``{p: {'head': [...], 'tail': [...]}}`` with
+    relations and triples in insertion order (skge/base.py:743, 921, 1027-1028)."""
+    plan = plan or regroup_plan(test)
+    pos, fpos = {}, {}
+    if plan is None:
+        return pos, fpos
+    te, order2, groups = plan
     # permute once and convert to Python ints once; a relation's lists are then plain list slices
     # (per-relation numpy views + tolist() dominate the pass at 1k relations)
-    tails, heads = raw[order].tolist(), raw[te + order].tolist()
-    ftails, fheads = filt[order].tolist(), filt[te + order].tolist()
-    first = order[bounds[:-1]]                          # first test position of each relation
-    rels = ps[bounds[:-1]].tolist()
-    # Thousands of new containers would trigger generational collections that each walk the four
+    r, f = np.asarray(raw)[order2].tolist(), np.asarray(filt)[order2].tolist()
+    # Thousands of new containers would trigger generational collections that each walk the
     # big lists; nothing here can form a cycle, so the collector is paused for the loop.
     gc_was_on = gc.isenabled()
     gc.disable()
     try:
-        for g in np.argsort(first, kind='stable').tolist():  # relations in order of first appearance
-            a, b = bounds[g], bounds[g + 1]
-            pos[rels[g]] = {'head': heads[a:b], 'tail': tails[a:b]}
-            fpos[rels[g]] = {'head': fheads[a:b], 'tail': ftails[a:b]}
+        for p, a, b in groups:                              # relations in order of first appearance
+            pos[p] = {'head': r[te + a:te + b], 'tail': r[a:b]}
+            fpos[p] = {'head': f[te + a:te + b], 'tail': f[a:b]}
     finally:
         if gc_was_on:
             gc.enable()
@@ -242,7 +250,9 @@ class FilteredRankingEval(object):
             return {}, {}
         cnt = self.count_pass(mdl)
         raw, filt = ranks_from_counts(cnt)
-        return regroup(self.test, raw.cpu().numpy(), filt.cpu().numpy())
+        if getattr(self, '_regroup_plan', None) is None:
+            self._regroup_plan = regroup_plan(self.test)
+        return regroup(self.test, raw.cpu().numpy(), filt.cpu().numpy(), self._regroup_plan)
 
     def count_pass(self, mdl, E=None, world=None):
         """int32 [2, Q] counts, already summed over ranks.  ``world`` = (rank,
