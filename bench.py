@@ -45,7 +45,7 @@ WORKLOADS = {
 
 # per-launch DRAM bytes (read + write) and tensor-pipe active % of the coarse kernel at the full
 # config-5 size on one GPU, from the committed ncu --set full captures
-NCU_GEMM = {'tcgen05-f16x3': (12.875e9 + 0.180e9, 69.2), 'tcgen05-f16x2': (15.822e9 + 0.178e9, 49.0)}
+NCU_GEMM = {'tcgen05-f16x3': (12.875e9 + 0.180e9, 69.2), 'tcgen05-f16x2': (13.641e9 + 0.178e9, 53.5)}
 
 
 def parse():
