@@ -39,6 +39,22 @@ def main(worlds=(1, 2, 4, 8)):
     del true, g
     st = ev._device_state()
     Q = 2 * Te
+    if os.environ.get('SKGE_VERIFY'):
+        # full-size check: the three engines settle their bands in fp64, so their counts must be equal
+        ref = None
+        for eng, ns in (('umma', 3), ('umma', 2), ('sweep', 0)):
+            ev.engine, ev.nsplit = eng, ns
+            t0 = time.perf_counter()
+            c = ev.count_pass(mdl, world=(0, 1))
+            torch.cuda.synchronize()
+            print('%s nsplit %d: %.0f ms, candidates %d, sum of counts %d / %d' % (
+                ev.last_stats['engine'], ns, (time.perf_counter() - t0) * 1e3, ev.last_stats['candidates'],
+                int(c[0].sum().item()), int(c[1].sum().item())), flush=True)
+            assert ref is None or torch.equal(c, ref), 'engines disagree'
+            ref = c if ref is None else ref
+        print('verified: tcgen05 x3, tcgen05 x2 (refine) and the fp32 sweep give identical counts on all %d queries' % Q)
+        ev.engine = 'auto'
+        ev.nsplit = int(os.environ.get('SKGE_NSPLIT', 0))
     t1 = None
     for w in worlds:
         ms = ev_ms(lambda: ev.count_pass(mdl, world=(0, w)))
