@@ -207,7 +207,7 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
 
     import skge
-    from skge import kernels, ranking, _ext
+    from skge import kernels, ranking
     from skge.synth import make_graph, init_embeddings, SHAPES
     shape, model, d, desc = WORKLOADS[args.workload]
     N, M, T, V, Te = SHAPES[shape]

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'scikit-kge_b200')]
 import torch
 import skge
-from skge import kernels, ranking, _ext
+from skge import kernels, ranking
 from skge.synth import make_graph, init_embeddings, SHAPES
 
 

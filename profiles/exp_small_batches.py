@@ -4,7 +4,7 @@ Host time per fused batch (no sync) vs device time per batch."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'scikit-kge_b200')]
-import numpy as np, torch
+import torch
 import skge
 from skge.param import AdaGrad
 from skge.sample import RandomModeSampler

@@ -21,7 +21,6 @@ features of the fork outside the hot path and are rejected with a clear error.
 import argparse
 import logging
 import os
-import pickle
 import timeit
 
 import numpy as np

@@ -1,5 +1,4 @@
 """HolE on the device (reference: skge/hole.py)."""
-import numpy as np
 import torch
 
 from . import _ext, kernels

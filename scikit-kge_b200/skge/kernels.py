@@ -2,7 +2,6 @@
 
 Everything here takes and returns CUDA tensors; nothing computes on the host.
 """
-import numpy as np
 import torch
 
 from . import _ext

@@ -1,5 +1,4 @@
 """RESCAL on the device (reference: skge/rescal.py)."""
-import numpy as np
 
 from . import _ext, kernels
 from . import actfun as af

@@ -1,7 +1,6 @@
 """TransE on the device (reference: skge/transe.py)."""
 import logging
 
-import numpy as np
 
 from . import _ext, kernels
 from .base import Model
