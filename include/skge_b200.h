@@ -266,6 +266,10 @@ SKGE_API size_t skge_rank_packed_bytes(int64_t rows, int d); /* bytes of ONE (hi
 SKGE_API int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_scale,
                        float scalar_scale, void *hi, void *lo, void *lo_rowmajor, float *lo_norm2,
                        skge_stream_t stream);
+/* Row-major fp16 lo rows (lo_rowmajor of skge_rank_pack_f16, rows padded to 128, row length
+ * 64 * ceil(d / 64)) -> 8-bit rows: scale[row] = max|lo| / 127, byte = rn(lo / scale) + 128. */
+SKGE_API int skge_rank_quant_lo(const void *lo_rowmajor, int64_t rows, int d, void *lo8, float *scale,
+                       skge_stream_t stream);
 /* Per-query power-of-two scale (max|q| * qscale in [2^11, 2^12)) and the scaled
  * thresholds thr = (tscore -+ eps) * qscale * escale, rounded outwards. */
 SKGE_API int skge_rank_query_scale(const float *q32, const double *tscore, const float *eps, int64_t Q, int d,
@@ -278,12 +282,16 @@ SKGE_API int skge_rank_query_scale(const float *q32, const double *tscore, const
  * q_hi . e_lo added in the epilogue before the tight test.  Elo must then be the row-major lo
  * array of skge_rank_pack_f16.  perm (nullable) maps packed shard row -> shard-local entity id, so
  * the caller may pack the shard in any order (e.g. by row norm, which makes tile_w tight);
- * candidates always carry shard_base + entity id.  qwidth, tile_w, perm may be NULL unless
+ * candidates always carry shard_base + entity id.  With lo_scale != NULL, Elo is instead the 8-bit
+ * row-major array of skge_rank_quant_lo (half the gather traffic) and q1w[q] >= 0.5 ||q_hi||_1 in
+ * scaled units: the quantisation error of a pair is at most q1w[q] * lo_scale[row], and that
+ * pair's tight band is widened by it.  qwidth, tile_w, perm, lo_scale, q1w may be NULL unless
  * nsplit == 2. */
 SKGE_API int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
                          const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
                          const float *thr_lo, const float *thr_hi, const float *qwidth,
-                         const float *tile_w, const int32_t *perm, int32_t *cnt_gt,
+                         const float *tile_w, const int32_t *perm, const float *lo_scale, const float *q1w,
+                         int32_t *cnt_gt,
                          int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                          unsigned long long *cand_count, skge_stream_t stream);
 

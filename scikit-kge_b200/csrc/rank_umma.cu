@@ -148,6 +148,10 @@ struct GemmArgs {
   // (scaled units); perm (nullable) maps a packed shard row to its shard-local entity id
   const float *qwidth, *tile_w;
   const int32_t *perm;
+  // refine mode with 8-bit lo rows (lo_scale != NULL): Elo points to uint8 rows [rows][kch * 64],
+  // byte = round(e_lo / lo_scale[row]) + 128; q1w[q] >= 0.5 ||q_hi||_1 bounds the quantisation error
+  // of one pair by q1w[q] * lo_scale[row], which widens that pair's band
+  const float *lo_scale, *q1w;
   int32_t *cnt_gt, *cand_q, *cand_e;
   int64_t cand_cap;
   unsigned long long *cand_count;
@@ -269,6 +273,27 @@ __device__ __forceinline__ float chunk_dot(const uint4 &qh, const uint4 &el) {
   return a.x + a.y;
 }
 
+// 16 k of q_hi (two 16-byte chunks) times 16 quantised e_lo bytes.  A byte b becomes the half
+// 8 + b / 128 by dropping it into the mantissa of 0x4800 (= 8.0, ulp 2^-7); minus 9 gives
+// (b - 128) / 128 exactly.  Four products per half2 accumulator lane (|q_hi| < 2^12, |x| <= 1).
+__device__ __forceinline__ float dot16_q8(const uint4 &q0, const uint4 &q1, const uint4 &w) {
+  const __half2 nine = __floats2half2_rn(9.f, 9.f);
+  const __half2 *h0 = reinterpret_cast<const __half2 *>(&q0), *h1 = reinterpret_cast<const __half2 *>(&q1);
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  __half2 A = __floats2half2_rn(0.f, 0.f), B = A;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    uint32_t lo2 = __byte_perm(ww[m], 0x48484848u, 0x5140), hi2 = __byte_perm(ww[m], 0x48484848u, 0x5342);
+    const __half2 x01 = __hsub2(*reinterpret_cast<__half2 *>(&lo2), nine);
+    const __half2 x23 = __hsub2(*reinterpret_cast<__half2 *>(&hi2), nine);
+    const __half2 *qq = m < 2 ? h0 : h1;
+    A = __hfma2(x01, qq[2 * (m & 1)], A);
+    B = __hfma2(x23, qq[2 * (m & 1) + 1], B);
+  }
+  const float2 fa = __half22float2(A), fb = __half22float2(B);
+  return (fa.x + fa.y) + (fb.x + fb.y);
+}
+
 template <bool REFINE>
 __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -386,10 +411,14 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
       const int64_t q = (int64_t)it.qt * TILE + row;
       float thi = INFINITY, tlo = INFINITY;       // tight thresholds: t +- eps
       float qw = 0.f;                             // refine mode: ||q|| (scaled, rounded up)
+      float q1 = 0.f;                             // refine mode, 8-bit lo rows: 0.5 ||q_hi||_1 (rounded up)
       if (q < a.Q) {
         thi = a.thr_hi[q];
         tlo = a.thr_lo[q];
-        if (REFINE) qw = a.qwidth[q];
+        if (REFINE) {
+          qw = a.qwidth[q];
+          if (a.q1w) q1 = a.q1w[q];
+        }
       }
       int cnt = 0;
       for (int et = it.et_beg; et < it.et_end; ++et) {
@@ -502,21 +531,45 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
               const int rc = mine ? wl->rc[w16][b + slot] : 0;
               const int qr = quarter * 32 + (rc >> 8), col = rc & 255;
               const uint32_t qbase = (qr >> 3) * SBO_BYTES + (qr & 7) * 16;
-              const __half *ebase = a.Elo + (e0 + col) * (int64_t)(kch * KCHUNK);   // row-major lo rows
-              uint4 el[8];
+              float acc = 0.f, tol = 0.f;
+              if (a.lo_scale) {
+                // 8-bit lo rows: 256 B per pair instead of 512 B (the gathers bound this kernel)
+                const uint8_t *ebase = reinterpret_cast<const uint8_t *>(a.Elo) + (e0 + col) * (int64_t)(kch * KCHUNK);
+                const float sj = mine ? __ldg(a.lo_scale + e0 + col) : 0.f;
+                uint4 w[4];
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const int ch = part + 4 * t;          // k-chunk 0 .. 31
-                if (mine && ch < kch * 8)
-                  el[t] = __ldg(reinterpret_cast<const uint4 *>(ebase + ch * 8));
-              }
-              float acc = 0.f;
+                for (int t = 0; t < 4; ++t) {
+                  const int cb = part + 4 * t;        // 16-byte chunk = 16 k
+                  if (mine && cb < kch * 4) w[t] = __ldg(reinterpret_cast<const uint4 *>(ebase + cb * 16));
+                }
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const int ch = part + 4 * t;
-                if (mine && ch < kch * 8) {
-                  const uint32_t qoff = (ch >> 3) * BLOCK_BYTES + (ch & 7) * LBO_BYTES + qbase;
-                  acc += chunk_dot(*reinterpret_cast<const uint4 *>(sA_hi + qoff), el[t]);
+                for (int t = 0; t < 4; ++t) {
+                  const int cb = part + 4 * t;
+                  if (mine && cb < kch * 4) {
+                    const int ch = 2 * cb;            // q chunks ch, ch + 1 (8 k each, same 64-k block)
+                    const uint32_t qoff = (ch >> 3) * BLOCK_BYTES + (ch & 7) * LBO_BYTES + qbase;
+                    acc += dot16_q8(*reinterpret_cast<const uint4 *>(sA_hi + qoff),
+                                    *reinterpret_cast<const uint4 *>(sA_hi + qoff + LBO_BYTES), w[t]);
+                  }
+                }
+                acc *= 128.f * sj;
+                tol = sj;   // times q1w of the owning lane, below
+              } else {
+                const __half *ebase = a.Elo + (e0 + col) * (int64_t)(kch * KCHUNK);   // row-major fp16 lo rows
+                uint4 el[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  const int ch = part + 4 * t;          // k-chunk 0 .. 31
+                  if (mine && ch < kch * 8)
+                    el[t] = __ldg(reinterpret_cast<const uint4 *>(ebase + ch * 8));
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  const int ch = part + 4 * t;
+                  if (mine && ch < kch * 8) {
+                    const uint32_t qoff = (ch >> 3) * BLOCK_BYTES + (ch & 7) * LBO_BYTES + qbase;
+                    acc += chunk_dot(*reinterpret_cast<const uint4 *>(sA_hi + qoff), el[t]);
+                  }
                 }
               }
               acc += __shfl_xor_sync(kFull, acc, 8);
@@ -528,9 +581,10 @@ __global__ void __launch_bounds__(REFINE ? 640 : 384, 1) rank_gemm_kernel(GemmAr
               for (int u = 0; u < 8; ++u) {
                 const float su = __shfl_sync(kFull, s2, u);
                 const int ru = __shfl_sync(kFull, rc, u);
+                const float tu = __shfl_sync(kFull, tol, u) * q1;   // this pair's quantisation bound
                 if (((have >> u) & 1u) && lane == (ru >> 8)) {
-                  if (su > thi) ++cnt;
-                  else if (su >= tlo) push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + (ru & 255))));
+                  if (su > __fadd_ru(thi, tu)) ++cnt;
+                  else if (su >= __fadd_rd(tlo, -tu)) push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + (ru & 255))));
                 }
               }
             }
@@ -597,6 +651,29 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const float *__restrict__
   }
 }
 
+// Row-major fp16 lo rows -> 8-bit rows with one scale per row (refine mode's gather operand):
+// scale = max|l| / 127, byte = rn(l / scale) + 128.  One warp per row.
+__global__ void __launch_bounds__(256) quant_lo_kernel(const __half *__restrict__ lo_rm, int64_t rows, int kbytes,
+                                                       uint8_t *__restrict__ lo8, float *__restrict__ scale) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const __half *src = lo_rm + r * kbytes;
+    float m = 0.f;
+    for (int k = lane; k < kbytes; k += 32) m = fmaxf(m, fabsf(__half2float(src[k])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    const float sc = m / 127.f, inv = m > 0.f ? 127.f / m : 0.f;
+    for (int k = lane; k < kbytes; k += 32) {
+      int i = __float2int_rn(__half2float(src[k]) * inv);
+      i = max(-127, min(127, i));
+      lo8[r * kbytes + k] = (uint8_t)(i + 128);
+    }
+    if (lane == 0) scale[r] = sc;
+  }
+}
+
 // Per-query power-of-two scale and the scaled thresholds.
 //   qscale = 2^(12 - ceil(log2 max|q|));  thr = (tscore -+ eps) * qscale * escale (rounded outwards)
 __global__ void __launch_bounds__(256) query_scale_kernel(const float *__restrict__ q32,
@@ -652,6 +729,19 @@ int skge_rank_pack_f16(const float *X, int64_t rows, int d, const float *row_sca
   return 0;
 }
 
+int skge_rank_quant_lo(const void *lo_rowmajor, int64_t rows, int d, void *lo8, float *scale,
+                       skge_stream_t stream) {
+  SKGE_REQUIRE(lo_rowmajor && lo8 && scale && rows > 0 && d > 0, "bad arguments");
+  int kbytes = (d + KCHUNK - 1) / KCHUNK * KCHUNK;
+  int64_t rp = round_up(rows, TILE);
+  int64_t blocks = (rp + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  quant_lo_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(static_cast<const __half *>(lo_rowmajor), rp, kbytes,
+                                                             static_cast<uint8_t *>(lo8), scale);
+  SKGE_LAUNCH_CHECK();
+  return 0;
+}
+
 int skge_rank_query_scale(const float *q32, const double *tscore, const float *eps, int64_t Q, int d,
                           float escale, float *qscale, float *thr_lo, float *thr_hi, skge_stream_t stream) {
   SKGE_REQUIRE(q32 && tscore && eps && qscale && thr_lo && thr_hi && Q >= 0 && d > 0, "bad arguments");
@@ -667,7 +757,8 @@ int skge_rank_query_scale(const float *q32, const double *tscore, const float *e
 int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int64_t shard_base,
                          const void *Qhi, const void *Qlo, int64_t Q, int d, int nsplit,
                          const float *thr_lo, const float *thr_hi, const float *qwidth,
-                         const float *tile_w, const int32_t *perm, int32_t *cnt_gt,
+                         const float *tile_w, const int32_t *perm, const float *lo_scale, const float *q1w,
+                         int32_t *cnt_gt,
                          int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                          unsigned long long *cand_count, skge_stream_t stream) {
   SKGE_REQUIRE(Ehi && Elo && Qhi && Qlo && thr_lo && thr_hi && cnt_gt && cand_q && cand_e && cand_count,
@@ -675,6 +766,7 @@ int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int6
   SKGE_REQUIRE(d > 0 && d <= MAX_KCH * KCHUNK, "the tcgen05 ranking kernel supports d <= 256");
   SKGE_REQUIRE(nsplit >= 1 && nsplit <= 3, "nsplit must be 1, 2 or 3");
   SKGE_REQUIRE(nsplit != 2 || (qwidth && tile_w), "nsplit = 2 needs qwidth and tile_w");
+  SKGE_REQUIRE((lo_scale == nullptr) == (q1w == nullptr), "lo_scale and q1w go together");
   SKGE_REQUIRE(n_shard >= 0 && Q >= 0, "bad sizes");
   if (Q == 0 || n_shard == 0) return 0;
   GemmArgs a;
@@ -692,6 +784,8 @@ int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_shard, int6
   a.qwidth = qwidth;
   a.tile_w = tile_w;
   a.perm = perm;
+  a.lo_scale = lo_scale;
+  a.q1w = q1w;
   a.cnt_gt = cnt_gt;
   a.cand_q = cand_q;
   a.cand_e = cand_e;

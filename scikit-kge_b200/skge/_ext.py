@@ -58,7 +58,8 @@ SIGNATURES = {
     'skge_rank_packed_bytes': (_Z, [_L, _I]),
     'skge_rank_pack_f16': (_I, [_P, _L, _I, _P, _F, _P, _P, _P, _P, _P]),
     'skge_rank_query_scale': (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
-    'skge_rank_gemm_count': (_I, [_P, _P, _L, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P]),
+    'skge_rank_gemm_count': (_I, [_P, _P, _L, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P]),
+    'skge_rank_quant_lo': (_I, [_P, _L, _I, _P, _P, _P]),
 }
 
 _lib = None

@@ -259,8 +259,20 @@ def query_scale(q, escale):
 
 
 def rank_gemm_count(Ehi, Elo, n_shard, shard_base, Qhi, Qlo, Q, d, nsplit, tlo, thi, cnt_gt, cand_q, cand_e,
-                    cand_count, qwidth=None, tile_w=None, perm=None):
+                    cand_count, qwidth=None, tile_w=None, perm=None, lo_scale=None, q1w=None):
     _count('gemm')
     check(lib().skge_rank_gemm_count(ptr(Ehi), ptr(Elo), n_shard, shard_base, ptr(Qhi), ptr(Qlo), Q, d, nsplit,
-                                     ptr(tlo), ptr(thi), ptr(qwidth), ptr(tile_w), ptr(perm), ptr(cnt_gt),
-                                     ptr(cand_q), ptr(cand_e), cand_q.numel(), ptr(cand_count), stream()))
+                                     ptr(tlo), ptr(thi), ptr(qwidth), ptr(tile_w), ptr(perm), ptr(lo_scale),
+                                     ptr(q1w), ptr(cnt_gt), ptr(cand_q), ptr(cand_e), cand_q.numel(),
+                                     ptr(cand_count), stream()))
+
+
+def quant_lo(lo_rm, rows, d):
+    """Row-major fp16 lo rows -> (uint8 rows, fp32 scale per padded row)."""
+    rp = (rows + 127) // 128 * 128
+    kb = (d + 63) // 64 * 64
+    lo8 = torch.empty(rp * kb, dtype=torch.uint8, device=_ext.device())
+    scale = torch.empty(rp, dtype=torch.float32, device=_ext.device())
+    _count('pack')
+    check(lib().skge_rank_quant_lo(ptr(lo_rm), rows, d, ptr(lo8), ptr(scale), stream()))
+    return lo8, scale

@@ -430,6 +430,7 @@ class _UmmaEngine(_SweepEngine):
     shadow of the entity shard is rebuilt once per ranking pass."""
     name = 'tcgen05-f16x3'
     cands_per_query = 160
+    lo8 = os.environ.get('SKGE_RANK_LO8', '1') != '0'   # refine mode: gather 8-bit lo rows
 
     def __init__(self, nsplit=3):
         super(_UmmaEngine, self).__init__()
@@ -454,6 +455,11 @@ class _UmmaEngine(_SweepEngine):
                 self.perm = torch.argsort(rn, descending=True).to(torch.int32)
                 ordered = self.shard.index_select(0, self.perm.to(torch.int64))
                 self.Ehi, _, self.Elo, n2 = kernels.pack_f16(ordered, None, self.escale, lo_rowmajor=True)
+                self.lo_scale = None
+                if self.lo8:
+                    # 8-bit lo rows with one scale per row halve the bytes the epilogue gathers; the
+                    # quantisation error of a pair is bounded per pair (||q_hi||_1 * scale / 2)
+                    self.Elo, self.lo_scale = kernels.quant_lo(self.Elo, ordered.shape[0], ordered.shape[1])
                 del ordered
                 pad = (-n2.numel()) % 128
                 if pad:
@@ -476,15 +482,18 @@ class _UmmaEngine(_SweepEngine):
         Q, d = q['q32'].shape
         qscale, tlo, thi = kernels.query_scale(q, self.escale)
         Qhi, Qlo = kernels.pack_f16(q['q32'], qscale, 1.0)
-        qwidth = tile_w = perm = None
+        qwidth = tile_w = perm = lo_scale = q1w = None
         if self.nsplit == 2:
             # ||q|| in scaled units; 1 % covers the fp32 roundings of the norm and of q itself
             qwidth = (q['qnorm'] * qscale * 1.01).contiguous()
-            tile_w, perm = self.tile_w, self.perm
+            tile_w, perm, lo_scale = self.tile_w, self.perm, self.lo_scale
+            if lo_scale is not None:
+                # |sum q_hi (e_lo - scale * i8)| <= ||q_hi||_1 * scale / 2  (0.51: roundings)
+                q1w = (q['q32'].abs().sum(dim=1) * qscale * 0.51).contiguous()
         work = 2.0 * (self.hi - self.lo) * d * Q
         self._timed(lambda: kernels.rank_gemm_count(self.Ehi, self.Elo, self.hi - self.lo, self.lo, Qhi, Qlo, Q, d,
                                                     self.nsplit, tlo, thi, cnt_gt, self.cand_q, self.cand_e,
-                                                    self.count, qwidth, tile_w, perm), work)
+                                                    self.count, qwidth, tile_w, perm, lo_scale, q1w), work)
 
 
 class TransEEval(FilteredRankingEval):
