@@ -314,6 +314,8 @@ def run_b200(args):
                     'mma_products_per_algorithmic_mac': nprod,
                     'executed_tflops': achieved * nprod,
                     'tensor_pipe_active_pct_ncu': pipe_pct,
+                    'ncu_note': ('captured one commit earlier (fp16 e_lo rows in the refinement; the 8-bit rows '
+                                 'gather half of those bytes)') if nprod == 2 and traffic else None,
                     'launch_ms': avg_ms, 'launches_timed': len(kt), 'peak_source': pk['src'] + ' bf16 sustained',
                     'algorithmic_flops_per_launch': work,
                     'kernel_share_of_step': sum(t for t, _ in kt) / max(ms, 1e-9)}
