@@ -142,6 +142,33 @@ def test_sharded_counts_recombine_to_reference_ranks(kind_name, world):
     assert list(pos.keys()) == list(rpos.keys())
 
 
+def test_regroup_plan_is_reusable_and_handles_edge_cases():
+    """The evaluator computes the grouping of the test triples once (regroup_plan) and reuses it
+    for every pass: same dicts as the one-shot call, relations in order of first appearance,
+    triples of a relation in test order; relation ids >= 65536 and an empty test set work."""
+    from skge.ranking import regroup, regroup_plan
+    rng = np.random.default_rng(0)
+    for M in (7, 70000):
+        n = 500
+        test = np.stack([rng.integers(100, size=n), rng.integers(100, size=n), rng.integers(M, size=n)], 1)
+        plan = regroup_plan(test)
+        for _ in range(2):
+            raw = rng.integers(1, 100, size=2 * n).astype(np.int32)
+            filt = rng.integers(1, 100, size=2 * n).astype(np.int32)
+            pos, fpos = regroup(test, raw, filt, plan)
+            want, fwant = {}, {}
+            for i, (s, o, p) in enumerate(test.tolist()):
+                for dst, arr in ((want, raw), (fwant, filt)):
+                    d = dst.setdefault(p, {'head': [], 'tail': []})
+                    d['tail'].append(int(arr[i]))
+                    d['head'].append(int(arr[n + i]))
+            assert pos == want and fpos == fwant
+            assert list(pos.keys()) == list(want.keys())
+            assert regroup(test, raw, filt) == (pos, fpos)
+    assert regroup_plan(np.zeros((0, 3), dtype=np.int64)) is None
+    assert regroup(np.zeros((0, 3), dtype=np.int64), np.zeros(0), np.zeros(0)) == ({}, {})
+
+
 _GLOO_WORKER = r'''
 import os, sys
 sys.path[:0] = [%(root)r, os.path.join(%(root)r, 'scikit-kge_b200'), os.path.join(%(root)r, 'tests')]
