@@ -295,6 +295,33 @@ SKGE_API int skge_rank_gemm_count(const void *Ehi, const void *Elo, int64_t n_sh
                          int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                          unsigned long long *cand_count, skge_stream_t stream);
 
+/* ---- refine kernel, second generation (csrc/rank_refine.cu) ------------------------------------
+ * Same contract as skge_rank_gemm_count with nsplit == 2 (two fp16 products on the tensor cores, the
+ * third one added in the epilogue for the pairs inside the wide band), rebuilt around UMMA N = 256:
+ * the refinement reads 8-bit copies of BOTH operands (exact integer dot products) instead of fp16
+ * query rows, and cta_group = 2 pairs two CTAs on one 256-query x 256-entity MMA so that each SM
+ * stages half of every entity tile.  Replaces the ranking loop of skge/base.py:950-1017 for
+ * skge/run_hole.py:15-19 scores on large sweeps.
+ *
+ * skge_rank_quant_lo_s8: row-major fp16 lo rows (lo_rowmajor of skge_rank_pack_f16) -> int8 rows
+ *   e8 = rn(lo / scale), scale = max|lo| / 127, and meta[row] = (scale, ||lo||_1 rounded up) as float2.
+ * skge_rank_pack_q8: int8 copy of the queries' fp16 hi parts (h = half(q32 * qscale), q8 = rn(h / sq),
+ *   sq = max|h| / 127) in tiles of 128 rows x 64 * ceil(d / 64) bytes whose 16-byte chunks are
+ *   XOR-swizzled with the row (bank-conflict-free gathers), and qmeta[q][8] = thr_lo, thr_hi,
+ *   1.01 * qnorm * qscale, sq, qA, qB, 0, 0: the int8 arithmetic of pair (q, e) is off by at most
+ *   qA[q] * meta[e].y + qB[q] * meta[e].x, which widens that pair's tight band.
+ * skge_rank_refine_count: Ehi must hold an EVEN number of 128-row tiles (zero padded), tile_w one
+ *   entry per 128-row tile (>= max ||e_lo||_2 over the tile, scaled units). */
+SKGE_API int skge_rank_quant_lo_s8(const void *lo_rowmajor, int64_t rows, int d, void *lo8, void *meta,
+                          skge_stream_t stream);
+SKGE_API int skge_rank_pack_q8(const float *q32, const float *qscale, const float *qnorm, const float *thr_lo,
+                      const float *thr_hi, int64_t Q, int d, void *Q8, float *qmeta, skge_stream_t stream);
+SKGE_API int skge_rank_refine_count(const void *Ehi, const void *Elo8, const void *lo_meta, const float *tile_w,
+                           const int32_t *perm, int64_t n_shard, int64_t shard_base, const void *Qhi,
+                           const void *Qlo, const void *Q8, const float *qmeta, int64_t Q, int d, int cta_group,
+                           int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
+                           unsigned long long *cand_count, skge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

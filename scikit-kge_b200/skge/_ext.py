@@ -60,6 +60,9 @@ SIGNATURES = {
     'skge_rank_query_scale': (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
     'skge_rank_gemm_count': (_I, [_P, _P, _L, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P]),
     'skge_rank_quant_lo': (_I, [_P, _L, _I, _P, _P, _P]),
+    'skge_rank_quant_lo_s8': (_I, [_P, _L, _I, _P, _P, _P]),
+    'skge_rank_pack_q8': (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
+    'skge_rank_refine_count': (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _L, _P, _P]),
 }
 
 _lib = None

@@ -234,12 +234,16 @@ def rank_scores_one(op, E, q64_row):
     return out
 
 
-def pack_f16(X, row_scale, scalar_scale, lo_rowmajor=False):
+def pack_f16(X, row_scale, scalar_scale, lo_rowmajor=False, even_tiles=False):
     """fp32 [rows, d] -> (hi, lo) fp16 UMMA blocks (uint8 tensors); with ``lo_rowmajor`` also the
-    row-major copy of the lo parts (the refine-mode gather operand) and each row's squared lo norm."""
+    row-major copy of the lo parts (the refine-mode gather operand) and each row's squared lo norm.
+    ``even_tiles`` pads ``hi`` with a zero tile to an even number of 128-row tiles (UMMA N = 256)."""
     rows, d = X.shape
     nbytes = lib().skge_rank_packed_bytes(rows, d)
-    hi = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
+    if even_tiles and ((rows + 127) // 128) % 2:
+        hi = torch.zeros(lib().skge_rank_packed_bytes(rows + 128, d), dtype=torch.uint8, device=_ext.device())
+    else:
+        hi = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
     lo = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device())
     lo_rm = torch.empty(nbytes, dtype=torch.uint8, device=_ext.device()) if lo_rowmajor else None
     lo_n2 = torch.zeros(rows, dtype=torch.float32, device=_ext.device()) if lo_rowmajor else None
@@ -276,3 +280,36 @@ def quant_lo(lo_rm, rows, d):
     _count('pack')
     check(lib().skge_rank_quant_lo(ptr(lo_rm), rows, d, ptr(lo8), ptr(scale), stream()))
     return lo8, scale
+
+
+def quant_lo_s8(lo_rm, rows, d):
+    """Row-major fp16 lo rows -> (int8 rows, float32 [padded rows, 2] = (scale, ||lo||_1))."""
+    rp = (rows + 127) // 128 * 128
+    kb = (d + 63) // 64 * 64
+    lo8 = torch.empty(rp * kb, dtype=torch.int8, device=_ext.device())
+    meta = torch.empty(rp, 2, dtype=torch.float32, device=_ext.device())
+    _count('pack')
+    check(lib().skge_rank_quant_lo_s8(ptr(lo_rm), rows, d, ptr(lo8), ptr(meta), stream()))
+    return lo8, meta
+
+
+def pack_q8(q, qscale, tlo, thi):
+    """Swizzled int8 query tiles + the per-query constants of the refine epilogue."""
+    Q, d = q['q32'].shape
+    kb = (d + 63) // 64 * 64
+    qtiles = (Q + 127) // 128
+    Q8 = torch.empty(qtiles * 128 * kb, dtype=torch.int8, device=_ext.device())
+    qmeta = torch.empty(Q, 8, dtype=torch.float32, device=_ext.device())
+    _count('pack')
+    check(lib().skge_rank_pack_q8(ptr(q['q32']), ptr(qscale), ptr(q['qnorm']), ptr(tlo), ptr(thi), Q, d, ptr(Q8),
+                                  ptr(qmeta), stream()))
+    return Q8, qmeta
+
+
+def rank_refine_count(Ehi, Elo8, lo_meta, tile_w, perm, n_shard, shard_base, Qhi, Qlo, Q8, qmeta, Q, d, cta_group,
+                      cnt_gt, cand_q, cand_e, cand_count):
+    _count('gemm')
+    check(lib().skge_rank_refine_count(ptr(Ehi), ptr(Elo8), ptr(lo_meta), ptr(tile_w), ptr(perm), n_shard,
+                                       shard_base, ptr(Qhi), ptr(Qlo), ptr(Q8), ptr(qmeta), Q, d, cta_group,
+                                       ptr(cnt_gt), ptr(cand_q), ptr(cand_e), cand_q.numel(), ptr(cand_count),
+                                       stream()))

@@ -169,6 +169,34 @@ def test_regroup_plan_is_reusable_and_handles_edge_cases():
     assert regroup(np.zeros((0, 3), dtype=np.int64), np.zeros(0), np.zeros(0)) == ({}, {})
 
 
+def test_lazy_relation_ranks_behave_like_plain_dicts():
+    """regroup hands out per-relation dicts whose lists are built on first use: every read path
+    (indexing, iteration, equality in both directions, pickling, the reference's metric loop of
+    skge/base.py:1086-1103) must see a plain ``{'head': [...], 'tail': [...]}``."""
+    import pickle
+    from skge.ranking import regroup, ranking_scores, _RelRanks
+    test = np.array([(0, 1, 3), (2, 3, 1), (4, 5, 3)])
+    raw = np.array([1, 2, 3, 4, 5, 6], dtype=np.int32)
+    pos, fpos = regroup(test, raw, raw)
+    want = {3: {'head': [4, 6], 'tail': [1, 3]}, 1: {'head': [5], 'tail': [2]}}
+    assert pos == want and want == pos and not (pos != want)
+    pos, _ = regroup(test, raw, raw)
+    assert isinstance(pos[3], _RelRanks) and pos[3]['head'] == [4, 6] and type(pos[3]['head'][0]) is int
+    pos, _ = regroup(test, raw, raw)
+    assert sorted(pos[1].keys()) == ['head', 'tail'] and len(pos[1]) == 2 and 'tail' in pos[1]
+    pos, _ = regroup(test, raw, raw)
+    assert pickle.loads(pickle.dumps(pos)) == want and type(pickle.loads(pickle.dumps(pos))[3]) is dict
+    pos, _ = regroup(test, raw, raw)
+    assert dict(pos[3].items()) == want[3] and pos[3].get('nope') is None
+    with pytest.raises(KeyError):
+        pos[3]['nope']
+    pos, fpos = regroup(test, raw, raw)
+    assert ranking_scores(None, pos, fpos, 0, 'x') == pytest.approx(np.mean(1.0 / raw))
+    pos, _ = regroup(test, raw, raw)
+    pos[3]['head'].append(9)
+    assert pos[3] == {'head': [4, 6, 9], 'tail': [1, 3]}
+
+
 _GLOO_WORKER = r'''
 import os, sys
 sys.path[:0] = [%(root)r, os.path.join(%(root)r, 'scikit-kge_b200'), os.path.join(%(root)r, 'tests')]

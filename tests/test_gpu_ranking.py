@@ -66,6 +66,76 @@ def test_appendix_a4_untied_ranks(golden):
                         assert fpos[p][side][i] == int(g['a4_%s_fpos_%d_%s' % (tag, p, side)][i])
 
 
+@pytest.mark.parametrize('cg', [1, 2])
+def test_refine_engine_matches_reference_golden(golden, cg):
+    """The engine bench.py times (two tensor-core products + int8 refinement, both CTA groupings)
+    on the reference's own ranks (skge/base.py:913-1031 run through oracle/make_golden.py)."""
+    g = golden('rank_hole')
+    m = _model('hole', g['E0'], g['R0'])
+    ev = _evaluator('hole')([tuple(t) for t in g['test'].tolist()], [tuple(t) for t in g['true'].tolist()])
+    ev.engine, ev.nsplit, ev.cta_group = 'umma', 2, cg
+    pos, fpos = ev.positions(m)
+    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert list(pos.keys()) == [int(p) for p in g['rel']]
+    for side in ('head', 'tail'):
+        np.testing.assert_array_equal(_flat(pos, g['rel'], side), g['pos_' + side])
+        np.testing.assert_array_equal(_flat(fpos, g['rel'], side), g['fpos_' + side])
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('kind,N,d', [('hole', 1500, 150), ('hole', 900, 256), ('rescal', 800, 100), ('hole', 333, 37),
+                                      ('hole', 129, 64), ('hole', 2100, 200)])
+def test_refine_engine_matches_oracle_on_random_graphs(kind, N, d, cg):
+    """Same cases as the three-product engine: ragged query chunks, ragged entity tiles, odd and
+    even numbers of 64-wide k chunks (the int8 query rows are swizzled only for even counts)."""
+    M = 5
+    rng, true, test = _graph(N + d, N, M, 6 * N, 150)
+    E0 = (rng.normal(size=(N, d)) * 0.3).astype(np.float32).astype(np.float64)
+    shape = (M, d, d) if kind == 'rescal' else (M, d)
+    R0 = (rng.normal(size=shape) * 0.3).astype(np.float32).astype(np.float64)
+    m = _model(kind, E0, R0)
+    ev = _evaluator(kind)(test, true)
+    ev.chunk_queries = 128
+    ev.engine, ev.nsplit, ev.cta_group = 'umma', 2, cg
+    pos, fpos = ev.positions(m)
+    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    opos, ofpos, margins = orc.rank_positions(kind, E0, R0, test, true, tie='argsort', with_scores=True)
+    assert list(pos.keys()) == list(opos.keys())
+    nt = 0
+    for p in opos:
+        for side in ('head', 'tail'):
+            for i, mg in enumerate(margins[p][side]):
+                if mg > 1e-6:
+                    nt += 1
+                    assert pos[p][side][i] == opos[p][side][i], (p, side, i)
+                    assert fpos[p][side][i] == ofpos[p][side][i], (p, side, i)
+    assert nt >= 290
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+def test_refine_engine_on_a_million_entities(cg):
+    """A 1 M-entity x 2 k-query slice of the benchmarked workload (HolE d = 256): the refine
+    engine's counts equal the fp32 sweep engine's bit for bit, and so do 2 emulated shards."""
+    N, M, d, te = 1000000, 1000, 256, 1000
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    import skge
+    m = skge.HolE((N, N, M), d)
+    m.E.data.copy_(torch.randn(N, d, device='cuda', generator=gen) / d ** 0.5)
+    m.R.data.copy_(torch.randn(M, d, device='cuda', generator=gen) / d ** 0.5)
+    rng = np.random.default_rng(9)
+    test = np.stack([rng.integers(N, size=te), rng.integers(N, size=te), rng.integers(M, size=te)], 1)
+    true = np.concatenate([test, np.stack([test[:, 0], rng.integers(N, size=te), test[:, 2]], 1)])
+    ev = _evaluator('hole')(test, true)
+    ev.engine = 'sweep'
+    ref = ev.count_pass(m)
+    ev.engine, ev.nsplit, ev.cta_group = 'umma', 2, cg
+    got = ev.count_pass(m)
+    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert torch.equal(got, ref)
+    parts = sum(ev.count_pass(m, world=(r, 2)) for r in range(2))
+    assert torch.equal(parts, ref)
+
+
 def _graph(seed, N, M, ntrue, ntest):
     rng = np.random.default_rng(seed)
     true = np.unique(np.stack([rng.integers(N, size=ntrue), rng.integers(N, size=ntrue),
@@ -106,8 +176,9 @@ def test_positions_match_oracle_on_random_graphs(kind, N, d, engine):
     assert ev.last_stats['filter_pairs'] > 0
 
 
+@pytest.mark.parametrize('cg', [1, 2])
 @pytest.mark.parametrize('N,d,te', [(40943, 150, 700), (20000, 256, 1500), (5000, 64, 300)])
-def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te):
+def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te, cg):
     """Both coarse engines settle their undecided band in fp64, so the final counts
     must agree exactly (config-2-sized table and a d = 256 table); the single-product
     fp16 mode (nsplit = 1) must agree too, it only lists more candidates."""
@@ -131,14 +202,25 @@ def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te):
     # two products on the tensor cores, the third added in the epilogue for the wide-band pairs:
     # the refined scores are tested against the same tight band, so the fp64 workload stays small
     ev.nsplit = 2
+    ev.cta_group = cg
     got2 = ev.count_pass(m)
     assert torch.equal(got2, ref)
     assert ev.last_stats['engine'] == 'tcgen05-f16x2'
     assert ev.last_stats['candidates'] < 4 * max(c3, 64)
+    # the shadow of the shard is cached behind the table's checksum: a second pass reuses it, a
+    # changed table rebuilds it
+    key = ev._engines[('umma', 2, cg)]._shadow_key
+    assert torch.equal(ev.count_pass(m), ref) and ev._engines[('umma', 2, cg)]._shadow_key == key
+    m.E.data[17] *= 1.5
+    ev.engine = 'sweep'
+    ref2 = ev.count_pass(m)
+    ev.engine = 'umma'
+    assert torch.equal(ev.count_pass(m), ref2) and ev._engines[('umma', 2, cg)]._shadow_key != key
 
 
+@pytest.mark.parametrize('cg', [1, 2])
 @pytest.mark.parametrize('N,d', [(7777, 256), (3001, 96)])
-def test_refine_mode_with_mixed_row_norms(N, d):
+def test_refine_mode_with_mixed_row_norms(N, d, cg):
     """nsplit = 2 packs the shard by decreasing row norm and widens the band per 128-row tile.
     Rows spanning a factor 50 in norm, a ragged last tile and emulated shards must still give the
     fp32 engine's counts bit for bit, with candidates reported under their original ids."""
@@ -152,6 +234,7 @@ def test_refine_mode_with_mixed_row_norms(N, d):
     ref = ev.count_pass(m)
     ev.engine = 'umma'
     ev.nsplit = 2
+    ev.cta_group = cg
     got = ev.count_pass(m)
     assert ev.last_stats['engine'] == 'tcgen05-f16x2'
     assert torch.equal(got, ref)
