@@ -9,6 +9,10 @@ from oracle import cpu_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
+# CTA groupings of the refine kernel under test (SKGE_TEST_CG=1 isolates the single-CTA kernel)
+import os
+CGS = [int(x) for x in os.environ.get('SKGE_TEST_CG', '1,2').split(',')]
+
 
 def _flat(d, rel, side):
     return np.concatenate([np.array(d[int(p)][side]) for p in rel])
@@ -66,7 +70,7 @@ def test_appendix_a4_untied_ranks(golden):
                         assert fpos[p][side][i] == int(g['a4_%s_fpos_%d_%s' % (tag, p, side)][i])
 
 
-@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('cg', CGS)
 def test_refine_engine_matches_reference_golden(golden, cg):
     """The engine bench.py times (two tensor-core products + int8 refinement, both CTA groupings)
     on the reference's own ranks (skge/base.py:913-1031 run through oracle/make_golden.py)."""
@@ -82,7 +86,7 @@ def test_refine_engine_matches_reference_golden(golden, cg):
         np.testing.assert_array_equal(_flat(fpos, g['rel'], side), g['fpos_' + side])
 
 
-@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('cg', CGS)
 @pytest.mark.parametrize('kind,N,d', [('hole', 1500, 150), ('hole', 900, 256), ('rescal', 800, 100), ('hole', 333, 37),
                                       ('hole', 129, 64), ('hole', 2100, 200)])
 def test_refine_engine_matches_oracle_on_random_graphs(kind, N, d, cg):
@@ -112,7 +116,7 @@ def test_refine_engine_matches_oracle_on_random_graphs(kind, N, d, cg):
     assert nt >= 290
 
 
-@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('cg', CGS)
 def test_refine_engine_on_a_million_entities(cg):
     """A 1 M-entity x 2 k-query slice of the benchmarked workload (HolE d = 256): the refine
     engine's counts equal the fp32 sweep engine's bit for bit, and so do 2 emulated shards."""
@@ -176,7 +180,7 @@ def test_positions_match_oracle_on_random_graphs(kind, N, d, engine):
     assert ev.last_stats['filter_pairs'] > 0
 
 
-@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('cg', CGS)
 @pytest.mark.parametrize('N,d,te', [(40943, 150, 700), (20000, 256, 1500), (5000, 64, 300)])
 def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te, cg):
     """Both coarse engines settle their undecided band in fp64, so the final counts
@@ -218,7 +222,7 @@ def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te, cg):
     assert torch.equal(ev.count_pass(m), ref2) and ev._engines[('umma', 2, cg)]._shadow_key != key
 
 
-@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('cg', CGS)
 @pytest.mark.parametrize('N,d', [(7777, 256), (3001, 96)])
 def test_refine_mode_with_mixed_row_norms(N, d, cg):
     """nsplit = 2 packs the shard by decreasing row norm and widens the band per 128-row tile.
