@@ -169,10 +169,18 @@ class _GraphedStep(object):
     (parameters, optimiser state, counters, the sampler's device-side Philox offset).  Any
     capture failure falls back to eager launches."""
 
-    def __init__(self, body, enabled=True):
+    def __init__(self, body, enabled=True, signature=None):
         self.body, self.enabled, self.slots = body, enabled, {}
+        # host scalars and buffer addresses that a captured graph bakes in (learning rate, margin,
+        # AdaGrad state pointers ...): when they change the graphs are dropped and captured again
+        self.signature = signature
+        self._sig = signature() if signature else None
 
     def __call__(self, batch):
+        if self.signature is not None:
+            sig = self.signature()
+            if sig != self._sig:
+                self._sig, self.slots = sig, {}
         B = batch.numel()
         slot = self.slots.get(B)
         if slot is None:
@@ -255,9 +263,29 @@ class StochasticTrainer(object):
             return False
         if not hasattr(self.model, fused_attr) or hasattr(self.model, '_prepare_batch_step'):
             return False
+        # a subclass that overrides one of the reference's extension points must see it called
+        owner = next((c for c in type(self.model).__mro__ if fused_attr in c.__dict__), None)
+        for hook in ('_scores', '_gradients', '_pairwise_gradients'):
+            if getattr(type(self.model), hook, None) is not getattr(owner, hook, None):
+                return False
+        for base in (StochasticTrainer, PairwiseStochasticTrainer):
+            if isinstance(self, base):
+                own = base
+        if type(self)._process_batch is not own._process_batch or type(self)._batch_step is not own._batch_step:
+            return False
         if any(post_code(p.post) is None for p in self.model.params.values()):
             return False
         return self.samplef is None or self._device_sampler() is not None
+
+    def _graph_signature(self):
+        """Everything a captured minibatch graph freezes besides the example indices."""
+        m = self.model
+        sig = [self.learning_rate, getattr(m, 'margin', None), getattr(m, 'rparam', None),
+               getattr(getattr(m, 'af', None), '__name__', None), getattr(m, 'l1', None)]
+        for key, u in self._updaters.items():
+            st = u._state() if hasattr(u, '_state') else None
+            sig += [key, u.learning_rate, u.param.data.data_ptr(), st.data_ptr() if st is not None else 0]
+        return tuple(sig)
 
     def _randperm(self, n):
         if self._gen is None:
@@ -335,7 +363,7 @@ class StochasticTrainer(object):
             self.model._fused_logistic_step(self._updaters, bs.contiguous(), bo.contiguous(), bp.contiguous(),
                                             by.contiguous(), self._counts, self._loss_dev, valid=valid)
 
-        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs))
+        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs, self._graph_signature))
 
     def _optim(self, xys):
         """Hook path: the reference's loop on host lists (skge/base.py:1242-1291)."""
@@ -415,17 +443,21 @@ class PairwiseStochasticTrainer(StochasticTrainer):
         _check_ids(xs, getattr(self.model, 'sz', None))
         self._setup_fused()
         sampler = self._device_sampler()
-        sampler.ensure_device(xs)
-        n = sampler.train_size()
+        sampler.ensure_device()
+        # the positives are fit's xs; the sampler's own triple set only rejects negatives
+        # (skge/base.py:1394-1402, skge/sample.py:28-46) -- the two may differ, e.g. a sampler built
+        # on train + valid + test
+        src = _triples_to_device(xs)
+        n = src[0].numel()
         philox = torch.zeros(1, dtype=torch.int64, device=_ext.device())   # device-side draw counter
         per_pos = sampler.n * len(sampler.modes)
 
         def body(idx):
-            pos, neg, valid = sampler.device_sample(idx, idx.numel(), 0, offset_dev=philox)
+            pos, neg, valid = sampler.device_sample(idx, idx.numel(), 0, src=src, offset_dev=philox)
             philox.add_(idx.numel() * per_pos)
             self.model._fused_pair_step(self._updaters, pos, neg, valid, self._counts, self._nviol_dev)
 
-        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs))
+        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs, self._graph_signature))
 
     def _fit_fused_supplied(self, n):
         _check_ids(self.pxs + self.nxs, getattr(self.model, 'sz', None))
@@ -441,7 +473,7 @@ class PairwiseStochasticTrainer(StochasticTrainer):
             neg = tuple(nn[:, i].contiguous() for i in range(3))
             self.model._fused_pair_step(self._updaters, pos, neg, None, self._counts, self._nviol_dev)
 
-        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs))
+        self._run_epochs(n, _GraphedStep(body, self.cuda_graphs, self._graph_signature))
 
     def _pre_epoch(self):
         self.nviolations = 0

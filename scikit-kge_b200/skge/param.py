@@ -375,4 +375,4 @@ class AdaGrad(ParameterUpdate):
         return self.p2
 
     def reset(self):
-        self.p2 = torch.zeros_like(self.p2)
+        self.p2.zero_()     # in place: fused steps captured in a CUDA graph keep this address

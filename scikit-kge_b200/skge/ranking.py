@@ -80,8 +80,13 @@ def build_filter_pairs(true_triples, kind, given, rel, target, device=None):
         if qsel.numel() == 0 or tt.numel() == 0:
             continue
         keys = tt[:, 2] * nmax + tt[:, gcol]
-        packed = torch.unique(keys * nmax + tt[:, vcol])     # sorted, duplicates collapsed
-        ukeys, uvals = packed // nmax, packed % nmax
+        if (int(tt[:, 2].max().item()) + 1) * nmax * nmax < 2 ** 62:
+            packed = torch.unique(keys * nmax + tt[:, vcol])     # sorted, duplicates collapsed
+            ukeys, uvals = packed // nmax, packed % nmax
+        else:
+            # (p, given, value) does not fit one int64 key: sort (key, value) rows lexicographically
+            rows = torch.unique(torch.stack([keys, tt[:, vcol]], 1), dim=0)
+            ukeys, uvals = rows[:, 0].contiguous(), rows[:, 1].contiguous()
         qkey = rel_t[qsel] * nmax + given_t[qsel]
         lo = torch.searchsorted(ukeys, qkey, right=False)
         hi = torch.searchsorted(ukeys, qkey, right=True)
@@ -309,6 +314,26 @@ class FilteredRankingEval(object):
             self._dev[k] = v.to(dev, non_blocking=True)
         return self._dev
 
+    def _check_ids(self, N, M):
+        """Out-of-range ids are an IndexError in the reference (fancy indexing, skge/base.py:944-966);
+        the kernels do not bounds-check, so the test and filter triples are validated once."""
+        if getattr(self, '_ids_ok', None) == (N, M):
+            return
+        for name, a in (('test', self.test), ('true', self._true)):
+            if isinstance(a, torch.Tensor):
+                if a.numel() == 0:
+                    continue
+                a2 = a.reshape(-1, 3)
+                lo, hi_e, hi_p = int(a2.min()), int(a2[:, :2].max()), int(a2[:, 2].max())
+            else:
+                a2 = np.asarray(a, dtype=np.int64).reshape(-1, 3)
+                if a2.size == 0:
+                    continue
+                lo, hi_e, hi_p = int(a2.min()), int(a2[:, :2].max()), int(a2[:, 2].max())
+            if lo < 0 or hi_e >= N or hi_p >= M:
+                raise IndexError('%s triples: ids out of range for %d entities / %d relations' % (name, N, M))
+        self._ids_ok = (N, M)
+
     def h2d_bytes(self):
         return int(sum(v.numel() * v.element_size() for v in self._host.values())) if self._dev else 0
 
@@ -342,6 +367,7 @@ class FilteredRankingEval(object):
         RW = self._second(mdl)
         N, d = E.shape
         Q = st['given'].numel()
+        self._check_ids(N, RW.shape[0])
         emulated = world is not None
         rank, world = world if emulated else _world()
         lo, hi = shard_range(N, rank, world)
