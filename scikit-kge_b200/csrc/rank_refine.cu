@@ -162,15 +162,18 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
   tc_fence_after();
   const uint32_t tmem = ctrl->tmem_base;
 
+  // The three control warps run their loops warp-converged and elect one lane only around the
+  // instruction that must be issued once: addresses and descriptors are then warp-uniform values
+  // (uniform registers), not per-thread values that have to be broadcast before every UTCHMMA / UBLKCP.
   if (warp == 0) {
     // ===================== producer: bulk copies global -> shared =====================
-    if (lane == 0) {
-      uint32_t bstage = 0, bphase = 0, aphase = 0;
-      const uint32_t a_bytes = (uint32_t)(2 * kch * BLOCK_BYTES + QT * kb);
-      for (int item = unit; item < nitems; item += nunits) {
-        const Item it = get_item(a, item);
-        const int qt = min(a.qtiles - 1, CG == 2 ? 2 * it.qunit + (int)rank : it.qunit);
-        mbar_wait(&ctrl->a_empty, aphase ^ 1);  // previous item's MMAs retired, epilogue done with the int8 rows
+    uint32_t bstage = 0, bphase = 0, aphase = 0;
+    const uint32_t a_bytes = (uint32_t)(2 * kch * BLOCK_BYTES + QT * kb);
+    for (int item = unit; item < nitems; item += nunits) {
+      const Item it = get_item(a, item);
+      const int qt = min(a.qtiles - 1, CG == 2 ? 2 * it.qunit + (int)rank : it.qunit);
+      mbar_wait(&ctrl->a_empty, aphase ^ 1);  // previous item's MMAs retired, epilogue done with the int8 rows
+      if (elect_one()) {
         mbar_expect_tx(&ctrl->a_full, a_bytes);
         const uint8_t *qh = a.Qhi + (int64_t)qt * kch * BLOCK_BYTES;
         const uint8_t *ql = a.Qlo + (int64_t)qt * kch * BLOCK_BYTES;
@@ -179,85 +182,94 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
           bulk_g2s(sA_lo + c * BLOCK_BYTES, ql + (int64_t)c * BLOCK_BYTES, BLOCK_BYTES, &ctrl->a_full);
         }
         bulk_g2s(sQ8, a.Q8 + (int64_t)qt * QT * kb, (uint32_t)(QT * kb), &ctrl->a_full);
-        aphase ^= 1;
-        for (int et = it.et_beg; et < it.et_end; ++et) {
-          for (int ks = 0; ks < nks; ++ks) {
-            mbar_wait(&ctrl->b_empty[bstage], bphase ^ 1);
+      }
+      __syncwarp();
+      aphase ^= 1;
+      for (int et = it.et_beg; et < it.et_end; ++et) {
+        // my part of the entity tile: 128-row tile 2 et + rank (CG = 2) or both 128-row tiles (CG = 1)
+        const uint8_t *tile0 = a.Ehi + (int64_t)(2 * et + (CG == 2 ? (int)rank : 0)) * kch * BLOCK_BYTES;
+        for (int ks = 0; ks < nks; ++ks) {
+          mbar_wait(&ctrl->b_empty[bstage], bphase ^ 1);
+          uint8_t *dst = sB + bstage * STAGE_BYTES;
+          if (elect_one()) {
             mbar_expect_tx(&ctrl->b_full[bstage], STAGE_BYTES);
-            uint8_t *dst = sB + bstage * STAGE_BYTES;
             if (CG == 2) {
-              // my half of the entity tile: 128-row tile 2 et + rank, k range [32 ks, 32 ks + 32)
-              const uint8_t *src = a.Ehi + ((int64_t)(2 * et + (int)rank) * kch + (ks >> 1)) * BLOCK_BYTES +
-                                   (ks & 1) * STAGE_BYTES;
-              bulk_g2s(dst, src, STAGE_BYTES, &ctrl->b_full[bstage]);
+              // k range [32 ks, 32 ks + 32): 8 KB, contiguous in the block
+              bulk_g2s(dst, tile0 + (int64_t)ks * STAGE_BYTES, STAGE_BYTES, &ctrl->b_full[bstage]);
             } else {
               // 256 rows x 16 k as [kcore 2][rowgroup 32][8][16 B]: four 2 KB pieces of two 128-row tiles
-              const int c = ks >> 2, kq = ks & 3;
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const uint8_t *src = a.Ehi + ((int64_t)(2 * et + u) * kch + c) * BLOCK_BYTES + (2 * kq) * 2048;
-                bulk_g2s(dst + u * 2048, src, 2048, &ctrl->b_full[bstage]);
-                bulk_g2s(dst + 4096 + u * 2048, src + 2048, 2048, &ctrl->b_full[bstage]);
-              }
+              const uint8_t *src = tile0 + (int64_t)(ks >> 2) * BLOCK_BYTES + (ks & 3) * 4096;
+              const int64_t t1 = (int64_t)kch * BLOCK_BYTES;
+              bulk_g2s(dst, src, 2048, &ctrl->b_full[bstage]);
+              bulk_g2s(dst + 2048, src + t1, 2048, &ctrl->b_full[bstage]);
+              bulk_g2s(dst + 4096, src + 2048, 2048, &ctrl->b_full[bstage]);
+              bulk_g2s(dst + 6144, src + t1 + 2048, 2048, &ctrl->b_full[bstage]);
             }
-            if (++bstage == (uint32_t)nb) { bstage = 0; bphase ^= 1; }
           }
+          __syncwarp();
+          if (++bstage == (uint32_t)nb) { bstage = 0; bphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (leader) {
       constexpr uint32_t IDESC = idesc_f16(QT * CG, ET);
       constexpr uint32_t B_LBO = CG == 2 ? 2048u : 4096u;
+      // descriptors: only the start-address field changes (smem offsets < 256 KB never carry out of it)
+      const uint64_t ahi0 = make_desc(smem_u32(sA_hi), 2048u, 128u);
+      const uint64_t alo0 = make_desc(smem_u32(sA_lo), 2048u, 128u);
+      const uint64_t b00 = make_desc(smem_u32(sB), B_LBO, 128u);
       uint32_t bstage = 0, bphase = 0, aphase = 0, accs = 0, accphase = 0;
       for (int item = unit; item < nitems; item += nunits) {
         const Item it = get_item(a, item);
         mbar_wait(&ctrl->a_full, aphase);
-        if (CG == 2) mbar_wait_cluster(&ctrl->a_peer, aphase);
+        if (CG == 2) mbar_wait(&ctrl->a_peer, aphase);
         aphase ^= 1;
         for (int et = it.et_beg; et < it.et_end; ++et) {
-          if (CG == 2) mbar_wait_cluster(&ctrl->acc_empty[accs], accphase ^ 1);
-          else mbar_wait(&ctrl->acc_empty[accs], accphase ^ 1);
+          mbar_wait(&ctrl->acc_empty[accs], accphase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem + accs * ET;
-          uint32_t acc_on = 0;
           for (int ks = 0; ks < nks; ++ks) {
             mbar_wait(&ctrl->b_full[bstage], bphase);
-            if (CG == 2) mbar_wait_cluster(&ctrl->b_peer[bstage], bphase);
+            if (CG == 2) mbar_wait(&ctrl->b_peer[bstage], bphase);
             tc_fence_after();
-            const uint32_t b0 = smem_u32(sB + bstage * STAGE_BYTES);
+            const uint64_t bd = b00 + (uint64_t)((bstage * STAGE_BYTES) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < (CG == 2 ? 2 : 1); ++j) {
-              const int k16 = CG == 2 ? 2 * ks + j : ks;   // 16-k step within the row
-              const uint32_t aoff = (uint32_t)(k16 >> 2) * BLOCK_BYTES + (uint32_t)(k16 & 3) * 4096u;
-              const uint64_t bd = make_desc(b0 + j * 4096u, B_LBO, 128u);
-              umma_f16<CG>(d_tmem, make_desc(smem_u32(sA_hi) + aoff, 2048u, 128u), bd, IDESC, acc_on);
-              acc_on = 1;
-              umma_f16<CG>(d_tmem, make_desc(smem_u32(sA_lo) + aoff, 2048u, 128u), bd, IDESC, 1);
+              for (int j = 0; j < (CG == 2 ? 2 : 1); ++j) {
+                const int k16 = CG == 2 ? 2 * ks + j : ks;   // 16-k step within the row
+                const uint32_t aoff = ((uint32_t)(k16 >> 2) * BLOCK_BYTES + (uint32_t)(k16 & 3) * 4096u) >> 4;
+                umma_f16<CG>(d_tmem, ahi0 + aoff, bd + (uint64_t)(j * 256), IDESC, (uint32_t)(ks | j));
+                umma_f16<CG>(d_tmem, alo0 + aoff, bd + (uint64_t)(j * 256), IDESC, 1u);
+              }
+              tc_commit<CG>(&ctrl->b_empty[bstage]);  // frees the stage (in both CTAs) once these MMAs have read it
+              if (ks == nks - 1) tc_commit<CG>(&ctrl->acc_full[accs]);
             }
-            tc_commit<CG>(&ctrl->b_empty[bstage]);  // frees the stage (in both CTAs) once these MMAs have read it
+            __syncwarp();
             if (++bstage == (uint32_t)nb) { bstage = 0; bphase ^= 1; }
           }
-          tc_commit<CG>(&ctrl->acc_full[accs]);
           if (++accs == 2) { accs = 0; accphase ^= 1; }
         }
-        tc_commit<CG>(&ctrl->a_empty);
+        if (elect_one()) tc_commit<CG>(&ctrl->a_empty);
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
     // ===================== relay (peer CTA of a pair): my copies have landed -> tell the leader =====
-    if (CG == 2 && lane == 0 && !leader) {
+    if (CG == 2 && !leader) {
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       for (int item = unit; item < nitems; item += nunits) {
         const Item it = get_item(a, item);
         mbar_wait(&ctrl->a_full, aphase);
-        mbar_arrive_remote(&ctrl->a_peer, 0);
+        if (elect_one()) mbar_arrive_remote(&ctrl->a_peer, 0);
+        __syncwarp();
         aphase ^= 1;
         for (int et = it.et_beg; et < it.et_end; ++et) {
           for (int ks = 0; ks < nks; ++ks) {
             mbar_wait(&ctrl->b_full[bstage], bphase);
-            mbar_arrive_remote(&ctrl->b_peer[bstage], 0);
+            if (elect_one()) mbar_arrive_remote(&ctrl->b_peer[bstage], 0);
+            __syncwarp();
             if (++bstage == (uint32_t)nb) { bstage = 0; bphase ^= 1; }
           }
         }
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
     const int row = quarter * 32 + lane;             // query row inside the tile
     const int slot = lane & 7, part = lane >> 3;     // refinement: four lanes per pair
     const bool swz = (kch & 1) == 0;
+    constexpr uint32_t EPI_SLEEP = 128u;   // ns between polls of a waiting epilogue warp
     uint32_t tseq = 0, aphase = 0;
     for (int item = unit; item < nitems; item += nunits) {
       const Item it = get_item(a, item);
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
         tlo = m0.x; thi = m0.y; qw = m0.z; sq = m0.w;
         qA = m1.x; qB = m1.y;
       }
-      mbar_wait(&ctrl->a_full, aphase);   // the int8 query rows of this item are in shared memory
+      mbar_wait_sleep<EPI_SLEEP>(&ctrl->a_full, aphase);   // the int8 query rows of this item are in shared memory
       aphase ^= 1;
       int cnt = 0;
       for (int et = it.et_beg; et < it.et_end; ++et) {
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
         // this tile's wide band: the missing product is at most ||q|| * max ||e_lo|| over its rows
         const float tw = __ldg(a.tile_w + 2 * et + colhalf);
         const float whi = __fmaf_ru(qw, tw, thi), wlo = __fmaf_rd(-qw, tw, tlo);
-        mbar_wait(&ctrl->acc_full[st], (my >> 1) & 1u);
+        mbar_wait_sleep<EPI_SLEEP>(&ctrl->acc_full[st], (my >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + st * ET + colhalf * 128;
         for (int c2 = 0; c2 < 4; ++c2) {

@@ -24,51 +24,69 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) 
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
+// try_wait: the thread is suspended in hardware until the phase completes or a time limit passes.
+// HINT_NS > 0 sets that limit (ptxas turns it into NANOSLEEP.SYNCS, which an arrival on the
+// barrier ends early -- observed for local arrivals only: waits whose arrivals come from a peer
+// CTA or from tcgen05.commit.multicast use a short limit or none), so that waiting epilogue warps
+// do not spin through the issue slots the working ones need.
+template <uint32_t HINT_NS>
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  if constexpr (HINT_NS > 0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(HINT_NS)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
-// cluster-scope acquire: for barriers that a peer CTA arrives on
-__device__ __forceinline__ bool mbar_try_cluster(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must end in a launch failure, not in a hung GPU.  try_wait suspends
-// in hardware, so the clock is only read on the slow path.
+// Bounded wait: a protocol bug must end in a launch failure, not in a hung GPU.
+template <uint32_t HINT_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > (8ll << 30)) __trap();   // ~4 s
+  uint32_t spins = 0;
+  while (!mbar_try<HINT_NS>(bar, parity)) {
+    if (++spins > (HINT_NS >= 1000 ? (1u << 22) : (1u << 26))) __trap();   // seconds
   }
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-  if (mbar_try_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_cluster(bar, parity)) {
-    if (clock64() - t0 > (8ll << 30)) __trap();
+// Wait of a warp that has nothing else to do for a while (epilogue warps between accumulators):
+// poll, then give the issue slots away for SLEEP_NS before polling again.
+template <uint32_t SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try<0>(bar, parity)) {
+    __nanosleep(SLEEP_NS);
+    if (++spins > (1u << 24)) __trap();
   }
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 // 1-D bulk copy global -> this CTA's shared memory, completion on a local mbarrier
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
