@@ -9,16 +9,21 @@ One JSON line on rank 0.  Headline metric: filtered-rank queries/s on BASELINE.j
 config 5 (synthetic 1M entities / 1k relations, HolE d=256; 2 x 100k test queries,
 raw + filtered ranks, both directions), entity table sharded over the N GPUs
 (strong scaling: the graph and the query set are fixed).  A "step" is one full
-ranking pass over the test set.  At N=1 the line also carries `train` (HolE
-d=256 minibatch steps of 500k positives, config 5's batch size), `roofline`
-(the coarse contraction kernel), `cpu_baseline` (the oracle port on host cores)
-and `e2e` (through FilteredRankingEval.positions with host inputs / outputs).
+ranking pass over the test set.  The line carries `rank_checksum` (sums of the raw and filtered
+ranks and the filtered MRR of the whole test set: identical for every N), `roofline` (the coarse
+contraction kernel, CUDA events) and `e2e` (through FilteredRankingEval.positions with host inputs
+/ outputs); at N = 1 also `train` (HolE d=256 minibatch steps of 500k positives, config 5's batch
+size), `extra` (BASELINE configs 1-4: ranking and training) and `cpu_baseline`.
 
---impl reference times the reference's CPU algorithm (the numpy oracle port --
-the reference is Python and cannot travel to the GPU box) on a bounded sample
-of the same workload.
+--impl reference times the UNMODIFIED reference (oracle/_ref, shipped by oracle/build_ref.py):
+its own HolEEval(...).positions(model) (skge/base.py:913-1031, skge/run_hole.py:10-19) on the host
+cores, on the same synthetic graph and embeddings, one relation and two of its test triples per
+step with their real filter lists.  The `cpu_baseline` leg of the B200 arm runs the same code in a
+subprocess (the reference package is also called `skge`) and checks that the GPU's ranks of the
+sampled queries equal the reference's.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -27,9 +32,7 @@ import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, 'scikit-kge_b200')):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+PKG = os.path.join(ROOT, 'scikit-kge_b200')
 
 import numpy as np  # noqa: E402
 
@@ -43,11 +46,6 @@ WORKLOADS = {
 }
 
 
-# per-launch DRAM bytes (read + write) and tensor-pipe active % of the coarse kernel at the full
-# config-5 size on one GPU, from the committed ncu --set full captures
-NCU_GEMM = {'tcgen05-f16x3': (12.875e9 + 0.180e9, 69.2), 'tcgen05-f16x2': (13.641e9 + 0.178e9, 53.5)}
-
-
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -56,13 +54,16 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg5', choices=sorted(WORKLOADS))
     ap.add_argument('--test-triples', type=int, default=0, help='override the number of test triples')
-    ap.add_argument('--true-triples', type=int, default=0, help='override the number of known-true triples used for filtering')
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--train-batches', type=int, default=6)
     ap.add_argument('--engine', default='auto', choices=['auto', 'sweep', 'umma'])
     ap.add_argument('--nsplit', type=int, default=0, choices=[0, 1, 2, 3],
                     help='tcgen05 engine: fp16 products on the tensor cores (0 = the evaluator default)')
+    # reference arm as the child of the B200 arm's cpu_baseline leg
+    ap.add_argument('--from-npz', default='', help='(reference arm) read tables and samples from this file')
+    ap.add_argument('--emit-ranks', default='', help='(reference arm) write the sampled ranks to this JSON file')
     return ap.parse_args()
 
 
@@ -70,8 +71,59 @@ def peaks():
     f = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(f):
         p = json.load(open(f))
-        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p['bf16_tflops_sustained'], src='measured')
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p['bf16_tflops_sustained'],
+                    sm_max_mhz=p.get('sm_max_mhz', 1965.0), src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, sm_max_mhz=1965.0, src='fallback')
+
+
+def ncu_summary(kernel):
+    """Per-launch DRAM traffic and tensor-pipe activity of a kernel from the tracked summary of the
+    latest ncu --set full capture (profiles/r02_ncu_summary.json, written by profiles/summarize.py
+    together with the commit it was captured at)."""
+    f = os.path.join(ROOT, 'profiles', 'r02_ncu_summary.json')
+    if not os.path.exists(f):
+        return None
+    try:
+        return json.load(open(f)).get(kernel)
+    except Exception:
+        return None
+
+
+def load_synth():
+    """skge/synth.py of the product as a stand-alone module (numpy + torch only): the reference arm
+    must not import the product package, which shares the reference's name."""
+    spec = importlib.util.spec_from_file_location('skge_b200_synth', os.path.join(PKG, 'skge', 'synth.py'))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def build_workload(args, with_graph=True):
+    """The synthetic workload, generated on the HOST with seeded torch CPU generators so that the
+    B200 arm and the reference arm see bit-identical graphs and embeddings.  Returns a dict of CPU
+    tensors: true [*, 3] (train + valid + test), test [te, 3], E, R (fp32)."""
+    import torch
+    synth = load_synth()
+    shape, model, d, desc = WORKLOADS[args.workload]
+    N, M, T, V, Te = synth.SHAPES[shape]
+    te = args.test_triples or Te
+    out = dict(N=N, M=M, d=d, model=model, desc=desc, te=te)
+    E, R = synth.init_embeddings(model, N, M, d, device='cpu')
+    out['E'], out['R'] = E, R
+    if with_graph:
+        g = synth.make_graph(shape, device='cpu')
+        out['true'] = torch.cat([g['train'], g['valid'], g['test']])
+        out['test'] = g['test'][:te].contiguous()
+    return out
+
+
+def config_of(w):
+    """The workload description both arms print (identical keys and values)."""
+    N, M, d = w['N'], w['M'], w['d']
+    return {'workload': w['desc'], 'queries': 2 * w['te'], 'entities': N, 'relations': M, 'd': d,
+            'filter': 'known-true triples of train + valid + test',
+            'l2': ('inputs larger than L2 (entity table %.0f MB)' % (N * d * 4 / 1e6)) if N * d * 4 > 126e6
+            else 'entity table is L2-resident (%.1f MB); flagged' % (N * d * 4 / 1e6)}
 
 
 class ClockSampler(object):
@@ -100,12 +152,13 @@ class ClockSampler(object):
         self.f.flush()
         rows = [l.split(', ') for l in open(self.f.name).read().strip().splitlines() if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for nm, v in zip(names, r[5:9]):
                     if v.strip().lower().startswith('active'):
                         reasons.add(nm)
@@ -113,80 +166,112 @@ class ClockSampler(object):
                 continue
         if sm:
             out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm))
+                       samples=len(sm), power_w_max=float(max(pw)) if pw else None)
         return out
 
 
 # ---------------------------------------------------------------------------
-# reference arm: the numpy oracle port on the host cores
+# reference arm: the unmodified reference on the host cores
 # ---------------------------------------------------------------------------
 
-def cpu_rank_sample(model, E, R, N, M, d, queries_per_relation, nq=2, seed=0):
-    """One 'reference step': prepare() for one relation + nq queries of that relation
-    (skge/base.py:937-1017), float64 numpy.  Returns (t_prepare, t_per_query)."""
-    from oracle import cpu_oracle as orc
-    rng = np.random.default_rng(seed)
-    p = int(rng.integers(M))
-    prepare, scores_o, scores_s = orc._eval_hooks(model, E, R)
-    t0 = time.perf_counter()
-    prepare(p)
-    t1 = time.perf_counter()
-    for i in range(nq):
-        s, o = int(rng.integers(N)), int(rng.integers(N))
-        sc = (scores_o(s, p) if i % 2 == 0 else scores_s(o, p)).flatten()
-        tgt = o if i % 2 == 0 else s
-        order = np.argsort(sc)[::-1]
-        _ = int(np.where(order == tgt)[0][0]) + 1
-        sc[rng.integers(N, size=8)] = -np.inf           # the filter list of the query
-        order = np.argsort(sc)[::-1]
-        _ = int(np.where(order == tgt)[0][0]) + 1
-    t2 = time.perf_counter()
-    return t1 - t0, (t2 - t1) / nq
+def pick_sample(test, true, step, per_step=2):
+    """Step ``step`` of the reference arm: one relation (that of test triple ``step * 997``), its first
+    ``per_step`` test triples, and every known-true triple that can appear in their filter lists
+    (same relation, same subject or same object) -- the reference's tt[p]['os'][s] / tt[p]['ss'][o]
+    of skge/base.py:744-752 are then exactly those of the full graph."""
+    p = int(test[(step * 997) % len(test), 2])
+    mine = test[test[:, 2] == p][:per_step]
+    rel = true[true[:, 2] == p]
+    keep = np.isin(rel[:, 0], mine[:, 0]) | np.isin(rel[:, 1], mine[:, 1])
+    return mine, rel[keep]
 
 
-def host_tables(model, N, M, d):
-    rng = np.random.default_rng(7)
-    E = rng.uniform(-1, 1, (N, d)) * (np.sqrt(6) / np.sqrt(N + d))
-    E /= np.linalg.norm(E, axis=1, keepdims=True)
-    R = rng.uniform(-1, 1, (M, d)) * (np.sqrt(6) / np.sqrt(M + d))
-    return E, R
+def reference_steps(ref, kind, N, M, d, E, R, samples):
+    """Runs the reference's own evaluator on each (test, true) sample.  Returns per-sample
+    (t_positions, t_prepare, ranks) with ranks = [(raw tail, filtered tail, raw head, filtered head)]."""
+    cls = {'hole': ref.HolE, 'transe': ref.TransE}[kind]
+    Ev = {'hole': ref.HolEEval, 'transe': ref.TransEEval}[kind]
+    mdl = cls((N, N, M), d)
+    mdl.E[...] = np.asarray(E, dtype=np.float64)
+    mdl.R[...] = np.asarray(R, dtype=np.float64)
+    out = []
+    for test, true in samples:
+        ev = Ev([tuple(int(v) for v in t) for t in test], [tuple(int(v) for v in t) for t in true])
+        tprep = [0.0]
+        inner = ev.prepare
+
+        def timed_prepare(m, p, inner=inner):
+            t0 = time.perf_counter()
+            inner(m, p)
+            tprep[0] += time.perf_counter() - t0
+        ev.prepare = timed_prepare          # instance attribute: the reference's class is untouched
+        t0 = time.perf_counter()
+        pos, fpos = ev.positions(mdl)
+        dt = time.perf_counter() - t0
+        ranks = []
+        for p in pos:
+            for i in range(len(pos[p]['tail'])):
+                ranks.append((int(pos[p]['tail'][i]), int(fpos[p]['tail'][i]), int(pos[p]['head'][i]),
+                              int(fpos[p]['head'][i])))
+        out.append((dt, tprep[0], ranks))
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from skge.synth import SHAPES
-    shape, model, d, desc = WORKLOADS[args.workload]
-    N, M, T, V, Te = SHAPES[shape]
-    te = args.test_triples or Te
-    qpr = max(1.0, 2.0 * te / min(M, te))       # queries that share one prepare() in the full workload
-    E, R = host_tables(model, N, M, d)
-    tp, tq = [], []
-    for i in range(args.warmup):
-        cpu_rank_sample(model, E, R, N, M, d, qpr, seed=100 + i)
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    if ref_loader.find_reference() is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref is missing: run python oracle/build_ref.py '
+                                                                'where /root/reference exists'}))
+        return
+    ref = ref_loader.load()
+    if args.from_npz:
+        z = np.load(args.from_npz)
+        w = dict(N=int(z['N']), M=int(z['M']), d=int(z['d']), model=str(z['model']), desc=str(z['desc']),
+                 te=int(z['te']))
+        E, R = z['E'], z['R']
+        nsteps = int(z['nsamples'])
+        samples = [(z['test%d' % i], z['true%d' % i]) for i in range(nsteps)]
+        nrel_test = int(z['nrel_test'])
+        warm = 0
+    else:
+        w = build_workload(args)
+        E, R = w['E'].numpy(), w['R'].numpy()
+        test, true = w['test'].numpy(), w['true'].numpy()
+        nrel_test = int(len(np.unique(test[:, 2])))
+        warm = args.warmup
+        samples = [pick_sample(test, true, i) for i in range(warm + args.steps)]
+        del true
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        a, b = cpu_rank_sample(model, E, R, N, M, d, qpr, seed=i)
-        tp.append(a)
-        tq.append(b)
-    wall = time.perf_counter() - t0
-    tpm, tqm = float(np.mean(tp)), float(np.mean(tq))
-    value = qpr / (tpm + qpr * tqm)
+    res = reference_steps(ref, w['model'], w['N'], w['M'], w['d'], E, R, samples)
+    timed = res[warm:]
+    wall = sum(r[0] for r in timed)
+    tprep = float(np.mean([r[1] for r in timed]))
+    nq = sum(2 * len(r[2]) for r in timed)
+    tquery = float((wall - sum(r[1] for r in timed)) / max(nq, 1))
+    Q = 2 * w['te']
+    value = Q / (nrel_test * tprep + Q * tquery)      # the reference's whole job: one prepare() per relation
     cores = len(os.sched_getaffinity(0))
-    sample = ('per step: prepare() of one relation + 2 queries (raw+filtered argsort ranks) on the full N=%d table; '
-              'value extrapolates to the workload\'s %.0f queries per relation: q/(t_prepare + q*t_query), '
-              't_prepare=%.2fs t_query=%.3fs' % (N, qpr, tpm, tqm))
+    sample = ('per step: the unmodified reference\'s %sEval(test, true).positions(model) (oracle/_ref) for one relation '
+              'and %d of its test triples (raw + filtered argsort ranks, both directions) on the full N=%d table with '
+              'their real filter lists; value = Q / (relations_in_test * t_prepare + Q * t_query) with Q=%d, '
+              'relations_in_test=%d, t_prepare=%.2fs, t_query=%.3fs; numpy float64, default threading'
+              % ('HolE' if w['model'] == 'hole' else 'TransE', len(samples[0][0]), w['N'], Q, nrel_test, tprep, tquery))
     line = {
         'impl': 'reference', 'metric': 'filtered-rank queries/s', 'value': value, 'unit': 'queries/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1000.0 * wall / max(1, args.steps), 'higher_is_better': True, 'scaling': 'strong',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': desc, 'test_triples': te, 'engine': 'numpy oracle port (oracle/cpu_oracle.py)'},
-        'cpu_baseline': {'value': value, 'unit': 'queries/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'n_gpus': args.gpus, 'steps': len(timed), 'warmup': warm,
+        'ms_per_step': 1000.0 * wall / max(1, len(timed)), 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config_of(w),
+        'cpu_baseline': {'value': value, 'unit': 'queries/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
         'e2e': {'value': value, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
+        'gpu_launches': 0, 'reference_root': os.path.relpath(ref.root, ROOT),
     }
+    if args.emit_ranks:
+        with open(args.emit_ranks, 'w') as f:
+            json.dump({'ranks': [r[2] for r in res]}, f)
     print(json.dumps(line))
 
 
@@ -194,7 +279,58 @@ def run_reference(args):
 # B200 arm
 # ---------------------------------------------------------------------------
 
+def cpu_baseline_leg(w, E, R, test, true, mdl, Ev, nsamples=2):
+    """The reference itself (subprocess) on ``nsamples`` sampled relations of this very workload, and
+    the GPU's ranks of the same queries compared with the reference's."""
+    import torch
+    samples = [pick_sample(test, true, 3 + i) for i in range(nsamples)]
+    with tempfile.TemporaryDirectory() as tmp:
+        npz, out = os.path.join(tmp, 'w.npz'), os.path.join(tmp, 'ranks.json')
+        arrs = dict(N=w['N'], M=w['M'], d=w['d'], model=w['model'], desc=w['desc'], te=w['te'], E=E, R=R,
+                    nsamples=nsamples, nrel_test=int(len(np.unique(test[:, 2]))))
+        for i, (t, tr) in enumerate(samples):
+            arrs['test%d' % i], arrs['true%d' % i] = t, tr
+        np.savez(npz, **arrs)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--from-npz', npz,
+                            '--emit-ranks', out, '--workload', [k for k, v in WORKLOADS.items() if v[3] == w['desc']][0]],
+                           capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            return {'error': (r.stderr or r.stdout)[-400:]}
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        if 'cpu_baseline' not in line:
+            return {'error': line.get('unavailable', 'no cpu_baseline in the reference line')}
+        ref_ranks = json.load(open(out))['ranks']
+    base = line['cpu_baseline']
+    # the GPU's ranks for the same queries, same filter lists
+    equal, nq = True, 0
+    for (t, tr), rr in zip(samples, ref_ranks):
+        pos, fpos = Ev(t, tr).positions(mdl)
+        got = []
+        for p in pos:
+            for i in range(len(pos[p]['tail'])):
+                got.append((pos[p]['tail'][i], fpos[p]['tail'][i], pos[p]['head'][i], fpos[p]['head'][i]))
+        nq += 4 * len(got)
+        equal = equal and [tuple(x) for x in rr] == got
+    base['gpu_ranks_equal_reference'] = bool(equal)
+    base['ranks_compared'] = nq
+    return base
+
+
+def rank_checksum(cnt):
+    """Order-independent digest of a ranking pass: sums of the raw and filtered ranks and the
+    filtered MRR, from the all-reduced count array (identical on every rank and for every N)."""
+    import torch
+    raw = 1 + cnt[0].to(torch.int64)
+    filt = raw - cnt[1].to(torch.int64)
+    return {'sum_raw': int(raw.sum().item()), 'sum_filtered': int(filt.sum().item()),
+            'fmrr': float((1.0 / filt.double()).mean().item()),
+            'hits10_filtered': float((filt <= 10).double().mean().item())}
+
+
 def run_b200(args):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -208,31 +344,41 @@ def run_b200(args):
 
     import skge
     from skge import kernels, ranking
-    from skge.synth import make_graph, init_embeddings, SHAPES
     shape, model, d, desc = WORKLOADS[args.workload]
-    N, M, T, V, Te = SHAPES[shape]
-    te = args.test_triples or Te
 
-    # --- synthetic inputs (identical on every rank: same seed) -------------------
+    # --- synthetic inputs: generated once on the host (rank 0), identical everywhere -------------
     torch.manual_seed(1234)
     t_setup = time.perf_counter()
-    ntrue = args.true_triples or (T + V + Te)
-    g = make_graph((N, M, max(ntrue - V - te, 1), V, te), device=dev)
-    true = torch.cat([g['train'], g['valid'], g['test']])
-    test = g['test']
+    if rank == 0:
+        w = build_workload(args)
+        true, test, E, R = w['true'].to(dev), w['test'].to(dev), w['E'].to(dev), w['R'].to(dev)
+        meta = torch.tensor([true.shape[0], test.shape[0]], device=dev)
+    else:
+        w = build_workload(args, with_graph=False)
+        meta = torch.zeros(2, dtype=torch.int64, device=dev)
+        E, R = torch.empty_like(w['E'], device=dev), torch.empty_like(w['R'], device=dev)
+    if world > 1:
+        dist.broadcast(meta, 0)
+        if rank != 0:
+            true = torch.empty(int(meta[0]), 3, dtype=torch.int64, device=dev)
+            test = torch.empty(int(meta[1]), 3, dtype=torch.int64, device=dev)
+        for t in (true, test, E, R):
+            dist.broadcast(t, 0)
+    N, M, te = w['N'], w['M'], w['te']
     cls = {'hole': skge.HolE, 'transe': skge.TransE}[model]
     mdl = cls((N, N, M), d)
-    E, R = init_embeddings(model, N, M, d, device=dev)
     mdl.E.data.copy_(E)
     mdl.R.data.copy_(R)
-    del E, R
     Ev = {'hole': ranking.HolEEval, 'transe': ranking.TransEEval}[model]
     ev = Ev(test, true)
     if args.engine != 'auto':
         ev.engine = args.engine
     if args.nsplit:
         ev.nsplit = args.nsplit
-    del true, g
+    host = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        host = (E.cpu().numpy(), R.cpu().numpy(), test.cpu().numpy(), true.cpu().numpy())
+    del true, E, R
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
     Q = 2 * te
@@ -267,20 +413,18 @@ def run_b200(args):
     clk = clocks.stop()
     launches = kernels.LAUNCHES['n'] - l0
     ranking._SweepEngine.timing = False
-    kt = [(a.elapsed_time(b), w) for a, b, w in ranking.TIMINGS]
+    kt = [(a.elapsed_time(b), wk) for a, b, wk in ranking.TIMINGS]
     ranking.TIMINGS.clear()
     stats = dict(ev.last_stats)
     value = Q * args.steps / (ms / 1000.0)
+    checksum = rank_checksum(ev.count_pass(mdl))
 
     # --- end to end through the public API (host in, host out) --------------------
-    def e2e_step():
-        pos, fpos = ev.positions(mdl)
-        return pos, fpos
-    e2e_step()
+    ev.positions(mdl)
     wall0 = time.perf_counter()
     barrier()
     for _ in range(args.steps):
-        e2e_step()
+        ev.positions(mdl)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - wall0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -294,55 +438,17 @@ def run_b200(args):
         return
 
     pk = peaks()
-    # roofline of the dominant kernel (the coarse query x entity contraction)
-    tensor = model != 'transe'
-    if kt:
-        avg_ms = float(np.mean([t for t, _ in kt]))
-        work = float(np.mean([w for _, w in kt]))
-        if tensor:
-            achieved = work / (avg_ms * 1e-3) / 1e12
-            peak = pk['tf_sust']
-            traffic = pipe_pct = None
-            eng = str(stats.get('engine', ''))
-            if args.workload == 'cfg5' and world == 1 and te == Te:
-                # dram read + write of one launch and tensor-pipe activity from ncu --set full
-                # (profiles/r01_rank_cfg5_tcgen05_v2.txt, profiles/r01_rank_cfg5_tcgen05_refine.txt)
-                traffic, pipe_pct = NCU_GEMM.get(eng, (None, None))
-            nprod = {'tcgen05-f16x3': 3, 'tcgen05-f16x2': 2}.get(eng, 1)
-            roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak, 'traffic': traffic, 'kernel': eng,
-                    'mma_products_per_algorithmic_mac': nprod,
-                    'executed_tflops': achieved * nprod,
-                    'tensor_pipe_active_pct_ncu': pipe_pct,
-                    'ncu_note': ('captured one commit earlier (fp16 e_lo rows in the refinement; the 8-bit rows '
-                                 'gather half of those bytes)') if nprod == 2 and traffic else None,
-                    'launch_ms': avg_ms, 'launches_timed': len(kt), 'peak_source': pk['src'] + ' bf16 sustained',
-                    'algorithmic_flops_per_launch': work,
-                    'kernel_share_of_step': sum(t for t, _ in kt) / max(ms, 1e-9)}
-        else:
-            n_shard = stats['shard'][1] - stats['shard'][0]
-            # reference access pattern: one sweep of the fp32 table per query (4*N*d bytes)
-            bytes_per_launch = work / 2.0 * 4.0
-            achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s',
-                    'frac': achieved / pk['hbm'], 'traffic': None, 'kernel': stats.get('engine'),
-                    'launch_ms': avg_ms, 'launches_timed': len(kt), 'peak_source': pk['src'],
-                    'note': 'algorithmic bytes = 4*N*d per query (the reference re-reads the table per query); '
-                            'query tiling makes the kernel FP32-ALU bound, so frac > 1 is expected',
-                    'kernel_share_of_step': sum(t for t, _ in kt) / max(ms, 1e-9)}
-    else:
-        roof = None
-
+    roof = roofline_of(model, stats, kt, ms, pk, full=(args.workload == 'cfg5' and world == 1 and not args.test_triples))
+    cfg = config_of(w)
     line = {
         'metric': 'filtered-rank queries/s', 'value': value, 'unit': 'queries/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-        'dtype': stats.get('dtype', 'f32+f64'), 'data': 'synthetic',
-        'config': {'workload': desc, 'queries': Q, 'entities': N, 'relations': M, 'd': d,
-                   'filter_pairs': stats.get('filter_pairs'), 'band_candidates_last_step': stats.get('candidates'),
-                   'sharding': 'entity rows / %d ranks' % world, 'l2': 'inputs larger than L2 (entity table %.0f MB)'
-                   % (N * d * 4 / 1e6) if N * d * 4 > 126e6 else 'entity table is L2-resident (%.1f MB); flagged' % (N * d * 4 / 1e6),
-                   'engine': stats.get('engine'), 'setup_s': setup_s},
+        'dtype': stats.get('dtype', 'f32+f64'), 'data': 'synthetic', 'config': cfg,
+        'detail': {'filter_pairs': stats.get('filter_pairs'), 'band_candidates_last_step': stats.get('candidates'),
+                   'sharding': 'entity rows / %d ranks' % world, 'engine': stats.get('engine'), 'setup_s': setup_s,
+                   'cta_group': getattr(ev, 'cta_group', None)},
+        'rank_checksum': checksum,
         'clocks': clk,
         'e2e': {'value': e2e, 'unit': 'queries/s', 'h2d_bytes_per_step': ev.h2d_bytes(),
                 'd2h_bytes_per_step': 2 * Q * 4, 'api': '%s(test, true).positions(model)' % Ev.__name__},
@@ -357,18 +463,17 @@ def run_b200(args):
         except Exception as e:  # keep the headline line even if the side benchmark fails
             line['train'] = {'error': repr(e)}
 
-    # --- CPU baseline (oracle port) --------------------------------------------------
-    if world == 1 and not args.no_cpu:
+    # --- BASELINE configs 1-4 (ranking + training; milliseconds each) ----------------
+    if world == 1 and not args.no_extras and args.workload == 'cfg5':
         try:
-            qpr = max(1.0, 2.0 * te / min(M, te))
-            Eh = mdl.E.data.double().cpu().numpy()
-            Rh = mdl.R.data.double().cpu().numpy()
-            tp, tq = cpu_rank_sample(model, Eh, Rh, N, M, d, qpr, nq=4)
-            v = qpr / (tp + qpr * tq)
-            line['cpu_baseline'] = {
-                'value': v, 'unit': 'queries/s', 'cores': len(os.sched_getaffinity(0)), 'kind': 'port',
-                'sample': 'prepare() of one relation + 4 queries on the full table, extrapolated to %.0f queries per '
-                          'relation (t_prepare=%.2fs, t_query=%.3fs); numpy float64, default threading' % (qpr, tp, tq)}
+            line['extra'] = bench_extras(pk)
+        except Exception as e:
+            line['extra'] = {'error': repr(e)}
+
+    # --- CPU baseline: the reference itself on the host cores (subprocess) -----------
+    if host is not None:
+        try:
+            line['cpu_baseline'] = cpu_baseline_leg(w, host[0], host[1], host[2], host[3], mdl, Ev)
         except Exception as e:
             line['cpu_baseline'] = {'error': repr(e)}
 
@@ -378,6 +483,134 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def roofline_of(model, stats, kt, ms, pk, full=False):
+    """Roofline of the dominant kernel (the coarse query x entity contraction), CUDA events."""
+    if not kt:
+        return None
+    avg_ms = float(np.mean([t for t, _ in kt]))
+    work = float(np.mean([wk for _, wk in kt]))
+    share = sum(t for t, _ in kt) / max(ms, 1e-9)
+    eng = str(stats.get('engine', ''))
+    if model != 'transe':
+        achieved = work / (avg_ms * 1e-3) / 1e12
+        nprod = {'tcgen05-f16x3': 3, 'tcgen05-f16x2': 2}.get(eng, 1)
+        kname = 'rank_refine_kernel' if nprod == 2 else 'rank_gemm_kernel'
+        ncu = ncu_summary(kname) if full else None
+        return {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['tf_sust'], 'traffic': ncu.get('dram_bytes_per_launch') if ncu else None,
+                'kernel': kname, 'engine': eng, 'mma_products_per_algorithmic_mac': nprod,
+                'executed_tflops': achieved * nprod,
+                'ncu': ncu, 'launch_ms': avg_ms, 'launches_timed': len(kt),
+                'peak_source': pk['src'] + ' bf16 sustained', 'algorithmic_flops_per_launch': work,
+                'kernel_share_of_step': share}
+    # TransE: |e - q| accumulations on the FP32 pipe, 2 lane-instructions per (query, entity, k)
+    issue_peak = 148 * 128 * pk['sm_max_mhz'] * 1e6
+    achieved = work / (avg_ms * 1e-3)
+    return {'bound': 'fp32-issue', 'achieved': achieved / 1e12, 'peak': issue_peak / 1e12, 'unit': 'T lane-instr/s',
+            'frac': achieved / issue_peak, 'traffic': None, 'kernel': 'rank_sweep_kernel', 'engine': eng,
+            'launch_ms': avg_ms, 'launches_timed': len(kt),
+            'peak_source': '148 SMs x 128 FP32 lanes x %.0f MHz (max SM clock)' % pk['sm_max_mhz'],
+            'note': 'the table is read from L2 / shared memory once per 128-query tile, so the sweep is bound by '
+                    'instruction issue (one FADD + one FADD.abs per element), not by HBM',
+            'algorithmic_lane_instructions_per_launch': work, 'kernel_share_of_step': share}
+
+
+def bench_rank_small(name, pk, steps=5):
+    """Device-resident and end-to-end ranking of one of the small BASELINE configs on 1 GPU."""
+    import torch
+    import skge
+    from skge import kernels, ranking
+    synth = load_synth()
+    shape, model, d, desc = WORKLOADS[name]
+    N, M, T, V, Te = synth.SHAPES[shape]
+    g = synth.make_graph(shape, device='cpu')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    true = torch.cat([g['train'], g['valid'], g['test']]).to(dev)
+    test = g['test'].to(dev)
+    E, R = synth.init_embeddings(model, N, M, d, device='cpu')
+    mdl = {'hole': skge.HolE, 'transe': skge.TransE}[model]((N, N, M), d)
+    mdl.E.data.copy_(E.to(dev))
+    mdl.R.data.copy_(R.to(dev))
+    ev = {'hole': ranking.HolEEval, 'transe': ranking.TransEEval}[model](test, true)
+    for _ in range(3):
+        ev.count_pass(mdl)
+    ranking._SweepEngine.timing = True
+    ranking.TIMINGS.clear()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        ev.count_pass(mdl)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    ranking._SweepEngine.timing = False
+    kt = [(x.elapsed_time(y), wk) for x, y, wk in ranking.TIMINGS]
+    ranking.TIMINGS.clear()
+    stats = dict(ev.last_stats)
+    ev.positions(mdl)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ev.positions(mdl)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    Q = 2 * Te
+    return {'workload': desc, 'queries': Q, 'value': Q * steps / (ms / 1e3), 'e2e': Q * steps / e2e_s,
+            'unit': 'queries/s', 'ms_per_pass': ms / steps, 'steps': steps,
+            'rank_checksum': rank_checksum(ev.count_pass(mdl)),
+            'roofline': roofline_of(model, stats, kt, ms, pk)}
+
+
+def bench_train_small(name, shape, model, d, pairwise, upd_name, margin, epochs=5):
+    """Training of one of BASELINE's configs 1-4 through the public trainer API (steady-state epochs,
+    on-device sampler, nb = 100 as in the reference's run scripts)."""
+    import torch
+    import skge
+    from skge.param import AdaGrad, SGD
+    from skge.sample import RandomModeSampler
+    synth = load_synth()
+    g = synth.make_graph(shape, device='cpu')
+    xs = g['train'].numpy()
+    N, M = g['N'], g['M']
+    cls = {'transe': skge.TransE, 'hole': skge.HolE, 'rescal': skge.RESCAL}[model]
+    m = cls((N, N, M), d)
+    m.track_counters = False
+    smp = RandomModeSampler(1, [0, 1], xs, (N, N, M))
+    times = []
+
+    def cb(t):
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t.epoch_start)
+        return True
+    kw = dict(nbatches=100, max_epochs=epochs, learning_rate=0.1, samplef=smp.sample,
+              param_update={'adagrad': AdaGrad, 'sgd': SGD}[upd_name], post_epoch=[cb])
+    trn = skge.PairwiseStochasticTrainer(m, margin=margin, **kw) if pairwise else skge.StochasticTrainer(m, **kw)
+    trn.fit(xs, np.ones(len(xs), dtype=np.float32))
+    med = float(np.median(times[1:]))
+    return {'config': name, 'model': model, 'd': d, 'trainer': 'pairwise' if pairwise else 'logistic',
+            'optimizer': upd_name, 'triples': int(len(xs)), 'value': len(xs) / med, 'unit': 'triples/s',
+            'epoch_ms': 1e3 * med, 'us_per_minibatch': 1e6 * med / 101, 'epochs_timed': len(times) - 1}
+
+
+def bench_extras(pk):
+    out = {'ranking': {}, 'training': {}}
+    for name in ('cfg1', 'cfg2', 'cfg4'):
+        try:
+            out['ranking'][name] = bench_rank_small(name, pk)
+        except Exception as e:
+            out['ranking'][name] = {'error': repr(e)}
+    for name, shape, model, d, pw, upd, margin in (('cfg1', 'wn18', 'transe', 50, True, 'adagrad', 2.0),
+                                                   ('cfg2', 'wn18', 'hole', 150, True, 'adagrad', 0.2),
+                                                   ('cfg3', 'wn18', 'rescal', 100, False, 'sgd', None),
+                                                   ('cfg4', 'fb15k', 'transe', 200, True, 'adagrad', 2.0)):
+        try:
+            out['training'][name] = bench_train_small(name, shape, model, d, pw, upd, margin)
+        except Exception as e:
+            out['training'][name] = {'error': repr(e)}
+    return out
+
+
 def bench_train(args, mdl, N, M, d, model, pk):
     """Fused minibatch steps at config-5 batch size through PairwiseStochasticTrainer.fit."""
     import torch
@@ -385,16 +618,12 @@ def bench_train(args, mdl, N, M, d, model, pk):
     from skge import kernels
     from skge.param import AdaGrad
     from skge.sample import RandomModeSampler
-    from skge.synth import make_graph
+    synth = load_synth()
     dev = mdl.E.data.device
-    B = 500000 if N >= 1000000 else None
+    B = 500000
     nb = args.train_batches
-    T = (B * nb) if B else None
-    if T is None:
-        from skge.synth import SHAPES
-        T = [v for k, v in SHAPES.items() if v[0] == N][0][2]
-        nb = 100
-    g = make_graph((N, M, T, 1, 1), device=dev, seed=99)
+    T = B * nb
+    g = synth.make_graph((N, M, T, 1, 1), device=dev, seed=99)
     xs = g['train'].cpu().numpy()
     smp = RandomModeSampler(1, [0, 1], xs, (N, N, M))
     margin = 0.2 if model == 'hole' else 2.0
@@ -418,7 +647,7 @@ def bench_train(args, mdl, N, M, d, model, pk):
     nv, ue, ur, _ = trn._counts.tolist()
     bytes_batch = 4.0 * d * (4 * P + 4 * (ue + ur)) + 24.0 * P
     ach = bytes_batch / (best / nb) / 1e9
-    # worst-case algorithmic bytes per pair: 4*d*[4P + c(U_E+U_R)], U <= 4P, c = 4
+    ncu = ncu_summary('train_hole_step')
     return {'metric': 'train triples/s', 'value': T / best, 'unit': 'triples/s', 'epoch_s': best,
             'epochs_timed': len(times) - 1, 'model': model, 'd': d, 'batch_positives': T // nb,
             'pairs_per_batch': P, 'nbatches': nb, 'triples': T, 'violations_last_epoch': trn.nviolations,
@@ -427,8 +656,10 @@ def bench_train(args, mdl, N, M, d, model, pk):
             'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
                          'algorithmic_bytes_per_minibatch': bytes_batch, 'minibatch_ms': 1e3 * best / nb,
                          'unique_rows_last_minibatch': [ue, ur], 'violating_pairs_last_minibatch': nv,
-                         'peak_source': pk['src'], 'traffic': None,
-                         'note': 'whole fused step (sampler + pair kernel + sort + segmented update), wall clock per minibatch'},
+                         'peak_source': pk['src'], 'traffic': ncu.get('dram_bytes_per_step') if ncu else None,
+                         'ncu': ncu,
+                         'note': 'whole fused step (sampler + pair kernel + sort + segmented update), wall clock per '
+                                 'minibatch; the per-epoch spectra refresh is inside the timed epoch'},
             'note': 'steady-state epochs through PairwiseStochasticTrainer.fit (first epoch excluded)'}
 
 

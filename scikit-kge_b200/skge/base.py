@@ -307,10 +307,10 @@ class StochasticTrainer(object):
         prepare = getattr(self.model, '_prepare_fused', None)
         for self.epoch in range(1, self.max_epochs + 1):
             self._pre_epoch()
-            if prepare is not None:
-                prepare()       # per-epoch derived state of the model (HolE: spectra of E, R)
-            perm = self._randperm(n).to(torch.int32)
             self.epoch_start = timeit.default_timer()
+            if prepare is not None:
+                prepare()       # per-epoch derived state of the model (HolE: spectra of E, R): part of the epoch
+            perm = self._randperm(n).to(torch.int32)
             for lo, hi in bounds:
                 step(perm[lo:hi])
             self._end_epoch()
