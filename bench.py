@@ -456,6 +456,14 @@ def run_b200(args):
         'roofline': roof,
     }
 
+    # --- CPU baseline: the reference itself on the host cores (subprocess), before the
+    # training leg changes the model's parameters -----------
+    if host is not None:
+        try:
+            line['cpu_baseline'] = cpu_baseline_leg(w, host[0], host[1], host[2], host[3], mdl, Ev)
+        except Exception as e:
+            line['cpu_baseline'] = {'error': repr(e)}
+
     # --- training throughput on 1 GPU (config 5's batch size) ----------------------
     if world == 1 and not args.no_train:
         try:
@@ -469,13 +477,6 @@ def run_b200(args):
             line['extra'] = bench_extras(pk)
         except Exception as e:
             line['extra'] = {'error': repr(e)}
-
-    # --- CPU baseline: the reference itself on the host cores (subprocess) -----------
-    if host is not None:
-        try:
-            line['cpu_baseline'] = cpu_baseline_leg(w, host[0], host[1], host[2], host[3], mdl, Ev)
-        except Exception as e:
-            line['cpu_baseline'] = {'error': repr(e)}
 
     print(json.dumps(line))
     if world > 1:

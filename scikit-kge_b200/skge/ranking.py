@@ -423,7 +423,7 @@ class FilteredRankingEval(object):
     # 0 = choose: 2 for large sweeps (the saved MMA work outweighs the heavier epilogue), else 3
     nsplit = int(os.environ.get('SKGE_RANK_NSPLIT', '0'))
     # nsplit = 2 only: 2 pairs two CTAs on one 256-query x 256-entity MMA (cta_group::2), 1 = one CTA per MMA
-    cta_group = int(os.environ.get('SKGE_RANK_CG', '1'))
+    cta_group = int(os.environ.get('SKGE_RANK_CG', '2'))
     refine_min_pairs = 1 << 33  # queries x shard rows per coarse launch above which nsplit = 2 pays off
 
     def _coarse_engine(self, E, lo, hi, enorm, nqueries=0):
