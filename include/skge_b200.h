@@ -241,6 +241,17 @@ SKGE_API int skge_rank_sweep(int op, const float *Eshard, int64_t n_shard, int64
                     const float *q32, const double *tscore, const float *eps, int64_t Q,
                     int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                     unsigned long long *cand_count, skge_stream_t stream);
+/* The same sweep, Blackwell-staged (skge/run_transe.py:13-29 for TransE; dot models with d > 256):
+ * both operands are first packed by skge_rank_sweep_pack into k-major tiles
+ * [tile of 128 rows][chunk of 16 k][k][row] (skge_rank_sweep_packed_floats(rows, d) floats, zero
+ * padded) so that a pipeline stage is one contiguous bulk-TMA copy per operand; Epk holds rows
+ * [0, n_shard) of the shard, Qpk the fp32 query vectors.  Same outputs as skge_rank_sweep. */
+SKGE_API int64_t skge_rank_sweep_packed_floats(int64_t rows, int d);
+SKGE_API int skge_rank_sweep_pack(const float *src, int64_t rows, int d, float *out, skge_stream_t stream);
+SKGE_API int skge_rank_sweep_tiles(int op, const float *Epk, int64_t n_shard, int64_t shard_base, int d,
+                          const float *Qpk, const double *tscore, const float *eps, int64_t Q,
+                          int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
+                          unsigned long long *cand_count, skge_stream_t stream);
 /* fp64 settlement of (query, entity) pairs: cnt[q] += 1 where
  * score64(q, e) > tscore[q]; pairs with e == target[q] are ignored when
  * target != NULL.  npairs_dev (device, nullable) overrides npairs and is

@@ -53,6 +53,9 @@ SIGNATURES = {
                             + [_P] * 7 + [_P]),
     'skge_rank_make_queries': (_I, [_I, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F] + [_P] * 5 + [_P]),
     'skge_rank_sweep': (_I, [_I, _P, _L, _L, _I, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P]),
+    'skge_rank_sweep_packed_floats': (_L, [_L, _I]),
+    'skge_rank_sweep_pack': (_I, [_P, _L, _I, _P, _P]),
+    'skge_rank_sweep_tiles': (_I, [_I, _P, _L, _L, _I, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P]),
     'skge_rank_rescore': (_I, [_I, _P, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     'skge_rank_scores_one': (_I, [_I, _P, _L, _I, _P, _P, _P]),
     'skge_rank_packed_bytes': (_Z, [_L, _I]),

@@ -13,7 +13,7 @@ _ws = _ext.Workspace()
 # are not counted): bench.py reports the delta over its timed region.
 LAUNCHES = {'n': 0}
 _OWN_KERNELS = {'scores': 1, 'pair': 7, 'logistic_hole': 7, 'logistic_rescal': 13, 'sample': 1, 'set': 1,
-                'make_queries': 1, 'sweep': 1, 'rescore': 1, 'scores_one': 1, 'pack': 1, 'gemm': 1}
+                'make_queries': 1, 'sweep': 1, 'sweep_pack': 1, 'rescore': 1, 'scores_one': 1, 'pack': 1, 'gemm': 1}
 
 
 def _count(what, times=1):
@@ -220,6 +220,22 @@ def rank_sweep(op, Eshard, shard_base, q, cnt_gt, cand_q, cand_e, cand_count):
     check(lib().skge_rank_sweep(op, ptr(Eshard), n_shard, shard_base, d, ptr(q['q32']), ptr(q['tscore']),
                                 ptr(q['eps']), q['q32'].shape[0], ptr(cnt_gt), ptr(cand_q), ptr(cand_e),
                                 cand_q.numel(), ptr(cand_count), stream()))
+
+
+def sweep_pack(X):
+    """fp32 [rows, d] -> the k-major tiles of the bulk-TMA sweep (csrc/rank_sweep.cu)."""
+    rows, d = X.shape
+    out = torch.empty(lib().skge_rank_sweep_packed_floats(rows, d), dtype=torch.float32, device=X.device)
+    _count('sweep_pack')
+    check(lib().skge_rank_sweep_pack(ptr(X), rows, d, ptr(out), stream()))
+    return out
+
+
+def rank_sweep_tiles(op, Epk, n_shard, shard_base, d, q, Qpk, cnt_gt, cand_q, cand_e, cand_count):
+    _count('sweep')
+    check(lib().skge_rank_sweep_tiles(op, ptr(Epk), n_shard, shard_base, d, ptr(Qpk), ptr(q['tscore']), ptr(q['eps']),
+                                      q['q32'].shape[0], ptr(cnt_gt), ptr(cand_q), ptr(cand_e), cand_q.numel(),
+                                      ptr(cand_count), stream()))
 
 
 def rank_rescore(op, Efull, q, pair_q, pair_e, npairs, npairs_dev, target, cnt):
