@@ -58,7 +58,7 @@ def parse():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--train-batches', type=int, default=6)
-    ap.add_argument('--engine', default='auto', choices=['auto', 'sweep', 'umma'])
+    ap.add_argument('--engine', default='auto', choices=['auto', 'sweep', 'umma', 'single'])
     ap.add_argument('--nsplit', type=int, default=0, choices=[0, 1, 2, 3],
                     help='tcgen05 engine: fp16 products on the tensor cores (0 = the evaluator default)')
     # reference arm as the child of the B200 arm's cpu_baseline leg
@@ -495,7 +495,7 @@ def roofline_of(model, stats, kt, ms, pk, full=False):
     if model != 'transe':
         achieved = work / (avg_ms * 1e-3) / 1e12
         nprod = {'tcgen05-f16x3': 3, 'tcgen05-f16x2': 2}.get(eng, 1)
-        kname = 'rank_refine_kernel' if nprod == 2 else 'rank_gemm_kernel'
+        kname = {'tcgen05-f16x2': 'rank_refine_kernel', 'tcgen05-f16x1-refined': 'rank_single_kernel'}.get(eng, 'rank_gemm_kernel')
         ncu = ncu_summary(kname) if full else None
         return {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['tf_sust'], 'traffic': ncu.get('dram_bytes_per_launch') if ncu else None,

@@ -333,6 +333,31 @@ SKGE_API int skge_rank_refine_count(const void *Ehi, const void *Elo8, const voi
                            int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
                            unsigned long long *cand_count, skge_stream_t stream);
 
+/* ---- single-product kernel (csrc/rank_single.cu) -------------------------------------------------
+ * Same contract again with ONE fp16 product on the tensor cores (q_hi . e_hi); both cross terms
+ * (q_hi . e_lo and q_lo . e_hi) are added in the epilogue, from int8 copies of all four vectors, for
+ * the pairs inside the wide band.  The accumulators are pre-loaded with minus the middle of each
+ * query's undecided band, so the scan is a sign count plus a running |.| minimum.  Replaces the
+ * ranking loop of skge/base.py:950-1017 for skge/run_hole.py:15-19 scores on large sweeps.
+ *
+ * skge_rank_quant_rows: fp32 rows (packed order) -> E8[row][2][kb] = int8 of the fp16 lo part, then of the
+ *   fp16 hi part (the split skge_rank_pack_f16 stores for scalar_scale = scale), kb = 64 * ceil(d / 64);
+ *   meta[row] = (scale_lo, ||lo||_1, scale_hi, ||hi||_1) as float4, norms[row] = (||lo||_2, ||hi||_2) as
+ *   float2 (rounded up).  All three arrays have rows padded to a multiple of 256 (zeros).
+ * skge_rank_pack_q8x2: swizzled int8 tiles of the queries' hi and lo parts (layout of skge_rank_pack_q8)
+ *   and qmeta[q][16] = tmid, htight, ||q||, ||q_lo||, sq_hi, sq_lo, qA1, qB1, qA2, qB2, 0...; qmeta must be
+ *   allocated for a multiple of 128 queries.
+ * skge_rank_single_count: tile_w[128-row tile] = (max ||e_lo||_2, max (||e_hi||_2 + ||e_lo||_2)) as float2. */
+SKGE_API int skge_rank_quant_rows(const float *X, int64_t rows, int d, float scale, void *E8, void *meta, void *norms,
+                         skge_stream_t stream);
+SKGE_API int skge_rank_pack_q8x2(const float *q32, const float *qscale, const float *thr_lo, const float *thr_hi,
+                        int64_t Q, int d, void *Q8h, void *Q8l, float *qmeta, skge_stream_t stream);
+SKGE_API int skge_rank_single_count(const void *Ehi, const void *E8, const void *e_meta, const void *tile_w,
+                           const int32_t *perm, int64_t n_shard, int64_t shard_base, const void *Qhi,
+                           const void *Q8h, const void *Q8l, const float *qmeta, int64_t Q, int d, int cta_group,
+                           int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
+                           unsigned long long *cand_count, skge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

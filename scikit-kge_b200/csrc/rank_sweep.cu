@@ -129,7 +129,10 @@ __global__ void __launch_bounds__(THREADS, 2) rank_sweep_tma_kernel(const float 
       if (warp == 0 && chunk + NSTAGE - 1 < nchunks) issue(chunk + NSTAGE - 1);
       mbar_wait(&sm.full[stage], phase);
       const float *pq = sm.q[stage] + 4 * ty, *pe = sm.e[stage] + 4 * tx;
-#pragma unroll
+      // 4 k per loop body: 512 math instructions = 8 KB of code.  The warps of a CTA are not in lockstep
+      // here (no CTA barrier in the loop), so a fully unrolled stage (33 KB) thrashes the instruction
+      // cache: ncu showed 60 % of the stall samples as "no instruction".
+#pragma unroll 4
       for (int k = 0; k < KC; ++k) {
         const float4 qa = *reinterpret_cast<const float4 *>(pq + k * TILE);
         const float4 qb = *reinterpret_cast<const float4 *>(pq + k * TILE + 64);

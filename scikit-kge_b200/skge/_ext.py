@@ -65,6 +65,9 @@ SIGNATURES = {
     'skge_rank_quant_lo': (_I, [_P, _L, _I, _P, _P, _P]),
     'skge_rank_quant_lo_s8': (_I, [_P, _L, _I, _P, _P, _P]),
     'skge_rank_pack_q8': (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
+    'skge_rank_quant_rows': (_I, [_P, _L, _I, _F, _P, _P, _P, _P]),
+    'skge_rank_pack_q8x2': (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P, _P]),
+    'skge_rank_single_count': (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _L, _P, _P]),
     'skge_rank_refine_count': (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _L, _P, _P]),
 }
 

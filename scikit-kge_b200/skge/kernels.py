@@ -329,3 +329,40 @@ def rank_refine_count(Ehi, Elo8, lo_meta, tile_w, perm, n_shard, shard_base, Qhi
                                        shard_base, ptr(Qhi), ptr(Qlo), ptr(Q8), ptr(qmeta), Q, d, cta_group,
                                        ptr(cnt_gt), ptr(cand_q), ptr(cand_e), cand_q.numel(), ptr(cand_count),
                                        stream()))
+
+
+def quant_rows(X, scale):
+    """fp32 rows (packed order) -> (E8 int8 [padded rows, 2, kb], meta float32 [padded rows, 4],
+    norms float32 [padded rows, 2]) for the single-product engine; rows padded to a multiple of 256."""
+    rows, d = X.shape
+    rp = (rows + 255) // 256 * 256
+    kb = (d + 63) // 64 * 64
+    E8 = torch.empty(rp, 2, kb, dtype=torch.int8, device=_ext.device())
+    meta = torch.empty(rp, 4, dtype=torch.float32, device=_ext.device())
+    norms = torch.empty(rp, 2, dtype=torch.float32, device=_ext.device())
+    _count('pack')
+    check(lib().skge_rank_quant_rows(ptr(X), rows, d, float(scale), ptr(E8), ptr(meta), ptr(norms), stream()))
+    return E8, meta, norms
+
+
+def pack_q8x2(q, qscale, tlo, thi):
+    """Swizzled int8 tiles of the queries' hi and lo parts + the per-query constants of the
+    single-product epilogue (16 floats per query, allocated for whole 128-query tiles)."""
+    Q, d = q['q32'].shape
+    kb = (d + 63) // 64 * 64
+    qtiles = (Q + 127) // 128
+    Q8h = torch.empty(qtiles * 128 * kb, dtype=torch.int8, device=_ext.device())
+    Q8l = torch.empty(qtiles * 128 * kb, dtype=torch.int8, device=_ext.device())
+    qmeta = torch.zeros(qtiles * 128, 16, dtype=torch.float32, device=_ext.device())
+    _count('pack')
+    check(lib().skge_rank_pack_q8x2(ptr(q['q32']), ptr(qscale), ptr(tlo), ptr(thi), Q, d, ptr(Q8h), ptr(Q8l),
+                                    ptr(qmeta), stream()))
+    return Q8h, Q8l, qmeta
+
+
+def rank_single_count(Ehi, E8, e_meta, tile_w, perm, n_shard, shard_base, Qhi, Q8h, Q8l, qmeta, Q, d, cta_group,
+                      cnt_gt, cand_q, cand_e, cand_count):
+    _count('gemm')
+    check(lib().skge_rank_single_count(ptr(Ehi), ptr(E8), ptr(e_meta), ptr(tile_w), ptr(perm), n_shard, shard_base,
+                                       ptr(Qhi), ptr(Q8h), ptr(Q8l), ptr(qmeta), Q, d, cta_group, ptr(cnt_gt),
+                                       ptr(cand_q), ptr(cand_e), cand_q.numel(), ptr(cand_count), stream()))

@@ -418,13 +418,18 @@ class FilteredRankingEval(object):
             hit = cache[key] = (pqs, pes, int(pq.numel()))
         return hit
 
-    engine = 'auto'             # 'auto' | 'sweep' (fp32 CUDA cores) | 'umma' (tcgen05, DOT models, d <= 256)
+    # 'auto' | 'sweep' (fp32 CUDA cores) | 'umma' (tcgen05, DOT models, d <= 256; nsplit products) |
+    # 'single' (tcgen05, one product + int8 refinement of both cross terms)
+    engine = 'auto'
     # fp16 hi/lo products on the tensor cores: 3, 2 (third product added in the epilogue), 1 (fp16 only);
     # 0 = choose: 2 for large sweeps (the saved MMA work outweighs the heavier epilogue), else 3
     nsplit = int(os.environ.get('SKGE_RANK_NSPLIT', '0'))
     # nsplit = 2 only: 2 pairs two CTAs on one 256-query x 256-entity MMA (cta_group::2), 1 = one CTA per MMA
     cta_group = int(os.environ.get('SKGE_RANK_CG', '2'))
     refine_min_pairs = 1 << 33  # queries x shard rows per coarse launch above which nsplit = 2 pays off
+    # what 'auto' runs above that size: 'refine' (two products + one refined cross term, csrc/rank_refine.cu)
+    # or 'single' (one product + both cross terms refined, csrc/rank_single.cu)
+    large_sweep_engine = os.environ.get('SKGE_RANK_LARGE', 'refine')
 
     def _coarse_engine(self, E, lo, hi, enorm, nqueries=0):
         """The coarse-pass engine for this shard.  The object (and its candidate
@@ -434,18 +439,23 @@ class FilteredRankingEval(object):
         want = self.engine
         if want == 'auto':
             want = 'umma' if (dot and self.use_tensor_cores and E.shape[1] <= 256) else 'sweep'
-        if want == 'umma' and (not dot or E.shape[1] > 256):
-            raise ValueError('the tcgen05 engine needs a dot-product model with d <= 256')
+        if want in ('umma', 'single') and (not dot or E.shape[1] > 256):
+            raise ValueError('the tcgen05 engines need a dot-product model with d <= 256')
         nsplit = self.nsplit
         if not nsplit:
             nsplit = 3
             if want == 'umma' and nqueries * (hi - lo) >= self.refine_min_pairs:
                 nsplit = 2
-        key = (want, nsplit if want == 'umma' else 0, self.cta_group if want == 'umma' and nsplit == 2 else 0)
+                if self.large_sweep_engine == 'single':
+                    want = 'single'
+        if want == 'single':
+            nsplit = 1
+        key = (want, nsplit if want != 'sweep' else 0, self.cta_group if want == 'single' or nsplit == 2 else 0)
         cache = self.__dict__.setdefault('_engines', {})
         eng = cache.get(key)
         if eng is None:
-            eng = cache[key] = _UmmaEngine(nsplit, self.cta_group) if want == 'umma' else _SweepEngine()
+            eng = cache[key] = (_SweepEngine() if want == 'sweep' else
+                                _UmmaEngine(nsplit, self.cta_group, single=(want == 'single')))
         eng.bind(E, lo, hi)
         return eng
 
@@ -587,12 +597,19 @@ class _UmmaEngine(_SweepEngine):
     name = 'tcgen05-f16x3'
     cands_per_query = 160
 
-    def __init__(self, nsplit=3, cta_group=1):
+    def __init__(self, nsplit=3, cta_group=1, single=False):
         super(_UmmaEngine, self).__init__()
         self.nsplit = nsplit
         self.cta_group = cta_group
+        self.single = single
         self.name = 'tcgen05-f16x%d' % nsplit
         self.dtype = 'f16x%d split (tcgen05, fp32 accumulate) + f64 settle' % nsplit
+        if single:
+            self.name = 'tcgen05-f16x1-refined'
+            self.dtype = 'f16 (tcgen05, fp32 accumulate) + int8 dp4a refinement of both cross terms + f64 settle'
+            self.cands_per_query = 320
+            self._shadow_key = None
+            return
         if nsplit == 2:
             self.dtype = 'f16x2 split (tcgen05, fp32 accumulate) + int8 dp4a refinement + f64 settle'
             self.cands_per_query = 256
@@ -613,7 +630,19 @@ class _UmmaEngine(_SweepEngine):
         self._shadow_key = None
         emax = float(self.shard.abs().max().item())
         self.escale = 2.0 ** (12 - math.ceil(math.log2(emax))) if emax > 0 else 1.0
-        if self.nsplit == 2:
+        if self.single:
+            # packed by decreasing row norm like nsplit = 2 (see below); int8 copies of the lo AND hi parts
+            rn = torch.linalg.vector_norm(self.shard, dim=1)
+            self.perm = torch.argsort(rn, descending=True).to(torch.int32)
+            ordered = self.shard.index_select(0, self.perm.to(torch.int64))
+            self.Ehi, _ = kernels.pack_f16(ordered, None, self.escale, even_tiles=True)
+            self.E8, self.e_meta, norms = kernels.quant_rows(ordered, self.escale)
+            del ordered, _
+            nl, nh = norms[:, 0].reshape(-1, 128), norms[:, 1].reshape(-1, 128)
+            wl = nl.max(dim=1).values * 1.001
+            wh = (nh + nl).max(dim=1).values * 1.001
+            self.tile_w = torch.stack([wl, wh], 1).contiguous()
+        elif self.nsplit == 2:
             # The epilogue gathers lo rows and widens the band of a 128-row entity tile by
             # ||q|| * max ||e_lo|| over the tile.  Counting does not care about the order of the
             # entities, so the shard is packed by decreasing row norm: the rows of a tile are then
@@ -641,14 +670,20 @@ class _UmmaEngine(_SweepEngine):
         # nsplit = 1 keeps only hi*hi: fp16 rounding of both operands, 2^-10 worst case.
         # nsplit = 2 adds the third product in the epilogue from int8 copies of both operands; the
         # quantisation error of that term is bounded per pair and added to that pair's band there.
-        return 2.0 ** -9 if self.nsplit == 1 else 2.0 ** -17
+        return 2.0 ** -9 if (self.nsplit == 1 and not self.single) else 2.0 ** -17
 
     def _coarse(self, op, q, cnt_gt):
         Q, d = q['q32'].shape
         qscale, tlo, thi = kernels.query_scale(q, self.escale)
         Qhi, Qlo = kernels.pack_f16(q['q32'], qscale, 1.0)
         work = 2.0 * (self.hi - self.lo) * d * Q
-        if self.nsplit == 2:
+        if self.single:
+            Q8h, Q8l, qmeta = kernels.pack_q8x2(q, qscale, tlo, thi)
+            self._timed(lambda: kernels.rank_single_count(self.Ehi, self.E8, self.e_meta, self.tile_w, self.perm,
+                                                          self.hi - self.lo, self.lo, Qhi, Q8h, Q8l, qmeta, Q, d,
+                                                          self.cta_group, cnt_gt, self.cand_q, self.cand_e,
+                                                          self.count), work)
+        elif self.nsplit == 2:
             Q8, qmeta = kernels.pack_q8(q, qscale, tlo, thi)
             self._timed(lambda: kernels.rank_refine_count(self.Ehi, self.Elo8, self.lo_meta, self.tile_w, self.perm,
                                                           self.hi - self.lo, self.lo, Qhi, Qlo, Q8, qmeta, Q, d,

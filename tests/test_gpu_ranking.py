@@ -12,6 +12,19 @@ pytestmark = pytest.mark.gpu
 # CTA groupings of the refine kernel under test (SKGE_TEST_CG=1 isolates the single-CTA kernel)
 import os
 CGS = [int(x) for x in os.environ.get('SKGE_TEST_CG', '1,2').split(',')]
+# large-sweep engines: 'refine' = two tensor-core products + one refined cross term (csrc/rank_refine.cu),
+# 'single' = one product + both cross terms refined (csrc/rank_single.cu)
+MODES = os.environ.get('SKGE_TEST_MODES', 'refine,single').split(',')
+
+
+def _set_engine(ev, mode, cg):
+    """Selects a large-sweep engine on the evaluator; returns the engine name last_stats must report."""
+    ev.cta_group = cg
+    if mode == 'single':
+        ev.engine, ev.nsplit = 'single', 0
+        return 'tcgen05-f16x1-refined'
+    ev.engine, ev.nsplit = 'umma', 2
+    return 'tcgen05-f16x2'
 
 
 def _flat(d, rel, side):
@@ -70,16 +83,17 @@ def test_appendix_a4_untied_ranks(golden):
                         assert fpos[p][side][i] == int(g['a4_%s_fpos_%d_%s' % (tag, p, side)][i])
 
 
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('cg', CGS)
-def test_refine_engine_matches_reference_golden(golden, cg):
+def test_refine_engine_matches_reference_golden(golden, cg, mode):
     """The engine bench.py times (two tensor-core products + int8 refinement, both CTA groupings)
     on the reference's own ranks (skge/base.py:913-1031 run through oracle/make_golden.py)."""
     g = golden('rank_hole')
     m = _model('hole', g['E0'], g['R0'])
     ev = _evaluator('hole')([tuple(t) for t in g['test'].tolist()], [tuple(t) for t in g['true'].tolist()])
-    ev.engine, ev.nsplit, ev.cta_group = 'umma', 2, cg
+    name = _set_engine(ev, mode, cg)
     pos, fpos = ev.positions(m)
-    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert ev.last_stats['engine'] == name
     assert list(pos.keys()) == [int(p) for p in g['rel']]
     for side in ('head', 'tail'):
         np.testing.assert_array_equal(_flat(pos, g['rel'], side), g['pos_' + side])
@@ -89,7 +103,8 @@ def test_refine_engine_matches_reference_golden(golden, cg):
 @pytest.mark.parametrize('cg', CGS)
 @pytest.mark.parametrize('kind,N,d', [('hole', 1500, 150), ('hole', 900, 256), ('rescal', 800, 100), ('hole', 333, 37),
                                       ('hole', 129, 64), ('hole', 2100, 200)])
-def test_refine_engine_matches_oracle_on_random_graphs(kind, N, d, cg):
+@pytest.mark.parametrize('mode', MODES)
+def test_refine_engine_matches_oracle_on_random_graphs(kind, N, d, cg, mode):
     """Same cases as the three-product engine: ragged query chunks, ragged entity tiles, odd and
     even numbers of 64-wide k chunks (the int8 query rows are swizzled only for even counts)."""
     M = 5
@@ -100,9 +115,9 @@ def test_refine_engine_matches_oracle_on_random_graphs(kind, N, d, cg):
     m = _model(kind, E0, R0)
     ev = _evaluator(kind)(test, true)
     ev.chunk_queries = 128
-    ev.engine, ev.nsplit, ev.cta_group = 'umma', 2, cg
+    name = _set_engine(ev, mode, cg)
     pos, fpos = ev.positions(m)
-    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert ev.last_stats['engine'] == name
     opos, ofpos, margins = orc.rank_positions(kind, E0, R0, test, true, tie='argsort', with_scores=True)
     assert list(pos.keys()) == list(opos.keys())
     nt = 0
@@ -116,8 +131,9 @@ def test_refine_engine_matches_oracle_on_random_graphs(kind, N, d, cg):
     assert nt >= 290
 
 
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('cg', CGS)
-def test_refine_engine_on_a_million_entities(cg):
+def test_refine_engine_on_a_million_entities(cg, mode):
     """A 1 M-entity x 2 k-query slice of the benchmarked workload (HolE d = 256): the refine
     engine's counts equal the fp32 sweep engine's bit for bit, and so do 2 emulated shards."""
     N, M, d, te = 1000000, 1000, 256, 1000
@@ -132,9 +148,9 @@ def test_refine_engine_on_a_million_entities(cg):
     ev = _evaluator('hole')(test, true)
     ev.engine = 'sweep'
     ref = ev.count_pass(m)
-    ev.engine, ev.nsplit, ev.cta_group = 'umma', 2, cg
+    name = _set_engine(ev, mode, cg)
     got = ev.count_pass(m)
-    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert ev.last_stats['engine'] == name
     assert torch.equal(got, ref)
     parts = sum(ev.count_pass(m, world=(r, 2)) for r in range(2))
     assert torch.equal(parts, ref)
@@ -223,8 +239,9 @@ def test_tensor_core_engine_counts_equal_the_fp32_engine(N, d, te, cg):
 
 
 @pytest.mark.parametrize('cg', CGS)
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('N,d', [(7777, 256), (3001, 96)])
-def test_refine_mode_with_mixed_row_norms(N, d, cg):
+def test_refine_mode_with_mixed_row_norms(N, d, cg, mode):
     """nsplit = 2 packs the shard by decreasing row norm and widens the band per 128-row tile.
     Rows spanning a factor 50 in norm, a ragged last tile and emulated shards must still give the
     fp32 engine's counts bit for bit, with candidates reported under their original ids."""
@@ -236,11 +253,9 @@ def test_refine_mode_with_mixed_row_norms(N, d, cg):
     ev = _evaluator('hole')(test, true)
     ev.engine = 'sweep'
     ref = ev.count_pass(m)
-    ev.engine = 'umma'
-    ev.nsplit = 2
-    ev.cta_group = cg
+    name = _set_engine(ev, mode, cg)
     got = ev.count_pass(m)
-    assert ev.last_stats['engine'] == 'tcgen05-f16x2'
+    assert ev.last_stats['engine'] == name
     assert torch.equal(got, ref)
     parts = sum(ev.count_pass(m, world=(r, 3)) for r in range(3))
     assert torch.equal(parts, ref)
