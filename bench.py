@@ -508,10 +508,10 @@ def roofline_of(model, stats, kt, ms, pk, full=False):
     issue_peak = 148 * 128 * pk['sm_max_mhz'] * 1e6
     achieved = work / (avg_ms * 1e-3)
     return {'bound': 'fp32-issue', 'achieved': achieved / 1e12, 'peak': issue_peak / 1e12, 'unit': 'T lane-instr/s',
-            'frac': achieved / issue_peak, 'traffic': None, 'kernel': 'rank_sweep_kernel', 'engine': eng,
+            'frac': achieved / issue_peak, 'traffic': None, 'kernel': 'rank_sweep_tma_kernel', 'engine': eng,
             'launch_ms': avg_ms, 'launches_timed': len(kt),
             'peak_source': '148 SMs x 128 FP32 lanes x %.0f MHz (max SM clock)' % pk['sm_max_mhz'],
-            'note': 'the table is read from L2 / shared memory once per 128-query tile, so the sweep is bound by '
+            'note': 'k-major packed tiles staged by bulk TMA; the table is read from L2 once per 128-query tile, so the sweep is bound by '
                     'instruction issue (one FADD + one FADD.abs per element), not by HBM',
             'algorithmic_lane_instructions_per_launch': work, 'kernel_share_of_step': share}
 

@@ -233,19 +233,13 @@ SKGE_API int skge_rank_make_queries(int model, const float *E, const float *RW, 
                            int64_t Q, int d, float enorm_max, float coarse_rel, double *q64,
                            float *q32, double *tscore, float *eps, float *qnorm,
                            skge_stream_t stream);
-/* CUDA-core coarse sweep in fp32 over rows [0, n_shard) of Eshard (global ids
- * shard_base + row).  cnt_gt[Q] += definite wins; candidates appended at
- * *cand_count (device, atomically); entries beyond cand_cap are dropped but
- * still counted, so the caller can detect overflow. */
-SKGE_API int skge_rank_sweep(int op, const float *Eshard, int64_t n_shard, int64_t shard_base, int d,
-                    const float *q32, const double *tscore, const float *eps, int64_t Q,
-                    int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
-                    unsigned long long *cand_count, skge_stream_t stream);
-/* The same sweep, Blackwell-staged (skge/run_transe.py:13-29 for TransE; dot models with d > 256):
- * both operands are first packed by skge_rank_sweep_pack into k-major tiles
- * [tile of 128 rows][chunk of 16 k][k][row] (skge_rank_sweep_packed_floats(rows, d) floats, zero
- * padded) so that a pipeline stage is one contiguous bulk-TMA copy per operand; Epk holds rows
- * [0, n_shard) of the shard, Qpk the fp32 query vectors.  Same outputs as skge_rank_sweep. */
+/* CUDA-core coarse sweep in fp32 (skge/run_transe.py:13-29 for TransE, always L1; dot models with
+ * d > 256) over rows [0, n_shard) of a shard (global ids shard_base + row).  Both operands are first
+ * packed by skge_rank_sweep_pack into k-major tiles [tile of 128 rows][chunk of 16 k][k][row]
+ * (skge_rank_sweep_packed_floats(rows, d) floats, zero padded) so that a pipeline stage is one
+ * contiguous bulk-TMA copy per operand; Epk holds the shard's rows, Qpk the fp32 query vectors.
+ * cnt_gt[Q] += definite wins; candidates appended at *cand_count (device, atomically); entries
+ * beyond cand_cap are dropped but still counted, so the caller can detect overflow. */
 SKGE_API int64_t skge_rank_sweep_packed_floats(int64_t rows, int d);
 SKGE_API int skge_rank_sweep_pack(const float *src, int64_t rows, int d, float *out, skge_stream_t stream);
 SKGE_API int skge_rank_sweep_tiles(int op, const float *Epk, int64_t n_shard, int64_t shard_base, int d,

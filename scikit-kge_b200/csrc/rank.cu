@@ -1,5 +1,5 @@
-// Filtered ranking: query construction, fp32 coarse sweep with an undecided
-// band, fp64 settlement of band candidates and filter entries.
+// Filtered ranking: query construction and the fp64 settlement of band candidates and
+// filter entries (the coarse passes live in rank_sweep.cu, rank_umma.cu, rank_refine.cu, rank_single.cu).
 //   FilteredRankingEval.positions : skge/base.py:913-1031
 //   TransEEval                    : skge/run_transe.py:13-29 (always L1)
 //   HolEEval                      : skge/run_hole.py:10-19
@@ -225,175 +225,7 @@ __global__ void __launch_bounds__(256) make_queries_hole_kernel(const float *__r
 #undef HP
 }
 
-// ---------------------------------------------------------------------------
-// coarse sweep on the FP32 pipes
-// ---------------------------------------------------------------------------
-// (Both sweeps need two instructions per (query, entity, k) element -- FADD + FADD|.| or one FFMA
-// with three register operands at half rate -- so they are bound by instruction issue at 64
-// elements / clk / SM.  Rewriting |q - e| as 2 max(q, e) - q - e to move half of the work to the
-// alu pipe (FMNMX) was measured: same time, since the issue slot, not a pipe, is the limit.)
-// 128 queries x 128 entities per CTA step, k staged in chunks of KC through
-// double-buffered shared memory (cp.async), 8x8 accumulators per thread.  Rows
-// are stored with a stride of KC+4 floats so that the 128-bit reads of eight
-// consecutive rows hit disjoint banks.
-static constexpr int BQ = 128, BE = 128, KC = 16, KS = KC + 4;
-
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool pred) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(dst);
-  int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src, bool pred) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(dst);
-  int sz = pred ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// Stage rows [row0, row0+128) x k in [k0, k0+KC) of a row-major [nrows][d] table.
-template <bool VEC4>
-__device__ __forceinline__ void stage_tile(float *dst, const float *__restrict__ src, int64_t row0,
-                                           int64_t nrows, int d, int k0) {
-  if (VEC4) {
-    // 128 rows x 4 float4
-    for (int t = threadIdx.x; t < 128 * (KC / 4); t += blockDim.x) {
-      int r = t >> 2, c = (t & 3) * 4;
-      int64_t row = row0 + r;
-      bool ok = row < nrows && k0 + c < d;  // d % 4 == 0: a float4 is all-in or all-out
-      const float *g = src + (ok ? row * d + k0 + c : 0);
-      cp_async16(dst + r * KS + c, g, ok);
-    }
-  } else {
-    for (int t = threadIdx.x; t < 128 * KC; t += blockDim.x) {
-      int r = t / KC, c = t % KC;
-      int64_t row = row0 + r;
-      bool ok = row < nrows && k0 + c < d;
-      const float *g = src + (ok ? row * d + k0 + c : 0);
-      cp_async4(dst + r * KS + c, g, ok);
-    }
-  }
-}
-
-template <int OP, bool VEC4>
-__global__ void __launch_bounds__(256, 2) rank_sweep_kernel(const float *__restrict__ Eshard, int64_t n_shard,
-                                                         int64_t shard_base, int d,
-                                                         const float *__restrict__ q32,
-                                                         const double *__restrict__ tscore,
-                                                         const float *__restrict__ eps, int64_t Q,
-                                                         int32_t *__restrict__ cnt_gt,
-                                                         int32_t *__restrict__ cand_q,
-                                                         int32_t *__restrict__ cand_e, int64_t cand_cap,
-                                                         unsigned long long *__restrict__ cand_count,
-                                                         int etiles_per_cta) {
-  __shared__ __align__(16) float sq[2][BQ * KS];
-  __shared__ __align__(16) float se[2][BE * KS];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int64_t q0 = (int64_t)blockIdx.x * BQ;
-  const int64_t ntiles_e = (n_shard + BE - 1) / BE;
-  const int64_t et_beg = (int64_t)blockIdx.y * etiles_per_cta;
-  int64_t et_end = et_beg + etiles_per_cta;
-  if (et_end > ntiles_e) et_end = ntiles_e;
-  const int nk = (d + KC - 1) / KC;
-
-  float thi[8], tlo[8];
-  int cnt[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int64_t q = q0 + ty + 16 * i;
-    cnt[i] = 0;
-    if (q < Q) {
-      double t = tscore[q], e = (double)eps[q];
-      thi[i] = __double2float_ru(t + e);
-      tlo[i] = __double2float_rd(t - e);
-    } else {
-      thi[i] = INFINITY;   // never counted, never in band
-      tlo[i] = INFINITY;
-    }
-  }
-
-  for (int64_t et = et_beg; et < et_end; ++et) {
-    const int64_t e0 = et * BE;
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    __syncthreads();
-    stage_tile<VEC4>(sq[0], q32, q0, Q, d, 0);
-    stage_tile<VEC4>(se[0], Eshard, e0, n_shard, d, 0);
-    cp_async_commit();
-    for (int kc = 0; kc < nk; ++kc) {
-      int cur = kc & 1;
-      if (kc + 1 < nk) {
-        stage_tile<VEC4>(sq[cur ^ 1], q32, q0, Q, d, (kc + 1) * KC);
-        stage_tile<VEC4>(se[cur ^ 1], Eshard, e0, n_shard, d, (kc + 1) * KC);
-        cp_async_commit();
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-      const float *pq = sq[cur], *pe = se[cur];
-#pragma unroll
-      for (int k4 = 0; k4 < KC; k4 += 4) {
-        float4 qv[8], ev[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qv[i] = *reinterpret_cast<const float4 *>(pq + (ty + 16 * i) * KS + k4);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ev[j] = *reinterpret_cast<const float4 *>(pe + (tx + 16 * j) * KS + k4);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (OP == SKGE_RANK_L1) {
-              acc[i][j] += fabsf(qv[i].x - ev[j].x);
-              acc[i][j] += fabsf(qv[i].y - ev[j].y);
-              acc[i][j] += fabsf(qv[i].z - ev[j].z);
-              acc[i][j] += fabsf(qv[i].w - ev[j].w);
-            } else {
-              acc[i][j] = fmaf(qv[i].x, ev[j].x, acc[i][j]);
-              acc[i][j] = fmaf(qv[i].y, ev[j].y, acc[i][j]);
-              acc[i][j] = fmaf(qv[i].z, ev[j].z, acc[i][j]);
-              acc[i][j] = fmaf(qv[i].w, ev[j].w, acc[i][j]);
-            }
-          }
-      }
-      __syncthreads();
-    }
-    // epilogue: compare against the per-query thresholds; never store a score
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int64_t e = e0 + tx + 16 * j;
-      if (e >= n_shard) continue;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float s = OP == SKGE_RANK_L1 ? -acc[i][j] : acc[i][j];
-        if (s > thi[i]) {
-          ++cnt[i];
-        } else if (s >= tlo[i]) {
-          unsigned long long slot = atomicAdd(cand_count, 1ull);
-          if ((int64_t)slot < cand_cap) {
-            cand_q[slot] = (int32_t)(q0 + ty + 16 * i);
-            cand_e[slot] = (int32_t)(shard_base + e);
-          }
-        }
-      }
-    }
-  }
-  // the 16 threads sharing ty sit in one half-warp: reduce, then one atomic per query
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int c = cnt[i];
-    c += __shfl_xor_sync(kFull, c, 8);
-    c += __shfl_xor_sync(kFull, c, 4);
-    c += __shfl_xor_sync(kFull, c, 2);
-    c += __shfl_xor_sync(kFull, c, 1);
-    int64_t q = q0 + ty + 16 * i;
-    if (tx == 0 && q < Q && c) atomicAdd(cnt_gt + q, c);
-  }
-}
+// (The fp32 coarse sweep lives in rank_sweep.cu.)
 
 // ---------------------------------------------------------------------------
 // fp64 settlement
@@ -535,43 +367,6 @@ int skge_rank_make_queries(int model, const float *E, const float *RW, const uin
   size_t smem = 2 * (size_t)d * sizeof(double);
   make_queries_kernel<<<(int)blocks, threads, smem, as_stream(stream)>>>(
       model, E, RW, kind, given, rel, target, Q, d, enorm_max, coarse_rel, q64, q32, tscore, eps, qnorm);
-  SKGE_LAUNCH_CHECK();
-  return 0;
-}
-
-int skge_rank_sweep(int op, const float *Eshard, int64_t n_shard, int64_t shard_base, int d,
-                    const float *q32, const double *tscore, const float *eps, int64_t Q,
-                    int32_t *cnt_gt, int32_t *cand_q, int32_t *cand_e, int64_t cand_cap,
-                    unsigned long long *cand_count, skge_stream_t stream) {
-  SKGE_REQUIRE(Eshard && q32 && tscore && eps && cnt_gt && cand_q && cand_e && cand_count, "null argument");
-  SKGE_REQUIRE((op == SKGE_RANK_L1 || op == SKGE_RANK_DOT) && d > 0 && n_shard >= 0 && Q >= 0, "bad sizes");
-  if (Q == 0 || n_shard == 0) return 0;
-  int64_t qtiles = (Q + BQ - 1) / BQ, etiles = (n_shard + BE - 1) / BE;
-  // Split the entity range so that the CTAs fill whole waves of the GPU (2 resident CTAs per SM):
-  // a 128-query tile against the whole shard is a long CTA, and a ragged last wave costs up to
-  // a full CTA time.  Take the smallest split whose wave efficiency is >= 97 %, else the best.
-  const int64_t slots = 2 * kNumSMs;
-  int64_t ysplit = 1;
-  int per = (int)etiles;
-  double best = -1.0;
-  for (int64_t ys = 1; ys <= etiles && ys <= 64; ++ys) {
-    const int64_t p = (etiles + ys - 1) / ys, yeff = (etiles + p - 1) / p;
-    if (yeff != ys) continue;  // same partition as a smaller split
-    const int64_t total = qtiles * ys, waves = (total + slots - 1) / slots;
-    // work is counted in entity tiles: the last slice of the split may be shorter than `per`
-    const double eff = (double)(qtiles * etiles) / ((double)waves * slots * p);
-    if (eff > best + 1e-9) { best = eff; ysplit = ys; per = (int)p; }
-    if (eff >= 0.97) break;
-  }
-  dim3 grid((unsigned)qtiles, (unsigned)ysplit);
-  cudaStream_t st = as_stream(stream);
-  bool v4 = d % 4 == 0;
-#define SKGE_SWEEP(OP, V)                                                                              \
-  rank_sweep_kernel<OP, V><<<grid, 256, 0, st>>>(Eshard, n_shard, shard_base, d, q32, tscore, eps, Q, \
-                                                 cnt_gt, cand_q, cand_e, cand_cap, cand_count, per)
-  if (op == SKGE_RANK_L1) { if (v4) SKGE_SWEEP(SKGE_RANK_L1, true); else SKGE_SWEEP(SKGE_RANK_L1, false); }
-  else { if (v4) SKGE_SWEEP(SKGE_RANK_DOT, true); else SKGE_SWEEP(SKGE_RANK_DOT, false); }
-#undef SKGE_SWEEP
   SKGE_LAUNCH_CHECK();
   return 0;
 }

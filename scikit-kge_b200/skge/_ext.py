@@ -52,7 +52,6 @@ SIGNATURES = {
     'skge_sample_corrupt': (_I, [_P, _Z, _P, _Z, _P, _P, _P, _P, _L, _I, _I, _L, _L, _I, _U64, _U64, _P]
                             + [_P] * 7 + [_P]),
     'skge_rank_make_queries': (_I, [_I, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F] + [_P] * 5 + [_P]),
-    'skge_rank_sweep': (_I, [_I, _P, _L, _L, _I, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P]),
     'skge_rank_sweep_packed_floats': (_L, [_L, _I]),
     'skge_rank_sweep_pack': (_I, [_P, _L, _I, _P, _P]),
     'skge_rank_sweep_tiles': (_I, [_I, _P, _L, _L, _I, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P]),

@@ -214,14 +214,6 @@ def make_queries(model, E, RW, kind, given, rel, target, enorm_max, coarse_rel):
     return dict(q64=q64, q32=q32, tscore=tscore, eps=eps, qnorm=qnorm)
 
 
-def rank_sweep(op, Eshard, shard_base, q, cnt_gt, cand_q, cand_e, cand_count):
-    n_shard, d = Eshard.shape
-    _count('sweep')
-    check(lib().skge_rank_sweep(op, ptr(Eshard), n_shard, shard_base, d, ptr(q['q32']), ptr(q['tscore']),
-                                ptr(q['eps']), q['q32'].shape[0], ptr(cnt_gt), ptr(cand_q), ptr(cand_e),
-                                cand_q.numel(), ptr(cand_count), stream()))
-
-
 def sweep_pack(X):
     """fp32 [rows, d] -> the k-major tiles of the bulk-TMA sweep (csrc/rank_sweep.cu)."""
     rows, d = X.shape

@@ -508,10 +508,6 @@ class _SweepEngine(object):
         self.cand_q = self.cand_e = self.count = None
         self._counts = []
 
-    # 'tma': operands packed into k-major tiles, bulk-TMA staged (csrc/rank_sweep.cu);
-    # 'cp.async': the round-1 kernel (csrc/rank.cu), kept for A/B checks
-    staging = os.environ.get('SKGE_SWEEP_STAGING', 'tma')
-
     def bind(self, E, lo, hi):
         self.E = E
         self.lo, self.hi = lo, hi
@@ -519,8 +515,8 @@ class _SweepEngine(object):
         if self.count is None or self.count.device != E.device:
             self.count = torch.zeros(1, dtype=torch.int64, device=E.device)
             self.cap = 0
-        if type(self) is _SweepEngine and self.staging == 'tma' and hi > lo:
-            # the packed copy of the shard is rebuilt only when the table's checksum changes
+        if type(self) is _SweepEngine and hi > lo:
+            # the k-major packed copy (csrc/rank_sweep.cu) of the shard is rebuilt only when the table's checksum changes
             whole = lo == 0 and hi == E.shape[0]
             chk = _table_stats(E)['chk'] if whole else int(torch.sum(self.shard.view(torch.int32),
                                                                      dtype=torch.int64).item())
@@ -557,13 +553,9 @@ class _SweepEngine(object):
     def _coarse(self, op, q, cnt_gt):
         d = self.E.shape[1]
         work = 2.0 * (self.hi - self.lo) * d * q['q32'].shape[0]
-        if self.staging == 'tma':
-            Qpk = kernels.sweep_pack(q['q32'])
-            self._timed(lambda: kernels.rank_sweep_tiles(op, self.Epk, self.hi - self.lo, self.lo, d, q, Qpk, cnt_gt,
-                                                         self.cand_q, self.cand_e, self.count), work)
-        else:
-            self._timed(lambda: kernels.rank_sweep(op, self.shard, self.lo, q, cnt_gt, self.cand_q, self.cand_e,
-                                                   self.count), work)
+        Qpk = kernels.sweep_pack(q['q32'])
+        self._timed(lambda: kernels.rank_sweep_tiles(op, self.Epk, self.hi - self.lo, self.lo, d, q, Qpk, cnt_gt,
+                                                     self.cand_q, self.cand_e, self.count), work)
 
     def begin_pass(self):
         self._counts = []
