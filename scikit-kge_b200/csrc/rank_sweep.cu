@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TILE) sweep_pack_kernel(const float *__restric
 
 template <int OP>
 __global__ void __launch_bounds__(THREADS, 2) rank_sweep_tma_kernel(const float *__restrict__ Epk, int64_t n_shard,
-                                                                    int64_t shard_base, int nch,
+                                                                    int64_t shard_base, int d, int nch,
                                                                     const float *__restrict__ Qpk,
                                                                     const double *__restrict__ tscore,
                                                                     const float *__restrict__ eps, int64_t Q,
@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(THREADS, 2) rank_sweep_tma_kernel(const float 
   if (warp == 0)
     for (int64_t i = 0; i < NSTAGE - 1 && i < nchunks; ++i) issue(i);
 
+  const int klast = ((d - (nch - 1) * KC) + 3) & ~3;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // entity rows 4 tx.., query rows 4 ty..
   uint32_t stage = 0, phase = 0;
   int cnt[8];
@@ -132,8 +133,9 @@ __global__ void __launch_bounds__(THREADS, 2) rank_sweep_tma_kernel(const float 
       // 4 k per loop body: 512 math instructions = 8 KB of code.  The warps of a CTA are not in lockstep
       // here (no CTA barrier in the loop), so a fully unrolled stage (33 KB) thrashes the instruction
       // cache: ncu showed 60 % of the stall samples as "no instruction".
+      const int kend = c == nch - 1 ? klast : KC;   // the zero padding of the last chunk is skipped (4 k granularity)
 #pragma unroll 4
-      for (int k = 0; k < KC; ++k) {
+      for (int k = 0; k < kend; ++k) {
         const float4 qa = *reinterpret_cast<const float4 *>(pq + k * TILE);
         const float4 qb = *reinterpret_cast<const float4 *>(pq + k * TILE + 64);
         const float4 ea = *reinterpret_cast<const float4 *>(pe + k * TILE);
@@ -243,13 +245,13 @@ int skge_rank_sweep_tiles(int op, const float *Epk, int64_t n_shard, int64_t sha
   if (op == SKGE_RANK_L1) {
     SKGE_CUDA(cudaFuncSetAttribute(rank_sweep_tma_kernel<SKGE_RANK_L1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    rank_sweep_tma_kernel<SKGE_RANK_L1><<<grid, THREADS, smem, st>>>(Epk, n_shard, shard_base, nch, Qpk, tscore, eps,
-                                                                    Q, cnt_gt, cand_q, cand_e, cand_cap, cand_count,
+    rank_sweep_tma_kernel<SKGE_RANK_L1><<<grid, THREADS, smem, st>>>(Epk, n_shard, shard_base, d, nch, Qpk, tscore,
+                                                                    eps, Q, cnt_gt, cand_q, cand_e, cand_cap, cand_count,
                                                                     per);
   } else {
     SKGE_CUDA(cudaFuncSetAttribute(rank_sweep_tma_kernel<SKGE_RANK_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    rank_sweep_tma_kernel<SKGE_RANK_DOT><<<grid, THREADS, smem, st>>>(Epk, n_shard, shard_base, nch, Qpk, tscore,
+    rank_sweep_tma_kernel<SKGE_RANK_DOT><<<grid, THREADS, smem, st>>>(Epk, n_shard, shard_base, d, nch, Qpk, tscore,
                                                                      eps, Q, cnt_gt, cand_q, cand_e, cand_cap,
                                                                      cand_count, per);
   }
