@@ -116,10 +116,10 @@ __device__ __forceinline__ void copy8(uint32_t (&v)[8], uint32_t x) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int CG>
+template <int CG, int KCH>
 __global__ void __launch_bounds__(THREADS, 1) rank_single_kernel(const SingleArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int kch = a.kch, kb = kch * 64;
+  constexpr int kch = KCH, kb = KCH * 64;   // compile-time row length: the refinement's addressing folds into immediates
   uint8_t *sA_hi = smem_raw;
   uint8_t *sQ8h = sA_hi + kch * BLOCK_BYTES;
   uint8_t *sQ8l = sQ8h + QT * kb;
@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(THREADS, 1) rank_single_kernel(const SingleArg
     const int colhalf = quad & 1;                    // which 128 of the stage's 256 columns
     const int row = quarter * 32 + lane;             // query row inside the tile
     const int slot = lane & 7, part = lane >> 3;     // refinement: four lanes per pair
-    const bool swz = (kch & 1) == 0;
+    constexpr bool swz = (KCH & 1) == 0;
+    // bank group of the swizzled shared-memory reads: distinct over the 8 slots of a quarter-warp
+    const int pi[2] = {(slot + part) & 7, (slot + part + 4) & 7};
     constexpr uint32_t EPI_SLEEP = 128u;   // ns between polls of a waiting epilogue warp
     const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + st * ET + colhalf * 128;
 
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_single_kernel(const SingleArg
         const float h = __fmaf_ru(qlon, tw.y, __fmaf_ru(qn, tw.x, htight));
         mbar_wait_sleep<EPI_SLEEP>(&ctrl->acc_full[st], (my >> 1) & 1u);
         tc_fence_after();
+        int nlist = 0;
         for (int c2 = 0; c2 < 4; ++c2) {
           uint32_t r[32];
           tmem_ld32(taddr + 32 * c2, r);
@@ -396,76 +399,75 @@ __global__ void __launch_bounds__(THREADS, 1) rank_single_kernel(const SingleArg
             cnt += __popc(mpos & vm);
             band &= vm;
           }
-          while (band) {   // inside the WIDE band: needs the two missing products
-            const int j = __ffs(band) - 1;
-            band &= band - 1;
-            const uint32_t bits = pick32(r, j);
-            const int idx = atomicAdd(&wl->count[w16], 1);
-            if (idx < LIST_CAP) {
-              wl->ent[w16][idx] = make_uint2(bits, (uint32_t)((lane << 8) | (c2 * 32 + j)));
-            } else {
-              // list full (rare): the fp64 pass settles this pair; it was counted if its sign bit is clear
-              if ((bits >> 31) == 0u) --cnt;
-              push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + c2 * 32 + j)));
+          // Wide-band elements -> the warp's list.  Slots come from a warp prefix sum of the per-lane
+          // counts (no shared-memory atomics in the dependent chain); nlist is warp-uniform.
+          const uint32_t hit = __ballot_sync(kFull, band != 0u);
+          if (hit) {
+            const int mine_n = __popc(band);
+            int pre_n = mine_n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(kFull, pre_n, o);
+              if (lane >= o) pre_n += t;
+            }
+            int idx = nlist + pre_n - mine_n;
+            nlist += __shfl_sync(kFull, pre_n, 31);
+            while (band) {   // inside the WIDE band: needs the two missing products
+              const int j = __ffs(band) - 1;
+              band &= band - 1;
+              const uint32_t bits = pick32(r, j);
+              if (idx < LIST_CAP) {
+                wl->ent[w16][idx] = make_uint2(bits, (uint32_t)((lane << 8) | (c2 * 32 + j)));
+              } else {
+                // list full (rare): the fp64 pass settles this pair; it was counted if its sign bit is clear
+                if ((bits >> 31) == 0u) --cnt;
+                push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + c2 * 32 + j)));
+              }
+              ++idx;
             }
           }
         }
-        __syncwarp();
-        const int n = min(wl->count[w16], LIST_CAP);
+        const int n = min(nlist, LIST_CAP);
         if (n) {
-          __syncwarp();
-          if (lane == 0) wl->count[w16] = 0;
+          __syncwarp();   // the list entries written above are visible to the whole warp
           for (int b = 0; b < n; b += 8) {
             const bool mine = b + slot < n;
-            const uint2 en = mine ? wl->ent[w16][b + slot] : make_uint2(0u, 0u);
+            const uint2 en = wl->ent[w16][mine ? b + slot : 0];
             const int L = (int)(en.y >> 8), col = (int)(en.y & 255u);
             const int qr = quarter * 32 + L;
             const int64_t erow = e0 + col;
             const int8_t *ebase = a.E8 + erow * (2 * kb);
             const uint8_t *qhb = sQ8h + qr * kb, *qlb = sQ8l + qr * kb;
-            int4 wlo[MAX_KCH], whi[MAX_KCH];
-            int phys[MAX_KCH];
+            const int x = swz ? (qr & 7) : 0;
+            // every load of the pair is issued before the first use: the rows' chunks and the row's constants
+            int4 wlo[KCH], whi[KCH];
 #pragma unroll
-            for (int t = 0; t < MAX_KCH; ++t) {
-              if (t < kch) {
-                int c, phi;
-                if (swz) {
-                  // bank group of the shared-memory read = pi: distinct over the 8 slots of a quarter-warp
-                  const int pi = (slot + part + 4 * (t & 1)) & 7;
-                  phi = 8 * (t >> 1) + pi;
-                  c = 8 * (t >> 1) + (pi ^ (qr & 7));
-                } else {
-                  c = phi = part + 4 * t;
-                }
-                phys[t] = phi;
-                if (mine) {
-                  wlo[t] = __ldg(reinterpret_cast<const int4 *>(ebase + c * 16));
-                  whi[t] = __ldg(reinterpret_cast<const int4 *>(ebase + kb + c * 16));
-                }
-              }
+            for (int t = 0; t < KCH; ++t) {
+              const int c = swz ? (8 * (t >> 1) + (pi[t & 1] ^ x)) : part + 4 * t;
+              wlo[t] = __ldg(reinterpret_cast<const int4 *>(ebase + c * 16));
+              whi[t] = __ldg(reinterpret_cast<const int4 *>(ebase + kb + c * 16));
             }
+            const float4 em = __ldg(a.e_meta + erow);                                    // selo, l1lo, sehi, l1hi
             int acc1 = 0, acc2 = 0;   // q_hi8 . e_lo8   and   q_lo8 . e_hi8
 #pragma unroll
-            for (int t = 0; t < MAX_KCH; ++t) {
-              if (t < kch && mine) {
-                const int4 qh = *reinterpret_cast<const int4 *>(qhb + phys[t] * 16);
-                const int4 ql = *reinterpret_cast<const int4 *>(qlb + phys[t] * 16);
-                acc1 = __dp4a(qh.x, wlo[t].x, acc1);
-                acc1 = __dp4a(qh.y, wlo[t].y, acc1);
-                acc1 = __dp4a(qh.z, wlo[t].z, acc1);
-                acc1 = __dp4a(qh.w, wlo[t].w, acc1);
-                acc2 = __dp4a(ql.x, whi[t].x, acc2);
-                acc2 = __dp4a(ql.y, whi[t].y, acc2);
-                acc2 = __dp4a(ql.z, whi[t].z, acc2);
-                acc2 = __dp4a(ql.w, whi[t].w, acc2);
-              }
+            for (int t = 0; t < KCH; ++t) {
+              const int phi = swz ? 8 * (t >> 1) + pi[t & 1] : part + 4 * t;
+              const int4 qh = *reinterpret_cast<const int4 *>(qhb + phi * 16);
+              const int4 ql = *reinterpret_cast<const int4 *>(qlb + phi * 16);
+              acc1 = __dp4a(qh.x, wlo[t].x, acc1);
+              acc1 = __dp4a(qh.y, wlo[t].y, acc1);
+              acc1 = __dp4a(qh.z, wlo[t].z, acc1);
+              acc1 = __dp4a(qh.w, wlo[t].w, acc1);
+              acc2 = __dp4a(ql.x, whi[t].x, acc2);
+              acc2 = __dp4a(ql.y, whi[t].y, acc2);
+              acc2 = __dp4a(ql.z, whi[t].z, acc2);
+              acc2 = __dp4a(ql.w, whi[t].w, acc2);
             }
             acc1 += __shfl_xor_sync(kFull, acc1, 8);
             acc2 += __shfl_xor_sync(kFull, acc2, 8);
             acc1 += __shfl_xor_sync(kFull, acc1, 16);
             acc2 += __shfl_xor_sync(kFull, acc2, 16);
             if (mine && part == 0) {
-              const float4 em = __ldg(a.e_meta + erow);                                    // selo, l1lo, sehi, l1hi
               const float4 m0 = *reinterpret_cast<const float4 *>(sQm + qr * QM);          // tmid, htight, qn, qlon
               const float4 m1 = *reinterpret_cast<const float4 *>(sQm + qr * QM + 4);      // sqh, sql, qA1, qB1
               const float2 m2 = *reinterpret_cast<const float2 *>(sQm + qr * QM + 8);      // qA2, qB2
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_single_kernel(const SingleArg
               if (delta) atomicAdd(a.cnt_gt + (int64_t)qt * QT + qr, delta);
             }
           }
-          __syncwarp();
+          __syncwarp();   // the next tile's entries overwrite the list
         }
       }
       __syncwarp();
@@ -720,25 +722,26 @@ int skge_rank_single_count(const void *Ehi, const void *E8, const void *e_meta, 
   a.nslices = (a.etiles + tps - 1) / tps;
   const int64_t nitems = (int64_t)a.qunits * a.nslices;
   int units = nitems < nunits ? (int)nitems : nunits;
-  if (cta_group == 2) {
-    SKGE_CUDA(cudaFuncSetAttribute(rank_single_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * units);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SKGE_CUDA(cudaLaunchKernelEx(&cfg, rank_single_kernel<2>, a));
-  } else {
-    SKGE_CUDA(cudaFuncSetAttribute(rank_single_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rank_single_kernel<1><<<units, THREADS, smem, as_stream(stream)>>>(a);
-  }
+  void (*kern)(const SingleArgs) = nullptr;
+#define SKGE_SINGLE(CGV, K) (cta_group == CGV && a.kch == K) kern = rank_single_kernel<CGV, K>
+  if SKGE_SINGLE(1, 1); else if SKGE_SINGLE(1, 2); else if SKGE_SINGLE(1, 3); else if SKGE_SINGLE(1, 4);
+  else if SKGE_SINGLE(2, 1); else if SKGE_SINGLE(2, 2); else if SKGE_SINGLE(2, 3); else if SKGE_SINGLE(2, 4);
+#undef SKGE_SINGLE
+  SKGE_REQUIRE(kern != nullptr, "no kernel for this shape");
+  SKGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cta_group == 2 ? 2 * units : units);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SKGE_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   SKGE_LAUNCH_CHECK();
   return 0;
 }
