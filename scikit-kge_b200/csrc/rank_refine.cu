@@ -117,10 +117,10 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int j) {
   return (j & 16) ? d1 : d0;
 }
 
-template <int CG>
+template <int CG, int KCH>
 __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int kch = a.kch, kb = kch * 64;
+  constexpr int kch = KCH, kb = KCH * 64;   // compile-time row length: the refinement's addressing folds into immediates
   uint8_t *sA_hi = smem_raw;
   uint8_t *sA_lo = sA_hi + kch * BLOCK_BYTES;
   uint8_t *sQ8 = sA_lo + kch * BLOCK_BYTES;
@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
     const int colhalf = quad & 1;                    // which 128 of the stage's 256 columns
     const int row = quarter * 32 + lane;             // query row inside the tile
     const int slot = lane & 7, part = lane >> 3;     // refinement: four lanes per pair
-    const bool swz = (kch & 1) == 0;
+    constexpr bool swz = (KCH & 1) == 0;
+    // bank group of the swizzled shared-memory reads: distinct over the 8 slots of a quarter-warp
+    const int pi[2] = {(slot + part) & 7, (slot + part + 4) & 7};
     constexpr uint32_t EPI_SLEEP = 128u;   // ns between polls of a waiting epilogue warp
     uint32_t tseq = 0, aphase = 0;
     for (int item = unit; item < nitems; item += nunits) {
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
         mbar_wait_sleep<EPI_SLEEP>(&ctrl->acc_full[st], (my >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + st * ET + colhalf * 128;
+        int nlist = 0;
         for (int c2 = 0; c2 < 4; ++c2) {
           uint32_t r[32];
           tmem_ld32(taddr + 32 * c2, r);
@@ -338,61 +341,67 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
           }
           cnt += __popc(mhi);
           uint32_t band = mlo & ~mhi;   // inside the WIDE band: needs the missing product
-          while (band) {
-            const int j = __ffs(band) - 1;
-            band &= band - 1;
-            const int idx = atomicAdd(&wl->count[w16], 1);
-            if (idx < LIST_CAP) {
-              wl->ent[w16][idx] = make_uint2(pick32(r, j), (uint32_t)((lane << 8) | (c2 * 32 + j)));
+          // -> the warp's list.  Slots come from a ballot (one element per lane, the usual case) or a warp
+          // prefix sum of the per-lane counts: no shared-memory atomics in the dependent chain.
+          const uint32_t hit = __ballot_sync(kFull, band != 0u);
+          if (hit) {
+            const int mine_n = __popc(band);
+            int idx;
+            if (__ballot_sync(kFull, mine_n > 1) == 0u) {
+              idx = nlist + __popc(hit & ((1u << lane) - 1u));
+              nlist += __popc(hit);
             } else {
-              // list full (rare): let the fp64 pass settle this pair
-              push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + c2 * 32 + j)));
+              int pre_n = mine_n;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, pre_n, o);
+                if (lane >= o) pre_n += t;
+              }
+              idx = nlist + pre_n - mine_n;
+              nlist += __shfl_sync(kFull, pre_n, 31);
+            }
+            while (band) {
+              const int j = __ffs(band) - 1;
+              band &= band - 1;
+              if (idx < LIST_CAP) {
+                wl->ent[w16][idx] = make_uint2(pick32(r, j), (uint32_t)((lane << 8) | (c2 * 32 + j)));
+              } else {
+                // list full (rare): let the fp64 pass settle this pair
+                push_global(a, (int)q, (int)(a.shard_base + entity_of(a, e0 + c2 * 32 + j)));
+              }
+              ++idx;
             }
           }
         }
-        __syncwarp();
-        const int n = min(wl->count[w16], LIST_CAP);
+        const int n = min(nlist, LIST_CAP);
         if (n) {
-          __syncwarp();
-          if (lane == 0) wl->count[w16] = 0;
+          __syncwarp();   // the list entries written above are visible to the whole warp
           for (int b = 0; b < n; b += 8) {
             const bool mine = b + slot < n;
-            const uint2 en = mine ? wl->ent[w16][b + slot] : make_uint2(0u, 0u);
+            const uint2 en = wl->ent[w16][mine ? b + slot : 0];
             const int L = (int)(en.y >> 8), col = (int)(en.y & 255u);
             const int qr = quarter * 32 + L;
             const int64_t erow = e0 + col;
             const int8_t *ebase = a.Elo8 + erow * kb;
             const uint8_t *qbase = sQ8 + qr * kb;
-            float2 meta = make_float2(0.f, 0.f);
-            if (mine) meta = __ldg(a.lo_meta + erow);
-            int4 w[MAX_KCH];
-            int phys[MAX_KCH];
+            const int x = swz ? (qr & 7) : 0;
+            // every load of the pair is issued before the first use: the row's chunks and its constants
+            int4 w[KCH];
 #pragma unroll
-            for (int t = 0; t < MAX_KCH; ++t) {
-              if (t < kch) {
-                int c, phi;
-                if (swz) {
-                  // bank group of the shared-memory read = pi: distinct over the 8 slots of a quarter-warp
-                  const int pi = (slot + part + 4 * (t & 1)) & 7;
-                  phi = 8 * (t >> 1) + pi;
-                  c = 8 * (t >> 1) + (pi ^ (qr & 7));
-                } else {
-                  c = phi = part + 4 * t;
-                }
-                phys[t] = phi;
-                if (mine) w[t] = __ldg(reinterpret_cast<const int4 *>(ebase + c * 16));
-              }
+            for (int t = 0; t < KCH; ++t) {
+              const int c = swz ? (8 * (t >> 1) + (pi[t & 1] ^ x)) : part + 4 * t;
+              w[t] = __ldg(reinterpret_cast<const int4 *>(ebase + c * 16));
             }
+            const float2 meta = __ldg(a.lo_meta + erow);
             int acc = 0;
 #pragma unroll
-            for (int t = 0; t < MAX_KCH; ++t) {
-              if (t < kch && mine) {
-                const int4 qv = *reinterpret_cast<const int4 *>(qbase + phys[t] * 16);
-                acc = __dp4a(qv.x, w[t].x, acc);
-                acc = __dp4a(qv.y, w[t].y, acc);
-                acc = __dp4a(qv.z, w[t].z, acc);
-                acc = __dp4a(qv.w, w[t].w, acc);
-              }
+            for (int t = 0; t < KCH; ++t) {
+              const int phi = swz ? 8 * (t >> 1) + pi[t & 1] : part + 4 * t;
+              const int4 qv = *reinterpret_cast<const int4 *>(qbase + phi * 16);
+              acc = __dp4a(qv.x, w[t].x, acc);
+              acc = __dp4a(qv.y, w[t].y, acc);
+              acc = __dp4a(qv.z, w[t].z, acc);
+              acc = __dp4a(qv.w, w[t].w, acc);
             }
             acc += __shfl_xor_sync(kFull, acc, 8);
             acc += __shfl_xor_sync(kFull, acc, 16);
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
                 push_global(a, (int)qg, (int)(a.shard_base + entity_of(a, erow)));
             }
           }
-          __syncwarp();
+          __syncwarp();   // the next tile's entries overwrite the list
         }
       }
       __syncwarp();
@@ -609,25 +618,26 @@ int skge_rank_refine_count(const void *Ehi, const void *Elo8, const void *lo_met
   a.nslices = (a.etiles + tps - 1) / tps;
   const int64_t nitems = (int64_t)a.qunits * a.nslices;
   int units = nitems < nunits ? (int)nitems : nunits;
-  if (cta_group == 2) {
-    SKGE_CUDA(cudaFuncSetAttribute(rank_refine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * units);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SKGE_CUDA(cudaLaunchKernelEx(&cfg, rank_refine_kernel<2>, a));
-  } else {
-    SKGE_CUDA(cudaFuncSetAttribute(rank_refine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rank_refine_kernel<1><<<units, THREADS, smem, as_stream(stream)>>>(a);
-  }
+  void (*kern)(const RefineArgs) = nullptr;
+#define SKGE_REFINE(CGV, K) (cta_group == CGV && a.kch == K) kern = rank_refine_kernel<CGV, K>
+  if SKGE_REFINE(1, 1); else if SKGE_REFINE(1, 2); else if SKGE_REFINE(1, 3); else if SKGE_REFINE(1, 4);
+  else if SKGE_REFINE(2, 1); else if SKGE_REFINE(2, 2); else if SKGE_REFINE(2, 3); else if SKGE_REFINE(2, 4);
+#undef SKGE_REFINE
+  SKGE_REQUIRE(kern != nullptr, "no kernel for this shape");
+  SKGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cta_group == 2 ? 2 * units : units);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SKGE_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   SKGE_LAUNCH_CHECK();
   return 0;
 }

@@ -404,14 +404,21 @@ __global__ void __launch_bounds__(THREADS, 1) rank_single_kernel(const SingleArg
           const uint32_t hit = __ballot_sync(kFull, band != 0u);
           if (hit) {
             const int mine_n = __popc(band);
-            int pre_n = mine_n;
+            int idx;
+            if (__ballot_sync(kFull, mine_n > 1) == 0u) {
+              // the usual case, one element per lane: slots straight from the ballot
+              idx = nlist + __popc(hit & ((1u << lane) - 1u));
+              nlist += __popc(hit);
+            } else {
+              int pre_n = mine_n;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int t = __shfl_up_sync(kFull, pre_n, o);
-              if (lane >= o) pre_n += t;
+              for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, pre_n, o);
+                if (lane >= o) pre_n += t;
+              }
+              idx = nlist + pre_n - mine_n;
+              nlist += __shfl_sync(kFull, pre_n, 31);
             }
-            int idx = nlist + pre_n - mine_n;
-            nlist += __shfl_sync(kFull, pre_n, 31);
             while (band) {   // inside the WIDE band: needs the two missing products
               const int j = __ffs(band) - 1;
               band &= band - 1;
