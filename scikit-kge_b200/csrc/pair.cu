@@ -604,6 +604,113 @@ __global__ void __launch_bounds__(256, 4) hole_pair_spec_kernel(const float *__r
   }
 }
 
+// The same kernel for d = 128 * NIT with 128-bit accesses: a lane owns the complex slots
+// (2 lane + 64 it, 2 lane + 64 it + 1), the six spectral rows stay in registers between the score
+// and the gradient rows, so every row is requested once and each request / store moves 16 bytes.
+template <int NIT>
+__global__ void __launch_bounds__(256, 3) hole_pair_spec4_kernel(const float *__restrict__ Ehat,
+                                                                 const float *__restrict__ Rhat, PairIdx ix,
+                                                                 int64_t P, int af, float margin,
+                                                                 uint8_t *__restrict__ flags, float *__restrict__ G,
+                                                                 int32_t *__restrict__ counts,
+                                                                 int64_t *__restrict__ nviol_accum) {
+  constexpr int d = 128 * NIT, h = d / 2;
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv_d = 1.0f / (float)d;
+  int nv = 0;
+  for (int64_t i = warp; i < P; i += nwarps) {
+    if (ix.valid && !ix.valid[i]) {
+      if (lane == 0) flags[i] = 0;
+      continue;
+    }
+    const float4 *S = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.sp[i] * d);
+    const float4 *O = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.op[i] * d);
+    const float4 *Rp = reinterpret_cast<const float4 *>(Rhat + (int64_t)ix.pp[i] * d);
+    const float4 *S2 = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.sn[i] * d);
+    const float4 *O2 = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.on[i] * d);
+    const float4 *Rn = reinterpret_cast<const float4 *>(Rhat + (int64_t)ix.pn[i] * d);
+    float4 s[NIT], o[NIT], rp[NIT], s2[NIT], o2[NIT], rn[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int f4 = lane + 32 * it;
+      s[it] = __ldg(S + f4); o[it] = __ldg(O + f4); rp[it] = __ldg(Rp + f4);
+      s2[it] = __ldg(S2 + f4); o2[it] = __ldg(O2 + f4); rn[it] = __ldg(Rn + f4);
+    }
+    float accp = 0.f, accn = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      // second slot of the float4: always a complex slot
+      const float2 a1 = cmulc(make_float2(s[it].z, s[it].w), make_float2(o[it].z, o[it].w));
+      const float2 b1 = cmulc(make_float2(s2[it].z, s2[it].w), make_float2(o2[it].z, o2[it].w));
+      accp += 2.f * (a1.x * rp[it].z + a1.y * rp[it].w);
+      accn += 2.f * (b1.x * rn[it].z + b1.y * rn[it].w);
+      if (it == 0 && lane == 0) {  // slot 0 = (X_0, X_{d/2}), both real
+        accp += s[it].x * o[it].x * rp[it].x + s[it].y * o[it].y * rp[it].y;
+        accn += s2[it].x * o2[it].x * rn[it].x + s2[it].y * o2[it].y * rn[it].y;
+      } else {
+        const float2 a0 = cmulc(make_float2(s[it].x, s[it].y), make_float2(o[it].x, o[it].y));
+        const float2 b0 = cmulc(make_float2(s2[it].x, s2[it].y), make_float2(o2[it].x, o2[it].y));
+        accp += 2.f * (a0.x * rp[it].x + a0.y * rp[it].y);
+        accn += 2.f * (b0.x * rn[it].x + b0.y * rn[it].y);
+      }
+    }
+    const float raw_p = warp_sum(accp) * inv_d, raw_n = warp_sum(accn) * inv_d;
+    const float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
+    const bool viol = fn + margin > fp;  // skge/hole.py:56
+    if (lane == 0) flags[i] = viol;
+    if (!viol) continue;
+    ++nv;
+    const float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // hole.py:66-67
+    float4 *g = reinterpret_cast<float4 *>(G + (int64_t)i * 6 * d);
+    const bool same_s = S == S2, same_o = O == O2, same_r = Rp == Rn;
+    constexpr int h4 = h / 2;   // float4 per spectral row
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int f4 = lane + 32 * it;
+      const bool real0 = it == 0 && lane == 0;
+      float2 a1[2], a2[2], a3[2], b1[2], b2[2], b3[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float2 sv = u ? make_float2(s[it].z, s[it].w) : make_float2(s[it].x, s[it].y);
+        const float2 ov = u ? make_float2(o[it].z, o[it].w) : make_float2(o[it].x, o[it].y);
+        const float2 rv = u ? make_float2(rp[it].z, rp[it].w) : make_float2(rp[it].x, rp[it].y);
+        const float2 sv2 = u ? make_float2(s2[it].z, s2[it].w) : make_float2(s2[it].x, s2[it].y);
+        const float2 ov2 = u ? make_float2(o2[it].z, o2[it].w) : make_float2(o2[it].x, o2[it].y);
+        const float2 rv2 = u ? make_float2(rn[it].z, rn[it].w) : make_float2(rn[it].x, rn[it].y);
+        if (u == 0 && real0) {
+          a1[u] = make_float2(sv.x * ov.x, sv.y * ov.y);     b1[u] = make_float2(sv2.x * ov2.x, sv2.y * ov2.y);
+          a2[u] = make_float2(rv.x * ov.x, rv.y * ov.y);     b2[u] = make_float2(rv2.x * ov2.x, rv2.y * ov2.y);
+          a3[u] = make_float2(sv.x * rv.x, sv.y * rv.y);     b3[u] = make_float2(sv2.x * rv2.x, sv2.y * rv2.y);
+        } else {
+          a1[u] = cmulc(sv, ov);  b1[u] = cmulc(sv2, ov2);   // ccorr(s, o)
+          a2[u] = cmulc(rv, ov);  b2[u] = cmulc(rv2, ov2);   // ccorr(r, o)
+          a3[u] = cmul(sv, rv);   b3[u] = cmul(sv2, rv2);    // cconv(s, r)
+        }
+      }
+      auto put = [&](int row, bool same, const float2 (&x)[2], const float2 (&y)[2]) {
+        const float4 vp = make_float4(gp * x[0].x, gp * x[0].y, gp * x[1].x, gp * x[1].y);
+        const float4 vn = make_float4(gn * y[0].x, gn * y[0].y, gn * y[1].x, gn * y[1].y);
+        float4 *dst = g + row * h4 + f4;
+        if (same) {
+          dst[0] = make_float4(vp.x + vn.x, vp.y + vn.y, vp.z + vn.z, vp.w + vn.w);
+        } else {
+          dst[0] = vp;
+          dst[h4] = vn;
+        }
+      };
+      put(0, same_s, a2, b2);  // -> sp | sn
+      put(2, same_o, a3, b3);  // -> op | on
+      put(4, same_r, a1, b1);  // -> pp | pn
+    }
+  }
+  if (lane == 0 && nv) {
+    atomicAdd(counts, nv);
+    if (nviol_accum) atomicAdd(reinterpret_cast<unsigned long long *>(nviol_accum), (unsigned long long)nv);
+  }
+}
+
 static int pair_block_threads(int d) {  // four groups of d4/4 threads (hole_pair_kernel)
   int t = (round4(d) + 31) / 32 * 32;
   return t < 64 ? 64 : t;
@@ -663,8 +770,14 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
     SKGE_REQUIRE(update && log2_exact(d) >= 5 && d <= 1024, "spectral HolE step needs a power-of-two d in [32, 1024]");
     int64_t blocks = (P + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    hole_pair_spec_kernel<<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, d, l1_or_af, margin, flags, G, counts,
-                                                      nviol_accum);
+    if (d == 128 || d == 256) {
+      // 128-bit accesses, register-resident rows
+      if (d == 128) hole_pair_spec4_kernel<1><<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum);
+      else hole_pair_spec4_kernel<2><<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum);
+    } else {
+      hole_pair_spec_kernel<<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, d, l1_or_af, margin, flags, G, counts,
+                                                        nviol_accum);
+    }
   } else {
     SKGE_REQUIRE(d <= 1024, "HolE pair kernel supports d <= 1024");
     bool fft_done = true;
