@@ -24,7 +24,7 @@ LIB = os.path.join(LIBDIR, 'libskge_b200.so')
 NVCC = os.environ.get('NVCC') or shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr',
-         '-I', INC, '-I', CSRC]
+         '-I', INC, '-I', CSRC] + os.environ.get('SKGE_NVCC_EXTRA', '').split()
 
 
 def sources():

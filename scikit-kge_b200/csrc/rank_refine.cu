@@ -47,6 +47,9 @@ namespace rr {
 
 using namespace ptx;
 
+#ifndef SKGE_EPI_SLEEP
+#define SKGE_EPI_SLEEP 128u
+#endif
 static constexpr int QT = 128;             // query rows per CTA (UMMA M per CTA)
 static constexpr int ET = 256;             // entity rows per MMA (UMMA N)
 static constexpr int BLOCK_BYTES = 16384;  // one (128-row tile, 64-k chunk) fp16 block
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_refine_kernel(const RefineArg
     constexpr bool swz = (KCH & 1) == 0;
     // bank group of the swizzled shared-memory reads: distinct over the 8 slots of a quarter-warp
     const int pi[2] = {(slot + part) & 7, (slot + part + 4) & 7};
-    constexpr uint32_t EPI_SLEEP = 128u;   // ns between polls of a waiting epilogue warp
+    constexpr uint32_t EPI_SLEEP = SKGE_EPI_SLEEP;   // ns between polls of a waiting epilogue warp
     uint32_t tseq = 0, aphase = 0;
     for (int item = unit; item < nitems; item += nunits) {
       const Item it = get_item(a, item);

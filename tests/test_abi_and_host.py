@@ -252,3 +252,22 @@ def test_trainer_batch_bounds_and_api_surface():
     a = np.arange(6.0).reshape(2, 3)
     np.testing.assert_allclose(ccorr(a, a[::-1]), orc.ccorr_direct(a, a[::-1]))
     np.testing.assert_allclose(cconv(a, a[::-1]), orc.cconv_direct(a, a[::-1]))
+
+
+def test_table_checksum_detects_any_change_on_both_paths():
+    """ranking._checksum validates everything cached across passes (packed shadows, norm bounds): the
+    int64-word fast path and the int32 fallback (odd element count / unaligned view) must both change when
+    a single element changes, and must not depend on a widening copy of the table."""
+    import torch
+    from skge import ranking
+    g = torch.Generator().manual_seed(3)
+    for shape, view in (((64, 6), slice(None)), ((7, 3), slice(None)), ((64, 6), slice(1, None))):
+        t = torch.randn(*shape, generator=g)[view]
+        a = ranking._checksum(t)
+        assert a == ranking._checksum(t.clone())
+        u = t.clone()
+        u[-1, -1] = torch.nextafter(u[-1, -1], torch.tensor(10.0))
+        assert ranking._checksum(u) != a
+        u = t.clone()
+        u[0, 0] = -u[0, 0]
+        assert ranking._checksum(u) != a
