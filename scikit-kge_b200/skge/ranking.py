@@ -430,7 +430,7 @@ class FilteredRankingEval(object):
     nsplit = int(os.environ.get('SKGE_RANK_NSPLIT', '0'))
     # nsplit = 2 only: 2 pairs two CTAs on one 256-query x 256-entity MMA (cta_group::2), 1 = one CTA per MMA
     cta_group = int(os.environ.get('SKGE_RANK_CG', '2'))
-    refine_min_pairs = 1 << 33  # queries x shard rows per coarse launch above which nsplit = 2 pays off
+    refine_min_pairs = 1 << 28  # queries x shard rows per coarse launch above which nsplit = 2 pays off (config 2: 2^28.6)
     # what 'auto' runs above that size: 'refine' (two products + one refined cross term, csrc/rank_refine.cu)
     # or 'single' (one product + both cross terms refined, csrc/rank_single.cu)
     large_sweep_engine = os.environ.get('SKGE_RANK_LARGE', 'refine')
