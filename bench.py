@@ -34,6 +34,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, 'scikit-kge_b200')
 
+if 'reference' in sys.argv and 'LOCAL_RANK' in os.environ and os.environ.get('OMP_NUM_THREADS') == '1':
+    # torchrun pins every rank to one OpenMP thread; the reference arm runs on rank 0 alone and is meant to
+    # use all the host threads it can (numpy reads the variable when it is first imported)
+    os.environ['OMP_NUM_THREADS'] = str(len(os.sched_getaffinity(0)))
+
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
