@@ -37,56 +37,40 @@ __device__ __forceinline__ void fill_twiddles(float2 *tw, int N, int tid, int nt
 // `out` (n float2 each, shared memory private to the warp).  The twiddle table belongs to a
 // transform of length n * tw_stride (tw[m] = exp(-2 pi i m / (n * tw_stride))).  Returns the
 // buffer that holds the result.  Callers must __syncwarp() after filling `in`.
-// Intermediate stages live in a PADDED layout (one float2 of slack per eight, index i at i + i / 8): the
-// Stockham scatter of a radix-4 stage writes with strides of 4 Ns elements, which in a plain layout puts
-// the lanes of a half-warp on two to four bank groups (ncu: 38 % of the update kernel's shared-memory
-// wavefronts were conflict replays).  The first stage reads, and the last stage writes, the plain layout the
-// callers use, so a buffer must hold warp_fft_buf(n) float2.
-__host__ __device__ __forceinline__ int warp_fft_pad(int i) { return i + (i >> 3); }
-__host__ __device__ __forceinline__ int warp_fft_buf(int n) { return n + (n >> 3); }
-
 template <bool INVERSE>
 __device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float2 *tw, int tw_stride, int logn,
                                             int lane) {
   const int N = 1 << logn, H = N >> 1, Qn = N >> 2;
   const int thalf = H * tw_stride;  // table entries
-  const int nstages = (logn & 1) + (logn >> 1);
-  int stage = 0;
   int Ns = 1;
   if (logn & 1) {
-    const bool wpad = nstages > 1;
     for (int j = lane; j < H; j += 32) {
       const float2 u0 = in[j], u1 = in[j + H];
-      const int o0 = wpad ? warp_fft_pad(2 * j) : 2 * j, o1 = wpad ? warp_fft_pad(2 * j + 1) : 2 * j + 1;
-      out[o0] = make_float2(u0.x + u1.x, u0.y + u1.y);
-      out[o1] = make_float2(u0.x - u1.x, u0.y - u1.y);
+      out[2 * j] = make_float2(u0.x + u1.x, u0.y + u1.y);
+      out[2 * j + 1] = make_float2(u0.x - u1.x, u0.y - u1.y);
     }
     __syncwarp();
     float2 *t = in; in = out; out = t;
     Ns = 2;
-    stage = 1;
   }
-  for (; Ns < N; Ns <<= 2, ++stage) {
-    const bool rpad = stage > 0, wpad = stage < nstages - 1;
+  for (; Ns < N; Ns <<= 2) {
     const int tstep = (N / (4 * Ns)) * tw_stride;
     for (int j = lane; j < Qn; j += 32) {
       const int k = j & (Ns - 1);
       const int j0 = ((j - k) << 2) + k;
       float2 w1 = tw_at(tw, k * tstep, thalf), w2 = tw_at(tw, 2 * k * tstep, thalf), w3 = tw_at(tw, 3 * k * tstep, thalf);
       if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-      const int i0 = j, i1 = j + Qn, i2 = j + 2 * Qn, i3 = j + 3 * Qn;
-      const float2 v0 = in[rpad ? warp_fft_pad(i0) : i0];
-      const float2 v1 = cmul(in[rpad ? warp_fft_pad(i1) : i1], w1);
-      const float2 v2 = cmul(in[rpad ? warp_fft_pad(i2) : i2], w2);
-      const float2 v3 = cmul(in[rpad ? warp_fft_pad(i3) : i3], w3);
+      const float2 v0 = in[j];
+      const float2 v1 = cmul(in[j + Qn], w1);
+      const float2 v2 = cmul(in[j + 2 * Qn], w2);
+      const float2 v3 = cmul(in[j + 3 * Qn], w3);
       const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
       const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
       const float2 jd = INVERSE ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);
-      const int o0 = j0, o1 = j0 + Ns, o2 = j0 + 2 * Ns, o3 = j0 + 3 * Ns;
-      out[wpad ? warp_fft_pad(o0) : o0] = make_float2(s02.x + s13.x, s02.y + s13.y);
-      out[wpad ? warp_fft_pad(o1) : o1] = make_float2(d02.x + jd.x, d02.y + jd.y);
-      out[wpad ? warp_fft_pad(o2) : o2] = make_float2(s02.x - s13.x, s02.y - s13.y);
-      out[wpad ? warp_fft_pad(o3) : o3] = make_float2(d02.x - jd.x, d02.y - jd.y);
+      out[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+      out[j0 + Ns] = make_float2(d02.x + jd.x, d02.y + jd.y);
+      out[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+      out[j0 + 3 * Ns] = make_float2(d02.x - jd.x, d02.y - jd.y);
     }
     __syncwarp();
     float2 *t = in; in = out; out = t;
@@ -97,8 +81,8 @@ __device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float
 // Real transforms of length d through ONE complex transform of length h = d/2
 // (z_m = x_{2m} + i x_{2m+1}):  with E, O the spectra of the even / odd samples,
 //   Z_f = E_f + i O_f,  conj(Z_{h-f}) = E_f - i O_f,  X_f = E_f + W_d^f O_f,  X_h = E_0 - O_0.
-// Per-warp scratch: two buffers of warp_fft_buf(h) float2.
-__host__ __device__ __forceinline__ size_t warp_fft_scratch_floats(int d) { return (size_t)4 * warp_fft_buf(d / 2); }
+// Per-warp scratch: two buffers of h float2 (= 2 d floats in total).
+__host__ __device__ __forceinline__ size_t warp_fft_scratch_floats(int d) { return (size_t)2 * d; }
 
 // packed spectrum (floats pk[0..d), in shared memory; may alias b1) -> time-domain row.
 // The returned buffer, viewed as d floats, holds x_n * (d/2): scale by 2/d.

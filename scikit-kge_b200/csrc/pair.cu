@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256) hole_spectra_kernel(const float *__restri
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int h = d / 2;
-  float2 *b0 = tw + h + (size_t)w * 2 * warp_fft_buf(h), *b1 = b0 + warp_fft_buf(h);
+  float2 *b0 = tw + h + (size_t)w * 2 * h, *b1 = b0 + h;
   for (int64_t r = (int64_t)blockIdx.x * nw + w; r < rows; r += (int64_t)gridDim.x * nw) {
     const float2 *x = reinterpret_cast<const float2 *>(X + r * d);
     __syncwarp();

@@ -305,8 +305,8 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
     // acc is a summed packed spectrum: back to the time domain
     const int h = d / 2;
     tw = reinterpret_cast<float2 *>(spec_smem);
-    b0 = tw + h + (size_t)warp_in_cta * 2 * warp_fft_buf(h);
-    b1 = b0 + warp_fft_buf(h);
+    b0 = tw + h + (size_t)warp_in_cta * 2 * h;
+    b1 = b0 + h;
     float *pk = reinterpret_cast<float *>(b1);   // the packed row may live in b1 until the first stage
     __syncwarp();
 #pragma unroll
