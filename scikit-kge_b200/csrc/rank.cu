@@ -11,9 +11,30 @@ namespace skge {
 // Exact (fp64) score of one entity row against one query vector; all 32 lanes
 // call it and all get the result.  Used for target scores, band candidates and
 // filter entries alike, so equal inputs give bit-equal scores on every GPU.
+// Summation order: for d % 128 == 0 lane l owns the elements 128 j + 4 l + v (one 128-bit load of the
+// entity row and two of the query row per j), v inner, j outer; otherwise the elements l + 32 j.  The
+// settlement kernel below forms its sums in exactly this order.
 __device__ __forceinline__ double score64_warp(int op, const double *__restrict__ q,
                                                const float *__restrict__ e, int d, int lane) {
   double acc = 0.0;
+  if ((d & 127) == 0) {
+    for (int c = 4 * lane; c < d; c += 128) {
+      const float4 ev = __ldg(reinterpret_cast<const float4 *>(e + c));
+      const double2 q01 = *reinterpret_cast<const double2 *>(q + c), q23 = *reinterpret_cast<const double2 *>(q + c + 2);
+      if (op == SKGE_RANK_L1) {
+        acc += fabs((double)ev.x - q01.x);
+        acc += fabs((double)ev.y - q01.y);
+        acc += fabs((double)ev.z - q23.x);
+        acc += fabs((double)ev.w - q23.y);
+      } else {
+        acc = fma((double)ev.x, q01.x, acc);
+        acc = fma((double)ev.y, q01.y, acc);
+        acc = fma((double)ev.z, q23.x, acc);
+        acc = fma((double)ev.w, q23.y, acc);
+      }
+    }
+    return op == SKGE_RANK_L1 ? -warp_sum(acc) : warp_sum(acc);
+  }
   if (op == SKGE_RANK_L1) {
     for (int c = lane; c < d; c += 32) acc += fabs((double)__ldg(e + c) - q[c]);
     return -warp_sum(acc);
@@ -247,7 +268,49 @@ __device__ __forceinline__ void settle4(int op, const double *__restrict__ q64, 
     ep[k] = E + (int64_t)es[k] * d;
     acc[k] = 0.0;
   }
-  if (NC > 0) {
+  auto add4 = [&](double &a, const float4 &ev, const double2 &q01, const double2 &q23) {
+    if (op == SKGE_RANK_L1) {
+      a += fabs((double)ev.x - q01.x);
+      a += fabs((double)ev.y - q01.y);
+      a += fabs((double)ev.z - q23.x);
+      a += fabs((double)ev.w - q23.y);
+    } else {
+      a = fma((double)ev.x, q01.x, a);
+      a = fma((double)ev.y, q01.y, a);
+      a = fma((double)ev.z, q23.x, a);
+      a = fma((double)ev.w, q23.y, a);
+    }
+  };
+  if (NC > 0 && NC % 4 == 0) {
+    // d = 128 or 256: score64_warp's 128-bit order, everything unrolled, all entity loads up front
+    constexpr int NJ = NC >= 4 ? NC / 4 : 1;
+    float4 ev[4][NJ];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) ev[k][j] = __ldg(reinterpret_cast<const float4 *>(ep[k] + 4 * lane + 128 * j));
+    if (same) {
+      double2 q01[NJ], q23[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        q01[j] = *reinterpret_cast<const double2 *>(qp[0] + 4 * lane + 128 * j);
+        q23[j] = *reinterpret_cast<const double2 *>(qp[0] + 4 * lane + 128 * j + 2);
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) add4(acc[k], ev[k][j], q01[j], q23[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double2 q01 = *reinterpret_cast<const double2 *>(qp[k] + 4 * lane + 128 * j);
+          const double2 q23 = *reinterpret_cast<const double2 *>(qp[k] + 4 * lane + 128 * j + 2);
+          add4(acc[k], ev[k][j], q01, q23);
+        }
+    }
+  } else if (NC > 0) {
     constexpr int NCC = NC > 0 ? NC : 1;
     float ev[4][NCC];
 #pragma unroll
@@ -272,6 +335,15 @@ __device__ __forceinline__ void settle4(int op, const double *__restrict__ q64, 
           acc[k] = op == SKGE_RANK_L1 ? acc[k] + fabs((double)ev[k][j] - qv) : fma((double)ev[k][j], qv, acc[k]);
         }
     }
+  } else if ((d & 127) == 0) {
+    for (int c = 4 * lane; c < d; c += 128)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 ev = __ldg(reinterpret_cast<const float4 *>(ep[k] + c));
+        const double2 q01 = *reinterpret_cast<const double2 *>(qp[k] + c);
+        const double2 q23 = *reinterpret_cast<const double2 *>(qp[k] + c + 2);
+        add4(acc[k], ev, q01, q23);
+      }
   } else {
     for (int c = lane; c < d; c += 32)
 #pragma unroll
