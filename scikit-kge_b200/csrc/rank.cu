@@ -357,7 +357,7 @@ __device__ __forceinline__ void settle4(int op, const double *__restrict__ q64, 
 }
 
 template <int NC>
-__global__ void __launch_bounds__(256) rank_rescore_kernel(int op, const float *__restrict__ E, int d,
+__global__ void __launch_bounds__(256, 4) rank_rescore_kernel(int op, const float *__restrict__ E, int d,
                                                            const double *__restrict__ q64,
                                                            const double *__restrict__ tscore,
                                                            const int32_t *__restrict__ pair_q,
