@@ -489,6 +489,12 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def full_sweep(stats):
+    """The ncu capture of the L1 sweep was taken on config 4 (14,951 entities): attach it only there."""
+    lo, hi = stats.get('shard', (0, 0))
+    return hi - lo == 14951
+
+
 def roofline_of(model, stats, kt, ms, pk, full=False):
     """Roofline of the dominant kernel (the coarse query x entity contraction), CUDA events."""
     if not kt:
@@ -512,7 +518,8 @@ def roofline_of(model, stats, kt, ms, pk, full=False):
     # TransE: |e - q| accumulations on the FP32 pipe, 2 lane-instructions per (query, entity, k)
     issue_peak = 148 * 128 * pk['sm_max_mhz'] * 1e6
     achieved = work / (avg_ms * 1e-3)
-    return {'bound': 'fp32-issue', 'achieved': achieved / 1e12, 'peak': issue_peak / 1e12, 'unit': 'T lane-instr/s',
+    ncu = ncu_summary('rank_sweep_tma_kernel') if full_sweep(stats) else None
+    return {'bound': 'fp32-issue', 'ncu': ncu, 'achieved': achieved / 1e12, 'peak': issue_peak / 1e12, 'unit': 'T lane-instr/s',
             'frac': achieved / issue_peak, 'traffic': None, 'kernel': 'rank_sweep_tma_kernel', 'engine': eng,
             'launch_ms': avg_ms, 'launches_timed': len(kt),
             'peak_source': '148 SMs x 128 FP32 lanes x %.0f MHz (max SM clock)' % pk['sm_max_mhz'],

@@ -34,6 +34,9 @@ WANT = {
     'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed': 'dram_throughput_pct',
     'launch__registers_per_thread': 'registers',
     'smsp__inst_executed.sum': 'warp_instructions',
+    'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active': 'fma_pipe_pct',
+    'sm__warps_active.avg.pct_of_peak_sustained_active': 'warps_active_pct',
+    'launch__grid_size': 'grid',
 }
 SCALE = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'ms': 1e-3, 'us': 1e-6, 'ns': 1e-9, 's': 1.0, 'msecond': 1e-3,
          'usecond': 1e-6, 'nsecond': 1e-9, 'second': 1.0, 'Ghz': 1e9, 'Mhz': 1e6, 'cycle/nsecond': 1e9}
