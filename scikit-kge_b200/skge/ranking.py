@@ -542,8 +542,8 @@ class _SweepEngine(object):
             self.cap = 0
         if type(self) is _SweepEngine and hi > lo:
             # the k-major packed copy (csrc/rank_sweep.cu) of the shard is rebuilt only when the table's checksum changes
-            whole = lo == 0 and hi == E.shape[0]
-            chk = _pass_stats(E)['chk'] if whole else _checksum(self.shard)
+            # the whole table's checksum (already computed for this pass) also validates a shard's shadow
+            chk = _pass_stats(E)['chk']
             key = (E.data_ptr(), lo, hi, E.shape[1], chk)
             if key != getattr(self, '_pack_key', None):
                 self._pack_key = None
@@ -637,8 +637,8 @@ class _UmmaEngine(_SweepEngine):
         super(_UmmaEngine, self).bind(E, lo, hi)
         if hi <= lo:
             return
-        whole = lo == 0 and hi == E.shape[0]
-        chk = _pass_stats(E)['chk'] if whole else _checksum(self.shard)
+        # the whole table's checksum (already computed for this pass) also validates a shard's shadow
+        chk = _pass_stats(E)['chk']
         key = (E.data_ptr(), lo, hi, E.shape[1], chk)
         if key == self._shadow_key:
             return
