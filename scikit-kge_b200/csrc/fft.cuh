@@ -125,6 +125,163 @@ __device__ __forceinline__ float2 packed_slot(const float2 *Z, int f, int h, con
   return make_float2(e.x + wo.x, e.y + wo.y);
 }
 
+// ---------------------------------------------------------------------------
+// Register-resident transforms for d = 256 (one warp, no shared memory inside the transform).
+// The half-length complex transform (128 points) is held four points per lane:
+//   time side       z[j] of lane l  = z_m,  m = 32 j + l   (floats 64 j + 2 l, 64 j + 2 l + 1 of the row)
+//   frequency side  Z[k] of lane p  = Z_f,  f = k + 4 brev5(p)
+// 128 = 4 x 32: a radix-4 butterfly over the four registers, the twiddle W_128^{l k}, then a
+// 32-point decimation-in-frequency transform ACROSS THE LANES (five __shfl_xor stages, which is
+// what leaves the lane index bit-reversed).  The inverse runs the same graph backwards.
+// The packed real spectrum (see the top of this file) is formed in the same permuted order;
+// the partner slot 128 - f lives in lane 31 - p, register 4 - k (k > 0) or lane q0, register 0.
+// ---------------------------------------------------------------------------
+struct RegFft256 {
+  float2 w1, w2, w3;   // W_128^{l k}, k = 1..3
+  float2 ws[4];        // lane stages of span 16, 8, 4, 2: W_{2 span}^{l mod span} in the upper lane, 1 in the lower
+  float sg[5];         // -1 in the upper lane of a stage, +1 in the lower (spans 16, 8, 4, 2, 1)
+  float2 wrh[4];       // W_256^f / 2 for the lane's four slots
+  int q0;              // lane holding slot 128 - 4 brev5(p) in register 0
+};
+
+__device__ __forceinline__ int brev5(int x) { return (int)(__brev((unsigned)x) >> 27); }
+
+__device__ __forceinline__ float2 unit_root(float num, float den) {   // exp(-2 pi i num / den)
+  float sn, cs;
+  sincospif(-2.0f * num / den, &sn, &cs);
+  return make_float2(cs, sn);
+}
+
+__device__ __forceinline__ void regfft256_init(RegFft256 &c, int lane) {
+  c.w1 = unit_root((float)lane, 128.f);
+  c.w2 = unit_root((float)(2 * lane), 128.f);
+  c.w3 = unit_root((float)(3 * lane), 128.f);
+#pragma unroll
+  for (int si = 0; si < 5; ++si) {
+    const int s = 16 >> si;
+    const bool upper = (lane & s) != 0;
+    c.sg[si] = upper ? -1.f : 1.f;
+    if (si < 4) c.ws[si] = upper ? unit_root((float)(lane & (s - 1)), (float)(2 * s)) : make_float2(1.f, 0.f);
+  }
+  const int bp = brev5(lane);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 w = unit_root((float)(k + 4 * bp), 256.f);
+    c.wrh[k] = make_float2(0.5f * w.x, 0.5f * w.y);
+  }
+  c.q0 = brev5((32 - bp) & 31);
+}
+
+// z (time order) -> Z (frequency order), unnormalised
+__device__ __forceinline__ void regfft256_fwd(float2 (&z)[4], const RegFft256 &c) {
+  {
+    const float2 s02 = make_float2(z[0].x + z[2].x, z[0].y + z[2].y), d02 = make_float2(z[0].x - z[2].x, z[0].y - z[2].y);
+    const float2 s13 = make_float2(z[1].x + z[3].x, z[1].y + z[3].y), d13 = make_float2(z[1].x - z[3].x, z[1].y - z[3].y);
+    z[0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+    z[1] = cmul(make_float2(d02.x + d13.y, d02.y - d13.x), c.w1);   // d02 - i d13
+    z[2] = cmul(make_float2(s02.x - s13.x, s02.y - s13.y), c.w2);
+    z[3] = cmul(make_float2(d02.x - d13.y, d02.y + d13.x), c.w3);   // d02 + i d13
+  }
+#pragma unroll
+  for (int si = 0; si < 5; ++si) {
+    const int s = 16 >> si;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float ox = __shfl_xor_sync(kFull, z[k].x, s), oy = __shfl_xor_sync(kFull, z[k].y, s);
+      const float2 u = make_float2(fmaf(c.sg[si], z[k].x, ox), fmaf(c.sg[si], z[k].y, oy));
+      z[k] = si < 4 ? cmul(u, c.ws[si]) : u;
+    }
+  }
+}
+
+// Z (frequency order) -> z (time order) times 128
+__device__ __forceinline__ void regfft256_inv(float2 (&z)[4], const RegFft256 &c) {
+#pragma unroll
+  for (int si = 4; si >= 0; --si) {
+    const int s = 16 >> si;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 t = si < 4 ? cmulc(c.ws[si], z[k]) : z[k];
+      const float ox = __shfl_xor_sync(kFull, t.x, s), oy = __shfl_xor_sync(kFull, t.y, s);
+      z[k] = make_float2(fmaf(c.sg[si], t.x, ox), fmaf(c.sg[si], t.y, oy));
+    }
+  }
+  const float2 y1 = cmulc(c.w1, z[1]), y2 = cmulc(c.w2, z[2]), y3 = cmulc(c.w3, z[3]);
+  const float2 s02 = make_float2(z[0].x + y2.x, z[0].y + y2.y), d02 = make_float2(z[0].x - y2.x, z[0].y - y2.y);
+  const float2 s13 = make_float2(y1.x + y3.x, y1.y + y3.y), d13 = make_float2(y1.x - y3.x, y1.y - y3.y);
+  z[0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+  z[1] = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+  z[2] = make_float2(s02.x - s13.x, s02.y - s13.y);
+  z[3] = make_float2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
+}
+
+// the four partner values (slot 128 - f) of a lane's registers
+__device__ __forceinline__ void regfft256_partners(const float2 (&v)[4], float2 (&g)[4], const RegFft256 &c, int lane) {
+  const int m = 31 - lane;
+  g[0] = make_float2(__shfl_sync(kFull, v[0].x, c.q0), __shfl_sync(kFull, v[0].y, c.q0));
+  g[1] = make_float2(__shfl_sync(kFull, v[3].x, m), __shfl_sync(kFull, v[3].y, m));
+  g[2] = make_float2(__shfl_sync(kFull, v[2].x, m), __shfl_sync(kFull, v[2].y, m));
+  g[3] = make_float2(__shfl_sync(kFull, v[1].x, m), __shfl_sync(kFull, v[1].y, m));
+}
+
+// packed real spectrum X (frequency order) -> real row: z[j] = (x_{64 j + 2 l}, x_{64 j + 2 l + 1}) * 128
+__device__ __forceinline__ void regfft256_irfft(float2 (&v)[4], const RegFft256 &c, int lane) {
+  float2 g[4];
+  regfft256_partners(v, g, c, lane);
+  const float2 z00 = make_float2(0.5f * (v[0].x + v[0].y), 0.5f * (v[0].x - v[0].y));   // slot 0 = (X_0, X_128)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 e2 = make_float2(v[k].x + g[k].x, v[k].y - g[k].y);     // X_f + conj X_{128-f}
+    const float2 d2 = make_float2(v[k].x - g[k].x, v[k].y + g[k].y);     // X_f - conj X_{128-f}
+    const float2 o = cmulc(c.wrh[k], d2);                                // W_256^{-f} (X_f - conj X_{128-f}) / 2
+    v[k] = make_float2(fmaf(0.5f, e2.x, -o.y), fmaf(0.5f, e2.y, o.x));   // E_f + i O_f
+  }
+  if (lane == 0) v[0] = z00;
+  regfft256_inv(v, c);
+}
+
+// real row (time order, as above) -> packed real spectrum (frequency order)
+__device__ __forceinline__ void regfft256_rfft(float2 (&v)[4], const RegFft256 &c, int lane) {
+  regfft256_fwd(v, c);
+  float2 g[4];
+  regfft256_partners(v, g, c, lane);
+  const float2 x00 = make_float2(v[0].x + v[0].y, v[0].x - v[0].y);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 e2 = make_float2(v[k].x + g[k].x, v[k].y - g[k].y);     // Z_f + conj Z_{128-f}
+    const float2 o2 = make_float2(v[k].y + g[k].y, g[k].x - v[k].x);     // -i (Z_f - conj Z_{128-f})
+    const float2 t = cmul(c.wrh[k], o2);
+    v[k] = make_float2(fmaf(0.5f, e2.x, t.x), fmaf(0.5f, e2.y, t.y));
+  }
+  if (lane == 0) v[0] = x00;
+}
+
+// Transposition between the frequency order above and the packed row in memory order (lane l owns
+// the 16-byte units l and 32 + l) through 1 KB of per-warp shared memory; units are XOR-swizzled so
+// that both access patterns are conflict-free.
+__device__ __forceinline__ int regfft256_swz(int u) { return u ^ ((u >> 3) & 7); }
+
+__device__ __forceinline__ void regfft256_row_to_freq(float4 *buf, const float4 &r0, const float4 &r1, float2 (&v)[4], int lane) {
+  __syncwarp();
+  buf[regfft256_swz(lane)] = r0;
+  buf[regfft256_swz(32 + lane)] = r1;
+  __syncwarp();
+  const int u = 2 * brev5(lane);
+  const float4 t0 = buf[regfft256_swz(u)], t1 = buf[regfft256_swz(u + 1)];
+  v[0] = make_float2(t0.x, t0.y); v[1] = make_float2(t0.z, t0.w);
+  v[2] = make_float2(t1.x, t1.y); v[3] = make_float2(t1.z, t1.w);
+}
+
+__device__ __forceinline__ void regfft256_freq_to_row(float4 *buf, const float2 (&v)[4], float4 &r0, float4 &r1, int lane) {
+  __syncwarp();
+  const int u = 2 * brev5(lane);
+  buf[regfft256_swz(u)] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+  buf[regfft256_swz(u + 1)] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+  __syncwarp();
+  r0 = buf[regfft256_swz(lane)];
+  r1 = buf[regfft256_swz(32 + lane)];
+}
+
 static inline int log2_exact(int d) {
   int l = 0;
   while ((1 << l) < d) ++l;

@@ -8,6 +8,7 @@
 
 #include "fft.cuh"
 #include "segment.cuh"
+#include "umma.cuh"
 
 namespace skge {
 
@@ -239,9 +240,13 @@ struct SegArgs {
 
 // shared memory of the spectral mode: twiddles [d/2] float2, then per warp two complex
 // buffers of d/2 float2 (2 d floats)
+// (d = 256 takes the register-resident transforms of fft.cuh: 1 KB of transposition space per warp)
 __host__ __device__ __forceinline__ size_t spec_smem_bytes(int d, int warps) {
+  if (d == 256) return (size_t)warps * 1024;
   return (size_t)(d / 2) * sizeof(float2) + (size_t)warps * warp_fft_scratch_floats(d) * sizeof(float);
 }
+template <int VEC, int MAXC, bool UPDATE, bool SPEC>
+struct SpecReg { static constexpr bool value = UPDATE && SPEC && VEC == 4 && MAXC == 2; };   // <=> d == 256
 
 // acc += signed gradient rows of occurrences [beg, end) of the sorted list.  The payloads of
 // up to 32 occurrences are fetched with one coalesced load and broadcast by shuffle; row loads
@@ -292,9 +297,46 @@ __device__ __forceinline__ int accumulate_rows(const SegArgs &a, int beg, int en
 
 // acc holds the SUM over the n occurrences of segment seg: take the mean and either apply
 // the optimiser step in place or emit (gradient row, row id).
+// d = 256, spectral update: acc is the summed packed spectrum of the row's n occurrences.  Inverse
+// transform, mean, optimiser step and post-hook in the time domain, forward transform of the updated
+// row into the spectral table -- all in registers (fft.cuh), two shared-memory transpositions.
+__device__ __forceinline__ void finish_row_spec256(const SegArgs &a, int key, int n, int lane, float (&acc)[2][4],
+                                                   float *spec_smem, int warp_in_cta, const RegFft256 &rc) {
+  constexpr int d = 256;
+  const int which = key >= a.N;
+  const int64_t row = which ? key - a.N : key;
+  const ParamDesc &pd = a.pd[which];
+  float4 *buf = reinterpret_cast<float4 *>(spec_smem) + warp_in_cta * 64;
+  float2 v[4];
+  regfft256_row_to_freq(buf, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]),
+                        make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]), v, lane);
+  regfft256_irfft(v, rc, lane);
+  const float sc = (2.0f / (float)d) / (float)n;   // transform scale and the mean (skge/util.py:97-101)
+  float g[4][2], x[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { g[j][0] = v[j].x * sc; g[j][1] = v[j].y * sc; }
+  row_update<2, 4>(pd.param + row * d, pd.p2 ? pd.p2 + row * d : nullptr, g, d, lane, a.opt, a.lr, pd.post, pd.rparam, x);
+  if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
+  if (pd.hat) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = make_float2(x[j][0], x[j][1]);
+    regfft256_rfft(v, rc, lane);
+    float4 r0, r1;
+    regfft256_freq_to_row(buf, v, r0, r1, lane);
+    float4 *hrow = reinterpret_cast<float4 *>(pd.hat + row * d);
+    hrow[lane] = r0;
+    hrow[32 + lane] = r1;
+  }
+}
+
 template <int VEC, int MAXC, bool UPDATE, bool SPEC>
 __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, int n, int lane,
-                                           float (&acc)[MAXC][VEC], float *spec_smem = nullptr, int warp_in_cta = 0) {
+                                           float (&acc)[MAXC][VEC], float *spec_smem, int warp_in_cta,
+                                           const RegFft256 &rc) {
+  if constexpr (SpecReg<VEC, MAXC, UPDATE, SPEC>::value) {
+    finish_row_spec256(a, key, n, lane, acc, spec_smem, warp_in_cta, rc);
+    return;
+  }
   const int d = a.d;
   const int U0 = a.meta[1];
   int which = key >= a.N;
@@ -370,14 +412,21 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
 
 // Pass 1: one warp per segment.  Short segments are finished here; long ones are registered
 // (segment, chunk range) for passes 2 and 3.
+#ifndef SKGE_SEG_SPEC256_CTAS
+#define SKGE_SEG_SPEC256_CTAS 4
+#endif
 template <int VEC, int MAXC, bool UPDATE, int BATCH, bool SPEC>
-__global__ void __launch_bounds__(256, (BATCH > 1 || MAXC > 2) ? 1 : 4) seg_reduce_kernel(SegArgs a) {
+__global__ void __launch_bounds__(256, SpecReg<VEC, MAXC, UPDATE, SPEC>::value ? SKGE_SEG_SPEC256_CTAS
+                                       : ((BATCH > 1 || MAXC > 2) ? 1 : 4)) seg_reduce_kernel(SegArgs a) {
   extern __shared__ __align__(16) float spec_smem[];
-  if (UPDATE && SPEC) {
+  const int lane = threadIdx.x & 31;
+  RegFft256 rc;
+  if constexpr (SpecReg<VEC, MAXC, UPDATE, SPEC>::value) {
+    regfft256_init(rc, lane);
+  } else if (UPDATE && SPEC) {
     fill_twiddles(reinterpret_cast<float2 *>(spec_smem), a.d, threadIdx.x, blockDim.x);
     __syncthreads();
   }
-  const int lane = threadIdx.x & 31;
   const int nseg = a.meta[0];
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.counts) {
     a.counts[1] = a.meta[1];
@@ -415,8 +464,207 @@ __global__ void __launch_bounds__(256, (BATCH > 1 || MAXC > 2) ? 1 : 4) seg_redu
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
     const int occ = accumulate_rows<VEC, MAXC, BATCH>(a, beg, end, lane, acc);
-    finish_row<VEC, MAXC, UPDATE, SPEC>(a, seg, key, occ, lane, acc, spec_smem, threadIdx.x >> 5);
+    finish_row<VEC, MAXC, UPDATE, SPEC>(a, seg, key, occ, lane, acc, spec_smem, threadIdx.x >> 5, rc);
   }
+}
+
+// ---------------------------------------------------------------------------
+// Pass 1 for large minibatches of 1 KB rows (d = 256), update mode: the same walk, but every row a
+// segment needs -- its parameter row, its AdaGrad row and up to SLOTS - 2 gradient rows at a time --
+// is brought into a per-warp shared-memory ring by 1-D bulk-TMA copies (one row = one contiguous
+// 1 KB copy, issued by one lane each, all completing on the warp's own mbarrier).  The register
+// walk above keeps ONE row (1 KB) in flight per warp, and with ~1.2 us of loaded DRAM latency the
+// SM then idles on memory (ncu: 44 % of DRAM peak at 28 resident warps); here a warp has
+// (n + 2) KB in flight without spending a register on it.
+// ---------------------------------------------------------------------------
+template <int VEC, int MAXC>
+__device__ __forceinline__ void row_update_staged(float *xrow, float *p2row, float (&g)[MAXC][VEC],
+                                                  float (&x)[MAXC][VEC], float (&p2)[MAXC][VEC], int lane, int opt,
+                                                  float lr, int post, float rparam) {
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (opt == SKGE_OPT_ADAGRAD) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float gg = g[c][v] + rparam * x[c][v];
+        p2[c][v] += gg * gg;                                   // skge/param.py:147
+        x[c][v] -= lr * gg * adagrad_rscale(p2[c][v]);         // skge/param.py:152-155
+      }
+      st_vec<VEC>(p2row + (c * 32 + lane) * VEC, p2[c]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) x[c][v] -= lr * (g[c][v] + rparam * x[c][v]);  // skge/param.py:130
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) ss += x[c][v] * x[c][v];
+  }
+  float scale = 1.f;
+  if (post != SKGE_POST_NONE) {
+    ss = warp_sum(ss);
+    if (post == SKGE_POST_NORMALIZE) scale = rsqrtf(ss);                 // skge/param.py:165-166
+    else scale = 1.0f / (ss < 1.0f ? 1.0f : ss);                        // skge/param.py:171-173 (squared norm)
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (post != SKGE_POST_NONE) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) x[c][v] *= scale;
+    }
+    st_vec<VEC>(xrow + (c * 32 + lane) * VEC, x[c]);
+  }
+}
+
+#ifndef SKGE_SEG_BULK_SLOTS
+#define SKGE_SEG_BULK_SLOTS 6
+#endif
+#ifndef SKGE_SEG_BULK_CTAS
+#define SKGE_SEG_BULK_CTAS 4
+#endif
+static constexpr int kBulkRowFloats = 256;
+static constexpr int kBulkRowBytes = kBulkRowFloats * 4;
+__host__ __device__ constexpr size_t seg_bulk_smem_bytes(int slots) { return 128 + (size_t)8 * slots * kBulkRowBytes; }
+
+template <bool SPEC, int SLOTS>
+__global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kernel(SegArgs a) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  constexpr int d = kBulkRowFloats, CAP = SLOTS - 2;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(bulk_smem) + w;
+  float4 *slots = reinterpret_cast<float4 *>(bulk_smem + 128) + (size_t)w * SLOTS * (d / 4);   // [SLOTS][64] float4
+  if (lane == 0) {
+    ptx::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  RegFft256 rc;
+  if constexpr (SPEC) regfft256_init(rc, lane);
+  const int nseg = a.meta[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.counts) {
+    a.counts[1] = a.meta[1];
+    a.counts[2] = nseg - a.meta[1];
+  }
+  const bool adagrad = a.opt == SKGE_OPT_ADAGRAD;
+  uint32_t phase = 0;
+  const int warp = blockIdx.x * 8 + w, nwarps = gridDim.x * 8;
+  for (int seg = warp; seg < nseg; seg += nwarps) {
+    const int key = a.seg_key[seg];
+    const int beg = a.seg_start[seg], end = a.seg_start[seg + 1];
+    const int n = end - beg;
+    if (n > a.seg_chunk) {   // hot row: passes 2 and 3
+      int nch = (n + a.seg_chunk - 1) / a.seg_chunk;
+      int slot = 0, first = 0;
+      if (lane == 0) {
+        slot = atomicAdd(a.long_meta, 1);
+        first = atomicAdd(a.long_meta + 1, nch);
+      }
+      slot = __shfl_sync(kFull, slot, 0);
+      first = __shfl_sync(kFull, first, 0);
+      if (lane == 0) {
+        a.long_seg[3 * slot] = seg;
+        a.long_seg[3 * slot + 1] = first;
+        a.long_seg[3 * slot + 2] = nch;
+      }
+      for (int k = lane; k < nch; k += 32) {
+        a.long_work[2 * (first + k)] = seg;
+        a.long_work[2 * (first + k) + 1] = k;
+      }
+      continue;
+    }
+    const int which = key >= a.N;
+    const int64_t row = which ? key - a.N : key;
+    const ParamDesc &pd = a.pd[which];
+    float *xrow = pd.param + row * d, *p2row = adagrad ? pd.p2 + row * d : nullptr;
+    float acc[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[c][v] = 0.f;
+    int folded = 0;
+    for (int j0 = beg; j0 < end; j0 += CAP) {
+      const int cnt = min(CAP, end - j0);
+      const int myval = lane < cnt ? a.vals[j0 + lane] : 0;
+      folded += __popc(__ballot_sync(kFull, (myval & 8) != 0));
+      const bool first = j0 == beg;
+      // the slots were last touched by this warp's own (generic-proxy) reads and writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) ptx::mbar_expect_tx(bar, (uint32_t)(cnt + (first ? (adagrad ? 2 : 1) : 0)) * kBulkRowBytes);
+      __syncwarp();
+      if (lane < cnt)
+        ptx::bulk_g2s(slots + (2 + lane) * (d / 4),
+                      a.G + ((int64_t)(myval >> 4) * a.rows_per_unit + a.grow[myval & 7]) * d, kBulkRowBytes, bar);
+      if (first) {
+        if (lane == 30) ptx::bulk_g2s(slots, xrow, kBulkRowBytes, bar);
+        if (lane == 31 && adagrad) ptx::bulk_g2s(slots + d / 4, p2row, kBulkRowBytes, bar);
+      }
+      ptx::mbar_wait(bar, phase);
+      phase ^= 1;
+      for (int t = 0; t < cnt; ++t) {
+        const float sgn = a.gsign[__shfl_sync(kFull, myval, t) & 7];
+        const float4 u0 = slots[(2 + t) * (d / 4) + lane], u1 = slots[(2 + t) * (d / 4) + 32 + lane];
+        acc[0][0] = fmaf(sgn, u0.x, acc[0][0]); acc[0][1] = fmaf(sgn, u0.y, acc[0][1]);
+        acc[0][2] = fmaf(sgn, u0.z, acc[0][2]); acc[0][3] = fmaf(sgn, u0.w, acc[0][3]);
+        acc[1][0] = fmaf(sgn, u1.x, acc[1][0]); acc[1][1] = fmaf(sgn, u1.y, acc[1][1]);
+        acc[1][2] = fmaf(sgn, u1.z, acc[1][2]); acc[1][3] = fmaf(sgn, u1.w, acc[1][3]);
+      }
+    }
+    const int occ = n + folded;
+    if constexpr (SPEC) {
+      // summed packed spectrum -> time domain (registers), update, -> spectrum of the updated row
+      float2 v[4];
+      float4 *tbuf = slots + 2 * (d / 4);   // a consumed gradient slot serves the two transpositions
+      regfft256_row_to_freq(tbuf, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]),
+                            make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]), v, lane);
+      regfft256_irfft(v, rc, lane);
+      const float sc = (2.0f / (float)d) / (float)occ;   // transform scale and the mean (skge/util.py:97-101)
+      float g[4][2], x[4][2], p2[4][2];
+      const float2 *xs = reinterpret_cast<const float2 *>(slots), *ps = reinterpret_cast<const float2 *>(slots + d / 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        g[j][0] = v[j].x * sc; g[j][1] = v[j].y * sc;
+        const float2 xv = xs[32 * j + lane];
+        x[j][0] = xv.x; x[j][1] = xv.y;
+        if (adagrad) { const float2 pv = ps[32 * j + lane]; p2[j][0] = pv.x; p2[j][1] = pv.y; }
+      }
+      row_update_staged<2, 4>(xrow, p2row, g, x, p2, lane, a.opt, a.lr, pd.post, pd.rparam);
+      if (pd.hat) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = make_float2(x[j][0], x[j][1]);
+        regfft256_rfft(v, rc, lane);
+        float4 r0, r1;
+        regfft256_freq_to_row(tbuf, v, r0, r1, lane);
+        float4 *hrow = reinterpret_cast<float4 *>(pd.hat + row * d);
+        hrow[lane] = r0;
+        hrow[32 + lane] = r1;
+      }
+    } else {
+      const float inv_n = 1.0f / (float)occ;
+      float x[2][4], p2[2][4];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[c][v] *= inv_n;   // the mean: skge/util.py:97-101
+        const float4 xv = slots[c * 32 + lane];
+        x[c][0] = xv.x; x[c][1] = xv.y; x[c][2] = xv.z; x[c][3] = xv.w;
+        if (adagrad) {
+          const float4 pv = slots[d / 4 + c * 32 + lane];
+          p2[c][0] = pv.x; p2[c][1] = pv.y; p2[c][2] = pv.z; p2[c][3] = pv.w;
+        }
+      }
+      row_update_staged<4, 2>(xrow, p2row, acc, x, p2, lane, a.opt, a.lr, pd.post, pd.rparam);
+    }
+    if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
+  }
+}
+
+static bool seg_bulk_ok(const SegArgs &a) {
+  if (a.d != kBulkRowFloats || a.seg_chunk <= 32) return false;
+  auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  for (int t = 0; t < 2; ++t)
+    if (!al(a.pd[t].param) || !al(a.pd[t].p2) || !al(a.pd[t].hat)) return false;
+  return al(a.G);
 }
 
 // Pass 2: one warp per chunk of a long segment -> partial sum row.
@@ -456,7 +704,10 @@ __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
   const int nlong = a.long_meta[0];
   const int d = a.d;
   float *spec_smem = red + 8 * d;
-  if (UPDATE && SPEC) {
+  RegFft256 rc;
+  if constexpr (SpecReg<VEC, MAXC, UPDATE, SPEC>::value) {
+    regfft256_init(rc, lane);
+  } else if (UPDATE && SPEC) {
     fill_twiddles(reinterpret_cast<float2 *>(spec_smem), d, threadIdx.x, blockDim.x);
     __syncthreads();
   }
@@ -504,7 +755,7 @@ __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
       for (int k = lane; k < nch; k += 32) n += a.partial_occ[first + k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
-      finish_row<VEC, MAXC, UPDATE, SPEC>(a, seg, a.seg_key[seg], n, lane, acc, spec_smem, 0);
+      finish_row<VEC, MAXC, UPDATE, SPEC>(a, seg, a.seg_key[seg], n, lane, acc, spec_smem, 0, rc);
     }
   }
 }
@@ -512,7 +763,14 @@ __global__ void __launch_bounds__(256) seg_long_finish_kernel(SegArgs a) {
 template <int VEC, int MAXC, int BATCH, bool SPEC>
 static void launch_seg_reduce_s(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
   size_t sm1 = SPEC ? spec_smem_bytes(a.d, 8) : 0;
-  if (update) {
+  if (update && VEC == 4 && MAXC == 2 && seg_bulk_ok(a)) {
+    constexpr int SL = SKGE_SEG_BULK_SLOTS;
+    const size_t smb = seg_bulk_smem_bytes(SL);
+    cudaFuncSetAttribute(seg_reduce_bulk_kernel<SPEC, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    int bb = kNumSMs * SKGE_SEG_BULK_CTAS;
+    if (bb > blocks) bb = blocks;
+    seg_reduce_bulk_kernel<SPEC, SL><<<bb, 256, smb, st>>>(a);
+  } else if (update) {
     if (sm1 > 48 * 1024)
       cudaFuncSetAttribute(seg_reduce_kernel<VEC, MAXC, true, BATCH, SPEC>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
