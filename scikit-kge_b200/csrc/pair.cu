@@ -6,6 +6,7 @@
 #include "fft.cuh"
 #include "hole_math.cuh"
 #include "segment.cuh"
+#include "umma.cuh"
 
 namespace skge {
 
@@ -607,102 +608,297 @@ __global__ void __launch_bounds__(256, 4) hole_pair_spec_kernel(const float *__r
 // The same kernel for d = 128 * NIT with 128-bit accesses: a lane owns the complex slots
 // (2 lane + 64 it, 2 lane + 64 it + 1), the six spectral rows stay in registers between the score
 // and the gradient rows, so every row is requested once and each request / store moves 16 bytes.
+//
+// Relation rows are PRE-REDUCED: the pairs are visited in relation order (`order`, a stable sort of
+// the pair indices by pp), a warp walks KBLK consecutive pairs of that order and keeps the sum of
+// their relation-gradient spectra in registers while the relation does not change; one row per run
+// is written (into the relation row of the run's first violating pair, `runw` = occurrences it
+// stands for, 0 for the other pairs of the run).  With M relations this turns P relation rows
+// (a quarter of G, and the hot-row chunk pass that had to read them) into about P / KBLK + M.
+#ifndef SKGE_PAIR_SPEC4_CTAS
+#define SKGE_PAIR_SPEC4_CTAS 3
+#endif
+// state of the relation run a warp is summing
 template <int NIT>
-__global__ void __launch_bounds__(256, 3) hole_pair_spec4_kernel(const float *__restrict__ Ehat,
-                                                                 const float *__restrict__ Rhat, PairIdx ix,
-                                                                 int64_t P, int af, float margin,
-                                                                 uint8_t *__restrict__ flags, float *__restrict__ G,
-                                                                 int32_t *__restrict__ counts,
-                                                                 int64_t *__restrict__ nviol_accum) {
+struct RelRun {
+  int p = -1, cnt = 0;
+  int64_t head = 0;
+  float4 acc[NIT];
+};
+
+template <int NIT>
+__device__ __forceinline__ void rel_run_flush(RelRun<NIT> &run, float *__restrict__ G, int32_t *__restrict__ runw, int lane) {
+  if (run.p < 0) return;
+  float4 *gr = reinterpret_cast<float4 *>(G + (run.head * 6 + 4) * (128 * NIT));
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) gr[lane + 32 * it] = run.acc[it];
+  if (lane == 0) runw[run.head] = run.cnt;
+  run.p = -1;
+}
+
+// slot-wise products of packed spectra; slot 0 of a row holds two REAL spectral values
+__device__ __forceinline__ float2 spec_mul(float2 a, float2 b, bool real0) {      // a b
+  return real0 ? make_float2(a.x * b.x, a.y * b.y) : cmul(a, b);
+}
+__device__ __forceinline__ float2 spec_mulc(float2 a, float2 b, bool real0) {     // conj(a) b
+  return real0 ? make_float2(a.x * b.x, a.y * b.y) : cmulc(a, b);
+}
+
+// One pair of any shape (both or no entity slot shared, a corrupted relation, ...): six rows through
+// registers, relation rows written per pair (runw = 2 for a folded row, 1 otherwise).  Rare on the
+// fused path, so it is kept out of line: its register needs must not shape the staged kernel.
+template <int NIT>
+__device__ __noinline__ int hole_spec4_generic_pair(const float *__restrict__ Ehat, const float *__restrict__ Rhat,
+                                                    const PairIdx &ix, int64_t i, int af, float margin,
+                                                    uint8_t *__restrict__ flags, float *__restrict__ G,
+                                                    int32_t *__restrict__ runw, int lane) {
   constexpr int d = 128 * NIT, h = d / 2;
-  const int lane = threadIdx.x & 31;
-  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float inv_d = 1.0f / (float)d;
-  int nv = 0;
-  for (int64_t i = warp; i < P; i += nwarps) {
-    if (ix.valid && !ix.valid[i]) {
-      if (lane == 0) flags[i] = 0;
-      continue;
-    }
-    const float4 *S = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.sp[i] * d);
-    const float4 *O = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.op[i] * d);
-    const float4 *Rp = reinterpret_cast<const float4 *>(Rhat + (int64_t)ix.pp[i] * d);
-    const float4 *S2 = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.sn[i] * d);
-    const float4 *O2 = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.on[i] * d);
-    const float4 *Rn = reinterpret_cast<const float4 *>(Rhat + (int64_t)ix.pn[i] * d);
-    float4 s[NIT], o[NIT], rp[NIT], s2[NIT], o2[NIT], rn[NIT];
+  const float4 *S = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.sp[i] * d);
+  const float4 *O = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.op[i] * d);
+  const float4 *Rp = reinterpret_cast<const float4 *>(Rhat + (int64_t)ix.pp[i] * d);
+  const float4 *S2 = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.sn[i] * d);
+  const float4 *O2 = reinterpret_cast<const float4 *>(Ehat + (int64_t)ix.on[i] * d);
+  const float4 *Rn = reinterpret_cast<const float4 *>(Rhat + (int64_t)ix.pn[i] * d);
+  float4 s[NIT], o[NIT], rp[NIT], s2[NIT], o2[NIT], rn[NIT];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int f4 = lane + 32 * it;
-      s[it] = __ldg(S + f4); o[it] = __ldg(O + f4); rp[it] = __ldg(Rp + f4);
-      s2[it] = __ldg(S2 + f4); o2[it] = __ldg(O2 + f4); rn[it] = __ldg(Rn + f4);
-    }
-    float accp = 0.f, accn = 0.f;
+  for (int it = 0; it < NIT; ++it) {
+    const int f4 = lane + 32 * it;
+    s[it] = __ldg(S + f4); o[it] = __ldg(O + f4); rp[it] = __ldg(Rp + f4);
+    s2[it] = __ldg(S2 + f4); o2[it] = __ldg(O2 + f4); rn[it] = __ldg(Rn + f4);
+  }
+  float accp = 0.f, accn = 0.f;
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      // second slot of the float4: always a complex slot
-      const float2 a1 = cmulc(make_float2(s[it].z, s[it].w), make_float2(o[it].z, o[it].w));
-      const float2 b1 = cmulc(make_float2(s2[it].z, s2[it].w), make_float2(o2[it].z, o2[it].w));
-      accp += 2.f * (a1.x * rp[it].z + a1.y * rp[it].w);
-      accn += 2.f * (b1.x * rn[it].z + b1.y * rn[it].w);
-      if (it == 0 && lane == 0) {  // slot 0 = (X_0, X_{d/2}), both real
-        accp += s[it].x * o[it].x * rp[it].x + s[it].y * o[it].y * rp[it].y;
-        accn += s2[it].x * o2[it].x * rn[it].x + s2[it].y * o2[it].y * rn[it].y;
+  for (int it = 0; it < NIT; ++it)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool real0 = it == 0 && u == 0 && lane == 0;
+      const float2 sv = u ? make_float2(s[it].z, s[it].w) : make_float2(s[it].x, s[it].y);
+      const float2 ov = u ? make_float2(o[it].z, o[it].w) : make_float2(o[it].x, o[it].y);
+      const float2 rv = u ? make_float2(rp[it].z, rp[it].w) : make_float2(rp[it].x, rp[it].y);
+      const float2 sv2 = u ? make_float2(s2[it].z, s2[it].w) : make_float2(s2[it].x, s2[it].y);
+      const float2 ov2 = u ? make_float2(o2[it].z, o2[it].w) : make_float2(o2[it].x, o2[it].y);
+      const float2 rv2 = u ? make_float2(rn[it].z, rn[it].w) : make_float2(rn[it].x, rn[it].y);
+      const float2 a1 = spec_mulc(sv, ov, real0), b1 = spec_mulc(sv2, ov2, real0);
+      const float wgt = real0 ? 1.f : 2.f;
+      accp += wgt * (a1.x * rv.x + a1.y * rv.y);
+      accn += wgt * (b1.x * rv2.x + b1.y * rv2.y);
+    }
+  const float raw_p = warp_sum(accp) * inv_d, raw_n = warp_sum(accn) * inv_d;
+  const float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
+  const bool viol = fn + margin > fp;  // skge/hole.py:56
+  if (lane == 0) flags[i] = viol;
+  if (!viol) return 0;
+  const float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // hole.py:66-67
+  float4 *g = reinterpret_cast<float4 *>(G + (int64_t)i * 6 * d);
+  const bool same_s = S == S2, same_o = O == O2, same_r = Rp == Rn;
+  if (lane == 0) runw[i] = same_r ? 2 : 1;
+  constexpr int h4 = h / 2;   // float4 per spectral row
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int f4 = lane + 32 * it;
+    float2 a1[2], a2[2], a3[2], b1[2], b2[2], b3[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool real0 = it == 0 && u == 0 && lane == 0;
+      const float2 sv = u ? make_float2(s[it].z, s[it].w) : make_float2(s[it].x, s[it].y);
+      const float2 ov = u ? make_float2(o[it].z, o[it].w) : make_float2(o[it].x, o[it].y);
+      const float2 rv = u ? make_float2(rp[it].z, rp[it].w) : make_float2(rp[it].x, rp[it].y);
+      const float2 sv2 = u ? make_float2(s2[it].z, s2[it].w) : make_float2(s2[it].x, s2[it].y);
+      const float2 ov2 = u ? make_float2(o2[it].z, o2[it].w) : make_float2(o2[it].x, o2[it].y);
+      const float2 rv2 = u ? make_float2(rn[it].z, rn[it].w) : make_float2(rn[it].x, rn[it].y);
+      a1[u] = spec_mulc(sv, ov, real0);  b1[u] = spec_mulc(sv2, ov2, real0);   // ccorr(s, o)
+      a2[u] = spec_mulc(rv, ov, real0);  b2[u] = spec_mulc(rv2, ov2, real0);   // ccorr(r, o)
+      a3[u] = spec_mul(sv, rv, real0);   b3[u] = spec_mul(sv2, rv2, real0);    // cconv(s, r)
+    }
+    auto put = [&](int row, bool same, const float2 (&x)[2], const float2 (&y)[2]) {
+      const float4 vp = make_float4(gp * x[0].x, gp * x[0].y, gp * x[1].x, gp * x[1].y);
+      const float4 vn = make_float4(gn * y[0].x, gn * y[0].y, gn * y[1].x, gn * y[1].y);
+      float4 *dst = g + row * h4 + f4;
+      if (same) {
+        dst[0] = make_float4(vp.x + vn.x, vp.y + vn.y, vp.z + vn.z, vp.w + vn.w);
       } else {
-        const float2 a0 = cmulc(make_float2(s[it].x, s[it].y), make_float2(o[it].x, o[it].y));
-        const float2 b0 = cmulc(make_float2(s2[it].x, s2[it].y), make_float2(o2[it].x, o2[it].y));
-        accp += 2.f * (a0.x * rp[it].x + a0.y * rp[it].y);
-        accn += 2.f * (b0.x * rn[it].x + b0.y * rn[it].y);
+        dst[0] = vp;
+        dst[h4] = vn;
+      }
+    };
+    put(0, same_s, a2, b2);  // -> sp | sn
+    put(2, same_o, a3, b3);  // -> op | on
+    put(4, same_r, a1, b1);  // -> pp | pn
+  }
+  return 1;
+}
+
+// A corrupted pair whose rows are staged in shared memory: S = E^[sp], O = E^[op], C = the
+// corrupted entity's row, R = R^[pp].  KIND 1: the object is corrupted (sn = sp, on = c),
+// KIND 2: the subject is (sn = c, on = op); pn = pp in both.  Four rows in, three entity gradient
+// rows out (the shared slot's row already folded), the relation gradient joins the warp's run.
+template <int NIT, int KIND>
+__device__ __forceinline__ int hole_spec4_staged_pair(const float4 *S, const float4 *O, const float4 *C,
+                                                      const float4 *R, int64_t i, int prel, int af, float margin,
+                                                      uint8_t *__restrict__ flags, float *__restrict__ G,
+                                                      int32_t *__restrict__ runw, RelRun<NIT> &run, int lane) {
+  constexpr int d = 128 * NIT, h4 = d / 4;
+  const float inv_d = 1.0f / (float)d;
+  // (the rows are read from the stage twice, for the scores and for the gradient rows: one 128-bit
+  //  slice of each row is live at a time instead of the whole row)
+  float accp = 0.f, accn = 0.f;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int f4 = lane + 32 * it;
+    const float4 s4 = S[f4], o4 = O[f4], c4 = C[f4], r4 = R[f4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool real0 = it == 0 && u == 0 && lane == 0;
+      const float2 sv = u ? make_float2(s4.z, s4.w) : make_float2(s4.x, s4.y);
+      const float2 ov = u ? make_float2(o4.z, o4.w) : make_float2(o4.x, o4.y);
+      const float2 cv = u ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
+      const float2 rv = u ? make_float2(r4.z, r4.w) : make_float2(r4.x, r4.y);
+      const float2 a1 = spec_mulc(sv, ov, real0);
+      const float2 b1 = KIND == 1 ? spec_mulc(sv, cv, real0) : spec_mulc(cv, ov, real0);
+      const float wgt = real0 ? 1.f : 2.f;
+      accp += wgt * (a1.x * rv.x + a1.y * rv.y);
+      accn += wgt * (b1.x * rv.x + b1.y * rv.y);
+    }
+  }
+  const float raw_p = warp_sum(accp) * inv_d, raw_n = warp_sum(accn) * inv_d;
+  const float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
+  const bool viol = fn + margin > fp;  // skge/hole.py:56
+  if (lane == 0) flags[i] = viol;
+  if (!viol) return 0;
+  const float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // hole.py:66-67
+  if (run.p != prel) {
+    rel_run_flush<NIT>(run, G, runw, lane);
+    run.p = prel; run.head = i; run.cnt = 0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) run.acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  run.cnt += 2;   // the positive's and the negative's occurrence of the relation row
+  if (i != run.head && lane == 0) runw[i] = 0;
+  float4 *g = reinterpret_cast<float4 *>(G + (int64_t)i * 6 * d);
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int f4 = lane + 32 * it;
+    const float4 s4 = S[f4], o4 = O[f4], c4 = C[f4], r4 = R[f4];
+    float2 x0[2], x1[2], x2[2], rel[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool real0 = it == 0 && u == 0 && lane == 0;
+      const float2 sv = u ? make_float2(s4.z, s4.w) : make_float2(s4.x, s4.y);
+      const float2 ov = u ? make_float2(o4.z, o4.w) : make_float2(o4.x, o4.y);
+      const float2 cv = u ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
+      const float2 rv = u ? make_float2(r4.z, r4.w) : make_float2(r4.x, r4.y);
+      if (KIND == 1) {
+        const float2 wv = make_float2(gp * ov.x + gn * cv.x, gp * ov.y + gn * cv.y);
+        const float2 t = spec_mul(sv, rv, real0);                                  // cconv(s, r)
+        x0[u] = spec_mulc(rv, wv, real0);                                          // -> sp (= sn): ccorr(r, gp o + gn c)
+        x1[u] = make_float2(gp * t.x, gp * t.y);                                   // -> op
+        x2[u] = make_float2(gn * t.x, gn * t.y);                                   // -> on
+        rel[u] = spec_mulc(sv, wv, real0);                                         // -> pp: ccorr(s, gp o + gn c)
+      } else {
+        const float2 wv = make_float2(gp * sv.x + gn * cv.x, gp * sv.y + gn * cv.y);
+        const float2 t = spec_mulc(rv, ov, real0);                                 // ccorr(r, o)
+        x0[u] = make_float2(gp * t.x, gp * t.y);                                   // -> sp
+        x1[u] = make_float2(gn * t.x, gn * t.y);                                   // -> sn
+        x2[u] = spec_mul(wv, rv, real0);                                           // -> op (= on): cconv(gp s + gn c, r)
+        rel[u] = spec_mulc(wv, ov, real0);                                         // -> pp: ccorr(gp s + gn c, o)
       }
     }
-    const float raw_p = warp_sum(accp) * inv_d, raw_n = warp_sum(accn) * inv_d;
-    const float fp = act_f(af, raw_p), fn = act_f(af, raw_n);
-    const bool viol = fn + margin > fp;  // skge/hole.py:56
-    if (lane == 0) flags[i] = viol;
-    if (!viol) continue;
-    ++nv;
-    const float gp = -act_g_given_f(af, fp), gn = act_g_given_f(af, fn);  // hole.py:66-67
-    float4 *g = reinterpret_cast<float4 *>(G + (int64_t)i * 6 * d);
-    const bool same_s = S == S2, same_o = O == O2, same_r = Rp == Rn;
-    constexpr int h4 = h / 2;   // float4 per spectral row
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int f4 = lane + 32 * it;
-      const bool real0 = it == 0 && lane == 0;
-      float2 a1[2], a2[2], a3[2], b1[2], b2[2], b3[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float2 sv = u ? make_float2(s[it].z, s[it].w) : make_float2(s[it].x, s[it].y);
-        const float2 ov = u ? make_float2(o[it].z, o[it].w) : make_float2(o[it].x, o[it].y);
-        const float2 rv = u ? make_float2(rp[it].z, rp[it].w) : make_float2(rp[it].x, rp[it].y);
-        const float2 sv2 = u ? make_float2(s2[it].z, s2[it].w) : make_float2(s2[it].x, s2[it].y);
-        const float2 ov2 = u ? make_float2(o2[it].z, o2[it].w) : make_float2(o2[it].x, o2[it].y);
-        const float2 rv2 = u ? make_float2(rn[it].z, rn[it].w) : make_float2(rn[it].x, rn[it].y);
-        if (u == 0 && real0) {
-          a1[u] = make_float2(sv.x * ov.x, sv.y * ov.y);     b1[u] = make_float2(sv2.x * ov2.x, sv2.y * ov2.y);
-          a2[u] = make_float2(rv.x * ov.x, rv.y * ov.y);     b2[u] = make_float2(rv2.x * ov2.x, rv2.y * ov2.y);
-          a3[u] = make_float2(sv.x * rv.x, sv.y * rv.y);     b3[u] = make_float2(sv2.x * rv2.x, sv2.y * rv2.y);
-        } else {
-          a1[u] = cmulc(sv, ov);  b1[u] = cmulc(sv2, ov2);   // ccorr(s, o)
-          a2[u] = cmulc(rv, ov);  b2[u] = cmulc(rv2, ov2);   // ccorr(r, o)
-          a3[u] = cmul(sv, rv);   b3[u] = cmul(sv2, rv2);    // cconv(s, r)
-        }
+    // G rows of a pair: 0 / 1 -> sp / sn, 2 / 3 -> op / on (a shared slot uses the lower row only)
+    g[(KIND == 1 ? 0 : 0) * h4 + f4] = make_float4(x0[0].x, x0[0].y, x0[1].x, x0[1].y);
+    g[(KIND == 1 ? 2 : 1) * h4 + f4] = make_float4(x1[0].x, x1[0].y, x1[1].x, x1[1].y);
+    g[(KIND == 1 ? 3 : 2) * h4 + f4] = make_float4(x2[0].x, x2[0].y, x2[1].x, x2[1].y);
+    run.acc[it].x += rel[0].x; run.acc[it].y += rel[0].y; run.acc[it].z += rel[1].x; run.acc[it].w += rel[1].y;
+  }
+  return 1;
+}
+
+__host__ __device__ constexpr size_t pair_spec4_smem_bytes(int nit) { return 128 + (size_t)8 * 2 * 4 * 512 * nit; }
+
+// Driver: a warp takes KBLK = 32 consecutive pairs of the relation order, one per lane for the index
+// work.  The four rows of a corrupted pair (kinds 1 and 2) come in by bulk-TMA copies, double
+// buffered per warp: the copies of the next pair are in flight while this one is computed.  Pairs of
+// any other shape (both or no entity slot shared, a corrupted relation) take the six-row register
+// path above afterwards.
+template <int NIT>
+__global__ void __launch_bounds__(256, SKGE_PAIR_SPEC4_CTAS) hole_pair_spec4_kernel(
+    const float *__restrict__ Ehat, const float *__restrict__ Rhat, PairIdx ix, int64_t P, int af, float margin,
+    uint8_t *__restrict__ flags, float *__restrict__ G, int32_t *__restrict__ counts, int64_t *__restrict__ nviol_accum,
+    const int32_t *__restrict__ order, int32_t *__restrict__ runw) {
+  extern __shared__ __align__(128) unsigned char pair_smem[];
+  constexpr int KBLK = 32, d = 128 * NIT, ROW4 = d / 4;
+  constexpr uint32_t ROWB = d * 4;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(pair_smem) + 2 * w;
+  float4 *buf = reinterpret_cast<float4 *>(pair_smem + 128) + (size_t)w * 2 * 4 * ROW4;   // [stage][slot][ROW4]
+  if (lane == 0) {
+    ptx::mbar_init(bars, 1);
+    ptx::mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+  int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t nblk = (P + KBLK - 1) / KBLK;
+  uint32_t issued = 0, done = 0;
+  int nv = 0;
+  for (int64_t blk = warp; blk < nblk; blk += nwarps) {
+    // lane l: the indices of pair l of the block
+    const int64_t pos = blk * KBLK + lane;
+    int my_i = -1, kind = 0, rowa = 0, rowb = 0, rowc = 0, rowr = 0;
+    if (pos < P) {
+      my_i = order[pos];
+      if (ix.valid && !ix.valid[my_i]) {
+        flags[my_i] = 0;
+      } else {
+        const int sp = ix.sp[my_i], op = ix.op[my_i], pp = ix.pp[my_i];
+        const int sn = ix.sn[my_i], on = ix.on[my_i], pn = ix.pn[my_i];
+        rowa = sp; rowb = op; rowr = pp;
+        if (pp == pn && sp == sn && op != on) { kind = 1; rowc = on; }
+        else if (pp == pn && op == on && sp != sn) { kind = 2; rowc = sn; }
+        else kind = 3;
       }
-      auto put = [&](int row, bool same, const float2 (&x)[2], const float2 (&y)[2]) {
-        const float4 vp = make_float4(gp * x[0].x, gp * x[0].y, gp * x[1].x, gp * x[1].y);
-        const float4 vn = make_float4(gn * y[0].x, gn * y[0].y, gn * y[1].x, gn * y[1].y);
-        float4 *dst = g + row * h4 + f4;
-        if (same) {
-          dst[0] = make_float4(vp.x + vn.x, vp.y + vn.y, vp.z + vn.z, vp.w + vn.w);
-        } else {
-          dst[0] = vp;
-          dst[h4] = vn;
-        }
-      };
-      put(0, same_s, a2, b2);  // -> sp | sn
-      put(2, same_o, a3, b3);  // -> op | on
-      put(4, same_r, a1, b1);  // -> pp | pn
+    }
+    RelRun<NIT> run;
+    auto issue = [&](int t) {
+      const int st = issued & 1;
+      const int ra = __shfl_sync(kFull, rowa, t), rb = __shfl_sync(kFull, rowb, t);
+      const int rcc = __shfl_sync(kFull, rowc, t), rr = __shfl_sync(kFull, rowr, t);
+      // the stage was last read by this warp's own (generic-proxy) loads
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) ptx::mbar_expect_tx(bars + st, 4 * ROWB);
+      __syncwarp();
+      if (lane < 4) {
+        const float *src = lane == 3 ? Rhat + (int64_t)rr * d : Ehat + (int64_t)(lane == 0 ? ra : lane == 1 ? rb : rcc) * d;
+        ptx::bulk_g2s(buf + (st * 4 + lane) * ROW4, src, ROWB, bars + st);
+      }
+      ++issued;
+    };
+    unsigned m = __ballot_sync(kFull, kind == 1 || kind == 2);
+    if (m) issue(__ffs(m) - 1);
+    while (m) {
+      const int t = __ffs(m) - 1;
+      m &= m - 1;
+      if (m) issue(__ffs(m) - 1);
+      const int st = done & 1;
+      ptx::mbar_wait(bars + st, (done >> 1) & 1);
+      ++done;
+      const int64_t i = __shfl_sync(kFull, my_i, t);
+      const int prel = __shfl_sync(kFull, rowr, t);
+      const float4 *sl = buf + st * 4 * ROW4;
+      if (__shfl_sync(kFull, kind, t) == 1)
+        nv += hole_spec4_staged_pair<NIT, 1>(sl, sl + ROW4, sl + 2 * ROW4, sl + 3 * ROW4, i, prel, af, margin, flags, G, runw, run, lane);
+      else
+        nv += hole_spec4_staged_pair<NIT, 2>(sl, sl + ROW4, sl + 2 * ROW4, sl + 3 * ROW4, i, prel, af, margin, flags, G, runw, run, lane);
+    }
+    rel_run_flush<NIT>(run, G, runw, lane);
+    unsigned gm = __ballot_sync(kFull, kind == 3);
+    while (gm) {
+      const int t = __ffs(gm) - 1;
+      gm &= gm - 1;
+      nv += hole_spec4_generic_pair<NIT>(Ehat, Rhat, ix, __shfl_sync(kFull, my_i, t), af, margin, flags, G, runw, lane);
     }
   }
   if (lane == 0 && nv) {
@@ -724,7 +920,7 @@ struct PairBuffers {
 static size_t pair_ws_bytes(int64_t P, int d, int rows, int nroles) {
   if (P < 1) P = 1;
   return align_up((size_t)P) + align_up((size_t)P * rows * d * sizeof(float)) +
-         seg_workspace_bytes((int64_t)nroles * P, d) + 1024;
+         seg_workspace_bytes((int64_t)nroles * P, d) + order_workspace_bytes(P) + align_up((size_t)P * 4) + 1024;
 }
 
 // model: 0 TransE, 1 HolE
@@ -748,6 +944,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
     return SKGE_EWORKSPACE;
   }
   SKGE_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
+  int32_t *runw = nullptr;
   if (model == 0) {
     int64_t blocks = (P + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
@@ -771,9 +968,29 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
     int64_t blocks = (P + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (d == 128 || d == 256) {
-      // 128-bit accesses, register-resident rows
-      if (d == 128) hole_pair_spec4_kernel<1><<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum);
-      else hole_pair_spec4_kernel<2><<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum);
+      // 128-bit accesses, register-resident rows, relation rows pre-reduced over relation-ordered pairs
+      const int32_t *order = nullptr;
+      int kb = 1;
+      while (((int64_t)1 << kb) < M) ++kb;
+      if (int rc = order_by_key(ix.pp, P, kb, ar, st, &order)) return rc;
+      runw = ar.take<int32_t>(P);
+      if (!ar.ok()) {
+        set_error("workspace too small: need > %zu bytes, have %zu", ar.off, ar.cap);
+        return SKGE_EWORKSPACE;
+      }
+      SKGE_REQUIRE(((reinterpret_cast<uintptr_t>(Ehat) | reinterpret_cast<uintptr_t>(Rhat)) & 15) == 0,
+                   "spectral tables must be 16-byte aligned");
+      blocks = ((P + 31) / 32 + 7) / 8;
+      if (blocks > kNumSMs * SKGE_PAIR_SPEC4_CTAS) blocks = kNumSMs * SKGE_PAIR_SPEC4_CTAS;
+      if (d == 128) {
+        const size_t smem = pair_spec4_smem_bytes(1);
+        SKGE_CUDA(cudaFuncSetAttribute(hole_pair_spec4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hole_pair_spec4_kernel<1><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw);
+      } else {
+        const size_t smem = pair_spec4_smem_bytes(2);
+        SKGE_CUDA(cudaFuncSetAttribute(hole_pair_spec4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hole_pair_spec4_kernel<2><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw);
+      }
     } else {
       hole_pair_spec_kernel<<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, d, l1_or_af, margin, flags, G, counts,
                                                         nviol_accum);
@@ -816,6 +1033,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
       rm.idx[r] = idx[r]; rm.is_rel[r] = isrel[r]; rm.grow[r] = grow[r]; rm.gsign[r] = 1.f;
       rm.twin[r] = r ^ 1;  // the kernels above fold rows (2q, 2q + 1) when the ids coincide
     }
+    if (runw) { rm.runw = runw; rm.runw_role = 4; }
   }
   rm.nroles = 6;
   ParamDesc pd[2];

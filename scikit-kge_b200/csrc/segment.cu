@@ -27,6 +27,7 @@ __global__ void build_keys_kernel(RoleMap rm, const uint8_t *__restrict__ flags,
     const int q = rm.twin[r];
     const bool same = q >= 0 && rm.idx[q][i] == id;
     if (same && q < r) ok = false;  // folded into the twin's row
+    if (rm.runw && r == rm.runw_role && ok) ok = rm.runw[i] > 0;  // folded into the head of its run
     keys[t] = ok ? id + (rm.is_rel[r] ? N : 0) : sentinel;
     vals[t] = (int32_t)(i * 16 + (same && q > r ? 8 : 0) + r);
   }
@@ -81,6 +82,31 @@ static size_t cub_sort_bytes(int64_t L) {
                                   (const int32_t *)nullptr, (int32_t *)nullptr, (int)L, 0, 32);
   return bytes;
 }
+__global__ void iota_kernel(int32_t *v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (int32_t)i;
+}
+size_t order_workspace_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return 3 * align_up((size_t)n * 4) + align_up(cub_sort_bytes(n)) + 256;
+}
+int order_by_key(const int32_t *keys, int64_t n, int key_bits, Arena &ar, cudaStream_t st, const int32_t **order) {
+  SKGE_REQUIRE(n > 0 && n < ((int64_t)1 << 31), "bad length");
+  int32_t *keys_out = ar.take<int32_t>(n), *vals_in = ar.take<int32_t>(n), *vals_out = ar.take<int32_t>(n);
+  size_t tb = cub_sort_bytes(n);
+  void *tmp = ar.take<char>(tb);
+  if (!ar.ok()) {
+    set_error("workspace too small: need %zu bytes, have %zu", ar.off, ar.cap);
+    return SKGE_EWORKSPACE;
+  }
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  iota_kernel<<<blocks, 256, 0, st>>>(vals_in, n);
+  SKGE_LAUNCH_CHECK();
+  SKGE_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys_out, vals_in, vals_out, (int)n, 0, key_bits, st));
+  *order = vals_out;
+  return 0;
+}
+
 static size_t cub_scan_bytes(int64_t L) {
   size_t bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (int)L);
@@ -236,7 +262,15 @@ struct SegArgs {
   int long_seg_cap, long_chunk_cap;
   int seg_chunk;        // segments longer than this are reduced chunk-wise
   int spec_logd;        // > 0: G rows are packed spectra of length 1 << spec_logd (see fft.cuh)
+  const int32_t *runw;  // RoleMap::runw (nullable)
+  int runw_role;
 };
+
+// occurrences a sorted payload stands for: a run sum (RoleMap::runw), a folded twin row (2) or 1
+__device__ __forceinline__ int occ_weight(const SegArgs &a, int val) {
+  if (a.runw && (val & 7) == a.runw_role) return a.runw[val >> 4];
+  return 1 + ((val >> 3) & 1);
+}
 
 // shared memory of the spectral mode: twiddles [d/2] float2, then per warp two complex
 // buffers of d/2 float2 (2 d floats)
@@ -259,11 +293,11 @@ template <int VEC, int MAXC, int BATCH>
 __device__ __forceinline__ int accumulate_rows(const SegArgs &a, int beg, int end, int lane,
                                                float (&acc)[MAXC][VEC]) {
   const int d = a.d;
-  int folded = 0;
+  int occ = 0;
   for (int j0 = beg; j0 < end; j0 += 32) {
     const int cnt = min(32, end - j0);
     const int myval = lane < cnt ? a.vals[j0 + lane] : 0;
-    folded += __popc(__ballot_sync(kFull, (myval & 8) != 0));
+    occ += __reduce_add_sync(kFull, lane < cnt ? occ_weight(a, myval) : 0);
     for (int t0 = 0; t0 < cnt; t0 += BATCH) {
       float tmp[BATCH][MAXC][VEC];
       float sgn[BATCH];
@@ -292,7 +326,7 @@ __device__ __forceinline__ int accumulate_rows(const SegArgs &a, int beg, int en
         }
     }
   }
-  return (end - beg) + folded;
+  return occ;
 }
 
 // acc holds the SUM over the n occurrences of segment seg: take the mean and either apply
@@ -581,11 +615,11 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
     for (int c = 0; c < 2; ++c)
 #pragma unroll
       for (int v = 0; v < 4; ++v) acc[c][v] = 0.f;
-    int folded = 0;
+    int occ = 0;
     for (int j0 = beg; j0 < end; j0 += CAP) {
       const int cnt = min(CAP, end - j0);
       const int myval = lane < cnt ? a.vals[j0 + lane] : 0;
-      folded += __popc(__ballot_sync(kFull, (myval & 8) != 0));
+      occ += __reduce_add_sync(kFull, lane < cnt ? occ_weight(a, myval) : 0);
       const bool first = j0 == beg;
       // the slots were last touched by this warp's own (generic-proxy) reads and writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -610,7 +644,6 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
         acc[1][2] = fmaf(sgn, u1.z, acc[1][2]); acc[1][3] = fmaf(sgn, u1.w, acc[1][3]);
       }
     }
-    const int occ = n + folded;
     if constexpr (SPEC) {
       // summed packed spectrum -> time domain (registers), update, -> spectrum of the updated row
       float2 v[4];
@@ -848,6 +881,8 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
     return SKGE_EWORKSPACE;
   }
   SKGE_CUDA(cudaMemsetAsync(a.long_meta, 0, 16, st));
+  a.runw = rm.runw;
+  a.runw_role = rm.runw_role;
   a.spec_logd = 0;
   if (spectral) {
     a.spec_logd = log2_exact(d);

@@ -22,7 +22,17 @@ struct RoleMap {
   float gsign[kMaxRoles];
   int twin[kMaxRoles] = {-1, -1, -1, -1, -1, -1};
   int nroles;
+  // Run weights (nullable): the producer has pre-summed the rows that role `runw_role` of several units
+  // would send to the same table row (consecutive pairs of one relation) into the row of the run's first
+  // unit.  runw[i] > 0: unit i carries such a sum standing for runw[i] occurrences; runw[i] == 0: unit i's
+  // occurrence of that role is contained in an earlier unit's row and is dropped.
+  const int32_t *runw = nullptr;
+  int runw_role = -1;
 };
+
+// order[] = the indices 0..n-1 sorted (stably) by keys[] (values below 1 << key_bits)
+size_t order_workspace_bytes(int64_t n);
+int order_by_key(const int32_t *keys, int64_t n, int key_bits, Arena &ar, cudaStream_t st, const int32_t **order);
 
 // One parameter table (E, or the relation table R).
 struct ParamDesc {
