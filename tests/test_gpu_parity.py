@@ -366,6 +366,83 @@ def test_wn18_shaped_minibatch_against_oracle(kind, d, margin, l1, opt):
     np.testing.assert_allclose(np.asarray(m.R), R, **PARAM_TOL)
 
 
+@pytest.mark.parametrize('kind,opt', [('hole', 'sgd'), ('hole', 'adagrad'), ('transe', 'sgd'), ('transe', 'adagrad')])
+def test_large_minibatch_staged_update_against_oracle(kind, opt):
+    """More than 2^18 occurrences of 1 KB rows (d = 256): the bulk-TMA staged segmented update
+    (csrc/segment.cu::seg_reduce_bulk_kernel), for HolE with the register-resident transforms and
+    the relation rows pre-reduced over relation-ordered pairs, a hub entity and a frequent
+    relation on the chunked path, pairs of every sharing pattern mixed in."""
+    import skge
+    from skge.param import AdaGrad, SGD
+    from skge._modelutil import idx_tensor
+    N, M, B, d = 30000, 40, 23000, 256
+    E0, R0, pos, neg = _full_size_batch(kind, N, M, d, B, seed=7 + (kind == 'hole'))
+    rng = np.random.default_rng(3)
+    P = len(pos)
+    assert 6 * P > (1 << 18)
+    hub = rng.choice(P, 3000, replace=False)
+    pos[hub, 0] = 17                                  # hub subject
+    neg[hub, 0] = np.where(neg[hub, 1] != pos[hub, 1], 17, neg[hub, 0])   # keep each pair's corruption pattern
+    pos[hub[:1500], 2] = 5                            # frequent relation
+    neg[hub[:1500], 2] = 5
+    odd = rng.choice(P, 600, replace=False)           # other shapes: predicate / both entities corrupted, neg == pos
+    neg[odd[:200], 2] = rng.integers(M, size=200)
+    neg[odd[200:400], 0] = rng.integers(N, size=200)
+    neg[odd[200:400], 1] = rng.integers(N, size=200)
+    neg[odd[400:]] = pos[odd[400:]]
+    margin = 2.0 if kind == 'transe' else 0.2
+    if kind == 'transe':
+        m = skge.TransE((N, N, M), d, l1=True)
+        ograds, info = orc.transe_pairwise_gradients(E0, R0, pos, neg, margin, True)
+    else:
+        m = skge.HolE((N, N, M), d)
+        ograds, info = orc.hole_pairwise_gradients(E0, R0, pos, neg, margin, 'sigmoid', 0.0)
+    near = _near_margin(info, margin, 1e-5)
+    keep = ~near                                      # pairs on the margin may flip between fp32 and float64
+    if near.any():
+        pos, neg = pos[keep], neg[keep]
+        assert 6 * len(pos) > (1 << 18)
+        if kind == 'transe':
+            ograds, info = orc.transe_pairwise_gradients(E0, R0, pos, neg, margin, True)
+        else:
+            ograds, info = orc.hole_pairwise_gradients(E0, R0, pos, neg, margin, 'sigmoid', 0.0)
+    m.E[...] = E0
+    m.R[...] = R0
+    trn = skge.PairwiseStochasticTrainer(m, nbatches=1, margin=margin, learning_rate=0.1,
+                                         param_update=AdaGrad if opt == 'adagrad' else SGD)
+    trn._setup_fused()
+    if kind == 'hole':
+        m._prepare_fused()
+        assert m._spec is not None
+    m._fused_pair_step(trn._updaters, tuple(idx_tensor(pos[:, i]) for i in range(3)),
+                       tuple(idx_tensor(neg[:, i]) for i in range(3)), None, trn._counts, trn._nviol_dev)
+    nv, ue, ur, _ = trn._counts.tolist()
+    assert nv == info['nviolations'] and ue == len(ograds['E'][1]) and ur == len(ograds['R'][1])
+    E, R = E0.copy(), R0.copy()
+    post = 'normalize' if kind == 'transe' else 'normless1'
+    if opt == 'sgd':
+        orc.sgd_update(E, ograds['E'][0], ograds['E'][1], 0.1, post)
+        orc.sgd_update(R, ograds['R'][0], ograds['R'][1], 0.1, None)
+        np.testing.assert_allclose(np.asarray(m.E), E, **PARAM_TOL)
+        np.testing.assert_allclose(np.asarray(m.R), R, **PARAM_TOL)
+    else:
+        orc.adagrad_update(E, np.zeros_like(E), ograds['E'][0], ograds['E'][1], 0.1, post)
+        orc.adagrad_update(R, np.zeros_like(R), ograds['R'][0], ograds['R'][1], 0.1, None)
+        # AdaGrad's first step is discontinuous in g near 0 (see test_wn18_shaped_minibatch_against_oracle)
+        gotE, ok = np.asarray(m.E, dtype=np.float64), np.ones(E.shape[0], dtype=bool)
+        ok[ograds['E'][1]] = ((np.abs(ograds['E'][0]) > 1e-6) | (ograds['E'][0] == 0)).all(axis=1)
+        assert (~ok).mean() < 2e-2
+        np.testing.assert_allclose(gotE[ok], E[ok], **PARAM_TOL)
+        okr = np.ones(R.shape[0], dtype=bool)
+        okr[ograds['R'][1]] = ((np.abs(ograds['R'][0]) > 1e-6) | (ograds['R'][0] == 0)).all(axis=1)
+        np.testing.assert_allclose(np.asarray(m.R, dtype=np.float64)[okr], R[okr], **PARAM_TOL)
+    if kind == 'hole':       # the spectra the step maintains must be the transforms of the updated tables
+        from skge import kernels
+        for tab, hat in ((m.E.data, m._spec[0]), (m.R.data, m._spec[1])):
+            ref = kernels.hole_spectra(tab)
+            torch.testing.assert_close(hat, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
+
+
 @pytest.mark.parametrize('kind,d', [('transe', 50), ('transe', 256), ('hole', 64), ('hole', 150)])
 def test_hot_rows_use_the_chunked_segment_reduction(kind, d):
     """Rows with thousands of occurrences in one minibatch (a hub entity, a frequent
@@ -575,13 +652,14 @@ def test_fused_step_is_bit_reproducible(kind, d):
             assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize('d', [150, 64, 24])
+@pytest.mark.parametrize('d', [150, 64, 24, 128, 256])
 def test_hole_twin_rows_fold_for_every_sharing_pattern(d):
     """The HolE kernels sum the positive's and the negative's contribution to a shared slot
     into one gradient row that counts twice in the mean.  Negatives that share 0, 1, 2 or all 3
     slots with their positive (supplied-negatives mode, predicate corruption, a pair scored
     against itself) must all give the reference's means: direct (d = 150, 24), shared-memory FFT
-    (d = 64) and, for d = 64, the frequency-domain fused step."""
+    (d = 64, 128, 256) and, for those, the frequency-domain fused step (d = 128 / 256: staged pairs
+    of the two corrupted shapes, every other shape through the six-row path)."""
     import skge
     from skge.param import SGD
     from skge._modelutil import idx_tensor
@@ -626,7 +704,7 @@ def test_hole_twin_rows_fold_for_every_sharing_pattern(d):
     t2 = skge.PairwiseStochasticTrainer(m2, nbatches=1, margin=margin, learning_rate=0.1, param_update=SGD)
     t2._setup_fused()
     m2._prepare_fused()
-    assert (m2._spec is not None) == (d == 64)
+    assert (m2._spec is not None) == (d in (64, 128, 256))
     m2._fused_pair_step(t2._updaters, tuple(idx_tensor(pos[:, i]) for i in range(3)),
                         tuple(idx_tensor(neg[:, i]) for i in range(3)), None, t2._counts, t2._nviol_dev)
     assert int(t2._nviol_dev.item()) == info['nviolations']
