@@ -737,7 +737,8 @@ template <int NIT, int KIND>
 __device__ __forceinline__ int hole_spec4_staged_pair(const float4 *S, const float4 *O, const float4 *C,
                                                       const float4 *R, int64_t i, int prel, int af, float margin,
                                                       uint8_t *__restrict__ flags, float *__restrict__ G,
-                                                      int32_t *__restrict__ runw, RelRun<NIT> &run, int lane) {
+                                                      int32_t *__restrict__ runw, float *__restrict__ coef,
+                                                      RelRun<NIT> &run, int lane) {
   constexpr int d = 128 * NIT, h4 = d / 4;
   const float inv_d = 1.0f / (float)d;
   // (the rows are read from the stage twice, for the scores and for the gradient rows: one 128-bit
@@ -774,13 +775,16 @@ __device__ __forceinline__ int hole_spec4_staged_pair(const float4 *S, const flo
     for (int it = 0; it < NIT; ++it) run.acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   run.cnt += 2;   // the positive's and the negative's occurrence of the relation row
-  if (i != run.head && lane == 0) runw[i] = 0;
+  if (lane == 0) {
+    if (i != run.head) runw[i] = 0;
+    *reinterpret_cast<float2 *>(coef + 2 * i) = make_float2(gp, gn);
+  }
   float4 *g = reinterpret_cast<float4 *>(G + (int64_t)i * 6 * d);
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int f4 = lane + 32 * it;
     const float4 s4 = S[f4], o4 = O[f4], c4 = C[f4], r4 = R[f4];
-    float2 x0[2], x1[2], x2[2], rel[2];
+    float2 x0[2], x2[2], rel[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const bool real0 = it == 0 && u == 0 && lane == 0;
@@ -790,24 +794,18 @@ __device__ __forceinline__ int hole_spec4_staged_pair(const float4 *S, const flo
       const float2 rv = u ? make_float2(r4.z, r4.w) : make_float2(r4.x, r4.y);
       if (KIND == 1) {
         const float2 wv = make_float2(gp * ov.x + gn * cv.x, gp * ov.y + gn * cv.y);
-        const float2 t = spec_mul(sv, rv, real0);                                  // cconv(s, r)
-        x0[u] = spec_mulc(rv, wv, real0);                                          // -> sp (= sn): ccorr(r, gp o + gn c)
-        x1[u] = make_float2(gp * t.x, gp * t.y);                                   // -> op
-        x2[u] = make_float2(gn * t.x, gn * t.y);                                   // -> on
-        rel[u] = spec_mulc(sv, wv, real0);                                         // -> pp: ccorr(s, gp o + gn c)
+        x0[u] = spec_mulc(rv, wv, real0);     // row 0 -> sp (= sn): ccorr(r, gp o + gn c)
+        x2[u] = spec_mul(sv, rv, real0);      // row 2 = cconv(s, r): -> op times gp, -> on times gn (RoleMap::coef)
+        rel[u] = spec_mulc(sv, wv, real0);    // -> pp: ccorr(s, gp o + gn c)
       } else {
         const float2 wv = make_float2(gp * sv.x + gn * cv.x, gp * sv.y + gn * cv.y);
-        const float2 t = spec_mulc(rv, ov, real0);                                 // ccorr(r, o)
-        x0[u] = make_float2(gp * t.x, gp * t.y);                                   // -> sp
-        x1[u] = make_float2(gn * t.x, gn * t.y);                                   // -> sn
-        x2[u] = spec_mul(wv, rv, real0);                                           // -> op (= on): cconv(gp s + gn c, r)
-        rel[u] = spec_mulc(wv, ov, real0);                                         // -> pp: ccorr(gp s + gn c, o)
+        x0[u] = spec_mulc(rv, ov, real0);     // row 0 = ccorr(r, o): -> sp times gp, -> sn times gn
+        x2[u] = spec_mul(wv, rv, real0);      // row 2 -> op (= on): cconv(gp s + gn c, r)
+        rel[u] = spec_mulc(wv, ov, real0);    // -> pp: ccorr(gp s + gn c, o)
       }
     }
-    // G rows of a pair: 0 / 1 -> sp / sn, 2 / 3 -> op / on (a shared slot uses the lower row only)
-    g[(KIND == 1 ? 0 : 0) * h4 + f4] = make_float4(x0[0].x, x0[0].y, x0[1].x, x0[1].y);
-    g[(KIND == 1 ? 2 : 1) * h4 + f4] = make_float4(x1[0].x, x1[0].y, x1[1].x, x1[1].y);
-    g[(KIND == 1 ? 3 : 2) * h4 + f4] = make_float4(x2[0].x, x2[0].y, x2[1].x, x2[1].y);
+    g[f4] = make_float4(x0[0].x, x0[0].y, x0[1].x, x0[1].y);
+    g[2 * h4 + f4] = make_float4(x2[0].x, x2[0].y, x2[1].x, x2[1].y);
     run.acc[it].x += rel[0].x; run.acc[it].y += rel[0].y; run.acc[it].z += rel[1].x; run.acc[it].w += rel[1].y;
   }
   return 1;
@@ -824,7 +822,7 @@ template <int NIT>
 __global__ void __launch_bounds__(256, SKGE_PAIR_SPEC4_CTAS) hole_pair_spec4_kernel(
     const float *__restrict__ Ehat, const float *__restrict__ Rhat, PairIdx ix, int64_t P, int af, float margin,
     uint8_t *__restrict__ flags, float *__restrict__ G, int32_t *__restrict__ counts, int64_t *__restrict__ nviol_accum,
-    const int32_t *__restrict__ order, int32_t *__restrict__ runw) {
+    const int32_t *__restrict__ order, int32_t *__restrict__ runw, float *__restrict__ coef) {
   extern __shared__ __align__(128) unsigned char pair_smem[];
   constexpr int KBLK = 32, d = 128 * NIT, ROW4 = d / 4;
   constexpr uint32_t ROWB = d * 4;
@@ -889,9 +887,9 @@ __global__ void __launch_bounds__(256, SKGE_PAIR_SPEC4_CTAS) hole_pair_spec4_ker
       const int prel = __shfl_sync(kFull, rowr, t);
       const float4 *sl = buf + st * 4 * ROW4;
       if (__shfl_sync(kFull, kind, t) == 1)
-        nv += hole_spec4_staged_pair<NIT, 1>(sl, sl + ROW4, sl + 2 * ROW4, sl + 3 * ROW4, i, prel, af, margin, flags, G, runw, run, lane);
+        nv += hole_spec4_staged_pair<NIT, 1>(sl, sl + ROW4, sl + 2 * ROW4, sl + 3 * ROW4, i, prel, af, margin, flags, G, runw, coef, run, lane);
       else
-        nv += hole_spec4_staged_pair<NIT, 2>(sl, sl + ROW4, sl + 2 * ROW4, sl + 3 * ROW4, i, prel, af, margin, flags, G, runw, run, lane);
+        nv += hole_spec4_staged_pair<NIT, 2>(sl, sl + ROW4, sl + 2 * ROW4, sl + 3 * ROW4, i, prel, af, margin, flags, G, runw, coef, run, lane);
     }
     rel_run_flush<NIT>(run, G, runw, lane);
     unsigned gm = __ballot_sync(kFull, kind == 3);
@@ -920,7 +918,8 @@ struct PairBuffers {
 static size_t pair_ws_bytes(int64_t P, int d, int rows, int nroles) {
   if (P < 1) P = 1;
   return align_up((size_t)P) + align_up((size_t)P * rows * d * sizeof(float)) +
-         seg_workspace_bytes((int64_t)nroles * P, d) + order_workspace_bytes(P) + align_up((size_t)P * 4) + 1024;
+         seg_workspace_bytes((int64_t)nroles * P, d) + order_workspace_bytes(P) + align_up((size_t)P * 4) +
+         align_up((size_t)P * 8) + 1024;
 }
 
 // model: 0 TransE, 1 HolE
@@ -945,6 +944,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
   }
   SKGE_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
   int32_t *runw = nullptr;
+  float *coef = nullptr;
   if (model == 0) {
     int64_t blocks = (P + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
@@ -974,6 +974,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
       while (((int64_t)1 << kb) < M) ++kb;
       if (int rc = order_by_key(ix.pp, P, kb, ar, st, &order)) return rc;
       runw = ar.take<int32_t>(P);
+      coef = ar.take<float>(2 * P);
       if (!ar.ok()) {
         set_error("workspace too small: need > %zu bytes, have %zu", ar.off, ar.cap);
         return SKGE_EWORKSPACE;
@@ -985,11 +986,11 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
       if (d == 128) {
         const size_t smem = pair_spec4_smem_bytes(1);
         SKGE_CUDA(cudaFuncSetAttribute(hole_pair_spec4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hole_pair_spec4_kernel<1><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw);
+        hole_pair_spec4_kernel<1><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw, coef);
       } else {
         const size_t smem = pair_spec4_smem_bytes(2);
         SKGE_CUDA(cudaFuncSetAttribute(hole_pair_spec4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hole_pair_spec4_kernel<2><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw);
+        hole_pair_spec4_kernel<2><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw, coef);
       }
     } else {
       hole_pair_spec_kernel<<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, d, l1_or_af, margin, flags, G, counts,
@@ -1033,7 +1034,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
       rm.idx[r] = idx[r]; rm.is_rel[r] = isrel[r]; rm.grow[r] = grow[r]; rm.gsign[r] = 1.f;
       rm.twin[r] = r ^ 1;  // the kernels above fold rows (2q, 2q + 1) when the ids coincide
     }
-    if (runw) { rm.runw = runw; rm.runw_role = 4; }
+    if (runw) { rm.runw = runw; rm.runw_role = 4; rm.coef = coef; }
   }
   rm.nroles = 6;
   ParamDesc pd[2];

@@ -28,8 +28,14 @@ __global__ void build_keys_kernel(RoleMap rm, const uint8_t *__restrict__ flags,
     const bool same = q >= 0 && rm.idx[q][i] == id;
     if (same && q < r) ok = false;  // folded into the twin's row
     if (rm.runw && r == rm.runw_role && ok) ok = rm.runw[i] > 0;  // folded into the head of its run
+    int code = (same && q > r ? 8 : 0) + r;
+    if (rm.coef && r < 4 && rm.idx[4][i] == rm.idx[5][i]) {   // shared rows (see RoleMap::coef)
+      const bool same_s = rm.idx[0][i] == rm.idx[1][i], same_o = rm.idx[2][i] == rm.idx[3][i];
+      if (same_s && !same_o && r >= 2) code = 6 + (r - 2);
+      else if (same_o && !same_s && r < 2) code = 14 + r;
+    }
     keys[t] = ok ? id + (rm.is_rel[r] ? N : 0) : sentinel;
-    vals[t] = (int32_t)(i * 16 + (same && q > r ? 8 : 0) + r);
+    vals[t] = (int32_t)(i * 16 + code);
   }
 }
 
@@ -264,12 +270,31 @@ struct SegArgs {
   int spec_logd;        // > 0: G rows are packed spectra of length 1 << spec_logd (see fft.cuh)
   const int32_t *runw;  // RoleMap::runw (nullable)
   int runw_role;
+  const float *coef;    // RoleMap::coef (nullable)
 };
 
-// occurrences a sorted payload stands for: a run sum (RoleMap::runw), a folded twin row (2) or 1
-__device__ __forceinline__ int occ_weight(const SegArgs &a, int val) {
-  if (a.runw && (val & 7) == a.runw_role) return a.runw[val >> 4];
-  return 1 + ((val >> 3) & 1);
+// What a sorted payload (unit * 16 + code) refers to: the gradient row (index into G, in rows), the
+// factor it is taken with, and the occurrences it stands for in the mean: a run sum (RoleMap::runw),
+// a folded twin row (2) or 1.  Codes 6, 7, 14, 15 are the shared rows of RoleMap::coef.
+struct OccRef {
+  int goff;
+  float coef;
+  int weight;
+};
+__device__ __forceinline__ OccRef occ_decode(const SegArgs &a, int val) {
+  const int c = val & 15, unit = val >> 4;
+  OccRef o;
+  if (a.coef && (c & 6) == 6) {
+    o.goff = unit * a.rows_per_unit + (c < 8 ? 2 : 0);
+    o.coef = a.coef[2 * unit + (c & 1)];
+    o.weight = 1;
+  } else {
+    const int r = c & 7;
+    o.goff = unit * a.rows_per_unit + a.grow[r];
+    o.coef = a.gsign[r];
+    o.weight = (a.runw && r == a.runw_role) ? a.runw[unit] : 1 + (c >> 3);
+  }
+  return o;
 }
 
 // shared memory of the spectral mode: twiddles [d/2] float2, then per warp two complex
@@ -296,18 +321,20 @@ __device__ __forceinline__ int accumulate_rows(const SegArgs &a, int beg, int en
   int occ = 0;
   for (int j0 = beg; j0 < end; j0 += 32) {
     const int cnt = min(32, end - j0);
-    const int myval = lane < cnt ? a.vals[j0 + lane] : 0;
-    occ += __reduce_add_sync(kFull, lane < cnt ? occ_weight(a, myval) : 0);
+    OccRef mine = {0, 0.f, 0};
+    if (lane < cnt) mine = occ_decode(a, a.vals[j0 + lane]);
+    occ += __reduce_add_sync(kFull, mine.weight);
     for (int t0 = 0; t0 < cnt; t0 += BATCH) {
       float tmp[BATCH][MAXC][VEC];
       float sgn[BATCH];
 #pragma unroll
       for (int b = 0; b < BATCH; ++b) {
-        const int val = __shfl_sync(kFull, myval, min(t0 + b, cnt - 1));
-        const int r = val & 7;
+        const int src = min(t0 + b, cnt - 1);
+        const int goff = __shfl_sync(kFull, mine.goff, src);
+        const float cf = __shfl_sync(kFull, mine.coef, src);
         const bool live = t0 + b < cnt;
-        sgn[b] = live ? a.gsign[r] : 0.f;
-        const float *g = a.G + ((int64_t)(val >> 4) * a.rows_per_unit + a.grow[r]) * d;
+        sgn[b] = live ? cf : 0.f;
+        const float *g = a.G + (int64_t)goff * d;
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
           int col = (c * 32 + lane) * VEC;
@@ -618,8 +645,9 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
     int occ = 0;
     for (int j0 = beg; j0 < end; j0 += CAP) {
       const int cnt = min(CAP, end - j0);
-      const int myval = lane < cnt ? a.vals[j0 + lane] : 0;
-      occ += __reduce_add_sync(kFull, lane < cnt ? occ_weight(a, myval) : 0);
+      OccRef mine = {0, 0.f, 0};
+      if (lane < cnt) mine = occ_decode(a, a.vals[j0 + lane]);
+      occ += __reduce_add_sync(kFull, mine.weight);
       const bool first = j0 == beg;
       // the slots were last touched by this warp's own (generic-proxy) reads and writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -627,8 +655,7 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
       if (lane == 0) ptx::mbar_expect_tx(bar, (uint32_t)(cnt + (first ? (adagrad ? 2 : 1) : 0)) * kBulkRowBytes);
       __syncwarp();
       if (lane < cnt)
-        ptx::bulk_g2s(slots + (2 + lane) * (d / 4),
-                      a.G + ((int64_t)(myval >> 4) * a.rows_per_unit + a.grow[myval & 7]) * d, kBulkRowBytes, bar);
+        ptx::bulk_g2s(slots + (2 + lane) * (d / 4), a.G + (int64_t)mine.goff * d, kBulkRowBytes, bar);
       if (first) {
         if (lane == 30) ptx::bulk_g2s(slots, xrow, kBulkRowBytes, bar);
         if (lane == 31 && adagrad) ptx::bulk_g2s(slots + d / 4, p2row, kBulkRowBytes, bar);
@@ -636,7 +663,7 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
       ptx::mbar_wait(bar, phase);
       phase ^= 1;
       for (int t = 0; t < cnt; ++t) {
-        const float sgn = a.gsign[__shfl_sync(kFull, myval, t) & 7];
+        const float sgn = __shfl_sync(kFull, mine.coef, t);
         const float4 u0 = slots[(2 + t) * (d / 4) + lane], u1 = slots[(2 + t) * (d / 4) + 32 + lane];
         acc[0][0] = fmaf(sgn, u0.x, acc[0][0]); acc[0][1] = fmaf(sgn, u0.y, acc[0][1]);
         acc[0][2] = fmaf(sgn, u0.z, acc[0][2]); acc[0][3] = fmaf(sgn, u0.w, acc[0][3]);
@@ -883,6 +910,8 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
   SKGE_CUDA(cudaMemsetAsync(a.long_meta, 0, 16, st));
   a.runw = rm.runw;
   a.runw_role = rm.runw_role;
+  a.coef = rm.coef;
+  SKGE_REQUIRE(P * (int64_t)rows_per_unit < ((int64_t)1 << 31), "minibatch too large");
   a.spec_logd = 0;
   if (spectral) {
     a.spec_logd = log2_exact(d);

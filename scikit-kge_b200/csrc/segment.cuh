@@ -28,6 +28,12 @@ struct RoleMap {
   // occurrence of that role is contained in an earlier unit's row and is dropped.
   const int32_t *runw = nullptr;
   int runw_role = -1;
+  // Shared rows (nullable; HolE pairs whose negative keeps the relation and corrupts exactly one
+  // entity): two of the pair's three entity gradients are the same row times gp resp. gn, so the
+  // producer writes that row once, unscaled, and (gp, gn) into coef[2 i], coef[2 i + 1].  With roles
+  // ordered (sp, sn, op, on, ...): object corrupted (sp == sn): roles 2, 3 read row 2 times gp, gn
+  // (payload codes 6, 7); subject corrupted (op == on): roles 0, 1 read row 0 times gp, gn (codes 14, 15).
+  const float *coef = nullptr;
 };
 
 // order[] = the indices 0..n-1 sorted (stably) by keys[] (values below 1 << key_bits)
