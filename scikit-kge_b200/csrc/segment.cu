@@ -577,10 +577,10 @@ __device__ __forceinline__ void row_update_staged(float *xrow, float *p2row, flo
 }
 
 #ifndef SKGE_SEG_BULK_SLOTS
-#define SKGE_SEG_BULK_SLOTS 6
+#define SKGE_SEG_BULK_SLOTS 8
 #endif
 #ifndef SKGE_SEG_BULK_CTAS
-#define SKGE_SEG_BULK_CTAS 4
+#define SKGE_SEG_BULK_CTAS 3
 #endif
 static constexpr int kBulkRowFloats = 256;
 static constexpr int kBulkRowBytes = kBulkRowFloats * 4;
@@ -608,10 +608,38 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
   }
   const bool adagrad = a.opt == SKGE_OPT_ADAGRAD;
   uint32_t phase = 0;
-  const int warp = blockIdx.x * 8 + w, nwarps = gridDim.x * 8;
-  for (int seg = warp; seg < nseg; seg += nwarps) {
-    const int key = a.seg_key[seg];
-    const int beg = a.seg_start[seg], end = a.seg_start[seg + 1];
+  // A warp takes 32 consecutive segments at a time (dealt out through a counter: the relation rows,
+  // whose runs are the longest, sit at the end of the key order and are started first).  The segment
+  // table entries and a 32-wide window of decoded occurrences live one per lane and are handed
+  // round by shuffles, so the dependent chain table -> payload -> (gp, gn) / run weight -> row address
+  // is paid once per 32 segments / occurrences instead of once per segment.
+  const int nblk = (nseg + 31) >> 5;
+  for (;;) {
+    int blk = 0;
+    if (lane == 0) blk = atomicAdd(a.long_meta + 2, 1);
+    blk = __shfl_sync(kFull, blk, 0);
+    if (blk >= nblk) break;
+    const int s0 = (nblk - 1 - blk) << 5;
+    const int ns = min(32, nseg - s0);
+    int mkey = 0, mbeg = 0, mend = 0;
+    if (lane < ns) {
+      mkey = a.seg_key[s0 + lane];
+      mbeg = a.seg_start[s0 + lane];
+      mend = a.seg_start[s0 + lane + 1];
+    }
+    const int wend = __shfl_sync(kFull, mend, ns - 1);
+    int w0 = 0;
+    OccRef mine;
+    auto load_window = [&](int base) {
+      w0 = base;
+      mine = OccRef{0, 0.f, 0};
+      if (base + lane < wend) mine = occ_decode(a, a.vals[base + lane]);
+    };
+    load_window(__shfl_sync(kFull, mbeg, 0));
+  for (int sj = 0; sj < ns; ++sj) {
+    const int seg = s0 + sj;
+    const int key = __shfl_sync(kFull, mkey, sj);
+    const int beg = __shfl_sync(kFull, mbeg, sj), end = __shfl_sync(kFull, mend, sj);
     const int n = end - beg;
     if (n > a.seg_chunk) {   // hot row: passes 2 and 3
       int nch = (n + a.seg_chunk - 1) / a.seg_chunk;
@@ -645,9 +673,11 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
     int occ = 0;
     for (int j0 = beg; j0 < end; j0 += CAP) {
       const int cnt = min(CAP, end - j0);
-      OccRef mine = {0, 0.f, 0};
-      if (lane < cnt) mine = occ_decode(a, a.vals[j0 + lane]);
-      occ += __reduce_add_sync(kFull, mine.weight);
+      if (j0 + cnt > w0 + 32) load_window(j0);
+      const int src = (j0 - w0 + lane) & 31;   // lane t < cnt: where occurrence j0 + t sits in the window
+      const int goff = __shfl_sync(kFull, mine.goff, src);
+      const int wgt = __shfl_sync(kFull, mine.weight, src);
+      occ += __reduce_add_sync(kFull, lane < cnt ? wgt : 0);
       const bool first = j0 == beg;
       // the slots were last touched by this warp's own (generic-proxy) reads and writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -655,7 +685,7 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
       if (lane == 0) ptx::mbar_expect_tx(bar, (uint32_t)(cnt + (first ? (adagrad ? 2 : 1) : 0)) * kBulkRowBytes);
       __syncwarp();
       if (lane < cnt)
-        ptx::bulk_g2s(slots + (2 + lane) * (d / 4), a.G + (int64_t)mine.goff * d, kBulkRowBytes, bar);
+        ptx::bulk_g2s(slots + (2 + lane) * (d / 4), a.G + (int64_t)goff * d, kBulkRowBytes, bar);
       if (first) {
         if (lane == 30) ptx::bulk_g2s(slots, xrow, kBulkRowBytes, bar);
         if (lane == 31 && adagrad) ptx::bulk_g2s(slots + d / 4, p2row, kBulkRowBytes, bar);
@@ -663,7 +693,7 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
       ptx::mbar_wait(bar, phase);
       phase ^= 1;
       for (int t = 0; t < cnt; ++t) {
-        const float sgn = __shfl_sync(kFull, mine.coef, t);
+        const float sgn = __shfl_sync(kFull, mine.coef, j0 - w0 + t);
         const float4 u0 = slots[(2 + t) * (d / 4) + lane], u1 = slots[(2 + t) * (d / 4) + 32 + lane];
         acc[0][0] = fmaf(sgn, u0.x, acc[0][0]); acc[0][1] = fmaf(sgn, u0.y, acc[0][1]);
         acc[0][2] = fmaf(sgn, u0.z, acc[0][2]); acc[0][3] = fmaf(sgn, u0.w, acc[0][3]);
@@ -716,6 +746,7 @@ __global__ void __launch_bounds__(256, SKGE_SEG_BULK_CTAS) seg_reduce_bulk_kerne
       row_update_staged<4, 2>(xrow, p2row, acc, x, p2, lane, a.opt, a.lr, pd.post, pd.rparam);
     }
     if (pd.upd_counts && lane == 0) pd.upd_counts[row] += 1;
+  }
   }
 }
 
