@@ -646,9 +646,10 @@ __device__ __forceinline__ float2 spec_mulc(float2 a, float2 b, bool real0) {   
 
 // One pair of any shape (both or no entity slot shared, a corrupted relation, ...): six rows through
 // registers, relation rows written per pair (runw = 2 for a folded row, 1 otherwise).  Rare on the
-// fused path, so it is kept out of line: its register needs must not shape the staged kernel.
+// fused path: the staged kernel only lists such pairs, a second small kernel works the list off, so
+// that their register needs do not shape the staged kernel.
 template <int NIT>
-__device__ __noinline__ int hole_spec4_generic_pair(const float *__restrict__ Ehat, const float *__restrict__ Rhat,
+__device__ __forceinline__ int hole_spec4_generic_pair(const float *__restrict__ Ehat, const float *__restrict__ Rhat,
                                                     const PairIdx &ix, int64_t i, int af, float margin,
                                                     uint8_t *__restrict__ flags, float *__restrict__ G,
                                                     int32_t *__restrict__ runw, int lane) {
@@ -822,7 +823,8 @@ template <int NIT>
 __global__ void __launch_bounds__(256, SKGE_PAIR_SPEC4_CTAS) hole_pair_spec4_kernel(
     const float *__restrict__ Ehat, const float *__restrict__ Rhat, PairIdx ix, int64_t P, int af, float margin,
     uint8_t *__restrict__ flags, float *__restrict__ G, int32_t *__restrict__ counts, int64_t *__restrict__ nviol_accum,
-    const int32_t *__restrict__ order, int32_t *__restrict__ runw, float *__restrict__ coef) {
+    const int32_t *__restrict__ order, int32_t *__restrict__ runw, float *__restrict__ coef,
+    int32_t *__restrict__ glist) {
   extern __shared__ __align__(128) unsigned char pair_smem[];
   constexpr int KBLK = 32, d = 128 * NIT, ROW4 = d / 4;
   constexpr uint32_t ROWB = d * 4;
@@ -892,13 +894,25 @@ __global__ void __launch_bounds__(256, SKGE_PAIR_SPEC4_CTAS) hole_pair_spec4_ker
         nv += hole_spec4_staged_pair<NIT, 2>(sl, sl + ROW4, sl + 2 * ROW4, sl + 3 * ROW4, i, prel, af, margin, flags, G, runw, coef, run, lane);
     }
     rel_run_flush<NIT>(run, G, runw, lane);
-    unsigned gm = __ballot_sync(kFull, kind == 3);
-    while (gm) {
-      const int t = __ffs(gm) - 1;
-      gm &= gm - 1;
-      nv += hole_spec4_generic_pair<NIT>(Ehat, Rhat, ix, __shfl_sync(kFull, my_i, t), af, margin, flags, G, runw, lane);
-    }
+    if (kind == 3) glist[atomicAdd(counts + 3, 1)] = my_i;   // any order: these pairs are independent of each other
   }
+  if (lane == 0 && nv) {
+    atomicAdd(counts, nv);
+    if (nviol_accum) atomicAdd(reinterpret_cast<unsigned long long *>(nviol_accum), (unsigned long long)nv);
+  }
+}
+
+// the pairs the staged kernel listed in glist[0 .. counts[3])
+template <int NIT>
+__global__ void __launch_bounds__(256) hole_pair_spec4_generic_kernel(
+    const float *__restrict__ Ehat, const float *__restrict__ Rhat, PairIdx ix, int af, float margin,
+    uint8_t *__restrict__ flags, float *__restrict__ G, int32_t *__restrict__ counts, int64_t *__restrict__ nviol_accum,
+    int32_t *__restrict__ runw, const int32_t *__restrict__ glist) {
+  const int lane = threadIdx.x & 31;
+  const int n = counts[3];
+  int nv = 0;
+  for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < n; k += gridDim.x * (blockDim.x >> 5))
+    nv += hole_spec4_generic_pair<NIT>(Ehat, Rhat, ix, glist[k], af, margin, flags, G, runw, lane);
   if (lane == 0 && nv) {
     atomicAdd(counts, nv);
     if (nviol_accum) atomicAdd(reinterpret_cast<unsigned long long *>(nviol_accum), (unsigned long long)nv);
@@ -919,7 +933,7 @@ static size_t pair_ws_bytes(int64_t P, int d, int rows, int nroles) {
   if (P < 1) P = 1;
   return align_up((size_t)P) + align_up((size_t)P * rows * d * sizeof(float)) +
          seg_workspace_bytes((int64_t)nroles * P, d) + order_workspace_bytes(P) + align_up((size_t)P * 4) +
-         align_up((size_t)P * 8) + 1024;
+         align_up((size_t)P * 8) + align_up((size_t)P * 4) + 1024;
 }
 
 // model: 0 TransE, 1 HolE
@@ -975,6 +989,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
       if (int rc = order_by_key(ix.pp, P, kb, ar, st, &order)) return rc;
       runw = ar.take<int32_t>(P);
       coef = ar.take<float>(2 * P);
+      int32_t *glist = ar.take<int32_t>(P);
       if (!ar.ok()) {
         set_error("workspace too small: need > %zu bytes, have %zu", ar.off, ar.cap);
         return SKGE_EWORKSPACE;
@@ -986,11 +1001,13 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
       if (d == 128) {
         const size_t smem = pair_spec4_smem_bytes(1);
         SKGE_CUDA(cudaFuncSetAttribute(hole_pair_spec4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hole_pair_spec4_kernel<1><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw, coef);
+        hole_pair_spec4_kernel<1><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw, coef, glist);
+        hole_pair_spec4_generic_kernel<1><<<kNumSMs, 256, 0, st>>>(Ehat, Rhat, ix, l1_or_af, margin, flags, G, counts, nviol_accum, runw, glist);
       } else {
         const size_t smem = pair_spec4_smem_bytes(2);
         SKGE_CUDA(cudaFuncSetAttribute(hole_pair_spec4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hole_pair_spec4_kernel<2><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw, coef);
+        hole_pair_spec4_kernel<2><<<(int)blocks, 256, smem, st>>>(Ehat, Rhat, ix, P, l1_or_af, margin, flags, G, counts, nviol_accum, order, runw, coef, glist);
+        hole_pair_spec4_generic_kernel<2><<<kNumSMs, 256, 0, st>>>(Ehat, Rhat, ix, l1_or_af, margin, flags, G, counts, nviol_accum, runw, glist);
       }
     } else {
       hole_pair_spec_kernel<<<(int)blocks, 256, 0, st>>>(Ehat, Rhat, ix, P, d, l1_or_af, margin, flags, G, counts,
