@@ -536,6 +536,28 @@ __global__ void __launch_bounds__(256) hole_spectra_kernel(const float *__restri
   }
 }
 
+// d = 256: the register-resident transform of fft.cuh (no shared-memory stages; the whole-table
+// refresh at the start of an epoch then runs at copy speed)
+__global__ void __launch_bounds__(256) hole_spectra256_kernel(const float *__restrict__ X, int64_t rows,
+                                                              float *__restrict__ Xhat) {
+  __shared__ __align__(16) float4 tbuf[8][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  RegFft256 rc;
+  regfft256_init(rc, lane);
+  for (int64_t r = (int64_t)blockIdx.x * 8 + w; r < rows; r += (int64_t)gridDim.x * 8) {
+    const float2 *x = reinterpret_cast<const float2 *>(X + r * 256);
+    float2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(x + 32 * j + lane);   // z_m = x_{2m} + i x_{2m+1}, m = 32 j + lane
+    regfft256_rfft(v, rc, lane);
+    float4 r0, r1;
+    regfft256_freq_to_row(tbuf[w], v, r0, r1, lane);
+    float4 *hr = reinterpret_cast<float4 *>(Xhat + r * 256);
+    hr[lane] = r0;
+    hr[32 + lane] = r1;
+  }
+}
+
 __global__ void __launch_bounds__(256, 4) hole_pair_spec_kernel(const float *__restrict__ Ehat,
                                                              const float *__restrict__ Rhat, PairIdx ix, int64_t P,
                                                              int d, int af, float margin,
@@ -1131,6 +1153,13 @@ int skge_hole_spectra(const float *X, int64_t rows, int d, float *Xhat, skge_str
   int logd = log2_exact(d);
   SKGE_REQUIRE(logd >= 5 && d <= 1024, "spectra need a power-of-two d in [32, 1024]");
   if (rows == 0) return 0;
+  if (d == 256 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xhat)) & 15) == 0) {
+    int64_t nb = (rows + 7) / 8;
+    if (nb > kNumSMs * 8) nb = kNumSMs * 8;
+    hole_spectra256_kernel<<<(int)nb, 256, 0, as_stream(stream)>>>(X, rows, Xhat);
+    SKGE_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = (size_t)(d / 2) * sizeof(float2) + (size_t)8 * warp_fft_scratch_floats(d) * sizeof(float);
   SKGE_CUDA(cudaFuncSetAttribute(hole_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = (rows + 7) / 8;
