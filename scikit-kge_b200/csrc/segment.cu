@@ -5,6 +5,7 @@
 //   SGD / AdaGrad / normalize / normless1 : skge/param.py:108-174
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <iterator>
 
 #include "fft.cuh"
 #include "segment.cuh"
@@ -16,44 +17,78 @@ namespace skge {
 // keys -> sorted segments
 // ---------------------------------------------------------------------------
 
+// One thread per unit: its role ids are read once and all of its (key, payload) entries written
+// (entry t = role * P + unit, coalesced per role).
 __global__ void build_keys_kernel(RoleMap rm, const uint8_t *__restrict__ flags, int64_t P, int N,
                                   int sentinel, int32_t *__restrict__ keys, int32_t *__restrict__ vals) {
-  int64_t L = (int64_t)rm.nroles * P;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < L; t += (int64_t)gridDim.x * blockDim.x) {
-    int r = (int)(t / P);
-    int64_t i = t - (int64_t)r * P;
-    bool ok = flags ? flags[i] != 0 : true;
-    const int id = rm.idx[r][i];
-    const int q = rm.twin[r];
-    const bool same = q >= 0 && rm.idx[q][i] == id;
-    if (same && q < r) ok = false;  // folded into the twin's row
-    if (rm.runw && r == rm.runw_role && ok) ok = rm.runw[i] > 0;  // folded into the head of its run
-    int code = (same && q > r ? 8 : 0) + r;
-    if (rm.coef && r < 4 && rm.idx[4][i] == rm.idx[5][i]) {   // shared rows (see RoleMap::coef)
-      const bool same_s = rm.idx[0][i] == rm.idx[1][i], same_o = rm.idx[2][i] == rm.idx[3][i];
-      if (same_s && !same_o && r >= 2) code = 6 + (r - 2);
-      else if (same_o && !same_s && r < 2) code = 14 + r;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = flags ? flags[i] != 0 : true;
+    int id[kMaxRoles];
+#pragma unroll
+    for (int r = 0; r < kMaxRoles; ++r) id[r] = r < rm.nroles ? rm.idx[r][i] : 0;
+    // shared rows (see RoleMap::coef): roles (sp, sn, op, on, pp, pn)
+    int shared = 0;
+    if (rm.coef && id[4] == id[5]) {
+      const bool same_s = id[0] == id[1], same_o = id[2] == id[3];
+      shared = same_s && !same_o ? 1 : (same_o && !same_s ? 2 : 0);
     }
-    keys[t] = ok ? id + (rm.is_rel[r] ? N : 0) : sentinel;
-    vals[t] = (int32_t)(i * 16 + code);
+    const bool run_ok = rm.runw ? rm.runw[i] > 0 : true;
+#pragma unroll
+    for (int r = 0; r < kMaxRoles; ++r) {
+      if (r >= rm.nroles) break;
+      bool ok = live;
+      const int q = rm.twin[r];
+      bool same = false;
+#pragma unroll
+      for (int qq = 0; qq < kMaxRoles; ++qq)
+        if (qq == q) same = id[qq] == id[r];
+      if (same && q < r) ok = false;  // folded into the twin's row
+      if (r == rm.runw_role && !run_ok) ok = false;  // folded into the head of its run
+      int code = (same && q > r ? 8 : 0) + r;
+      if (shared == 1 && (r == 2 || r == 3)) code = 6 + (r - 2);
+      else if (shared == 2 && r < 2) code = 14 + r;
+      keys[(int64_t)r * P + i] = ok ? id[r] + (rm.is_rel[r] ? N : 0) : sentinel;
+      vals[(int64_t)r * P + i] = (int32_t)(i * 16 + code);
+    }
   }
 }
 
-__global__ void mark_heads_kernel(const int32_t *__restrict__ keys, int64_t L, int sentinel,
-                                  int32_t *__restrict__ head) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x)
-    head[i] = (keys[i] != sentinel) && (i == 0 || keys[i] != keys[i - 1]);
-}
+// head[i] = 1 where a segment starts in the sorted keys; evaluated on the fly by the scan and by the
+// scatter pass (no pass of its own, no array)
+struct HeadFlag {
+  const int32_t *keys;
+  int sentinel;
+  __host__ __device__ __forceinline__ int32_t operator()(int64_t i) const {
+    const int32_t k = keys[i];
+    return (k != sentinel) && (i == 0 || k != keys[i - 1]);
+  }
+};
+struct HeadIter {   // random-access input iterator over HeadFlag
+  using value_type = int32_t;
+  using difference_type = int64_t;
+  using pointer = const int32_t *;
+  using reference = int32_t;
+  using iterator_category = std::random_access_iterator_tag;
+  HeadFlag f;
+  int64_t i;
+  __host__ __device__ __forceinline__ int32_t operator*() const { return f(i); }
+  __host__ __device__ __forceinline__ int32_t operator[](int64_t k) const { return f(i + k); }
+  __host__ __device__ __forceinline__ HeadIter operator+(int64_t k) const { return HeadIter{f, i + k}; }
+  __host__ __device__ __forceinline__ HeadIter operator-(int64_t k) const { return HeadIter{f, i - k}; }
+  __host__ __device__ __forceinline__ int64_t operator-(const HeadIter &o) const { return i - o.i; }
+  __host__ __device__ __forceinline__ HeadIter &operator+=(int64_t k) { i += k; return *this; }
+  __host__ __device__ __forceinline__ HeadIter &operator++() { ++i; return *this; }
+};
 
 // meta: [0] nseg, [1] segments of table 0 (keys < N), [3] number of valid keys. Pre-zeroed.
-__global__ void scatter_heads_kernel(const int32_t *__restrict__ keys, const int32_t *__restrict__ head,
+__global__ void scatter_heads_kernel(const int32_t *__restrict__ keys,
                                      const int32_t *__restrict__ pos, int64_t L, int N, int sentinel,
                                      int32_t *__restrict__ seg_start, int32_t *__restrict__ seg_key,
                                      int32_t *__restrict__ meta) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) {
     int k = keys[i];
     if (k == sentinel) continue;
-    int h = head[i], ps = pos[i];
+    int h = i == 0 || keys[i - 1] != k, ps = pos[i];
     if (h) {
       seg_start[ps] = (int32_t)i;
       seg_key[ps] = k;
@@ -115,7 +150,7 @@ int order_by_key(const int32_t *keys, int64_t n, int key_bits, Arena &ar, cudaSt
 
 static size_t cub_scan_bytes(int64_t L) {
   size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (int)L);
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, HeadIter{HeadFlag{nullptr, 0}, 0}, (int32_t *)nullptr, (int)L);
   return bytes;
 }
 
@@ -149,7 +184,7 @@ int seg_build(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int
   SKGE_REQUIRE(N + M < ((int64_t)1 << 31) - 1, "too many rows");
   int32_t *keys_in = ar.take<int32_t>(L), *keys_out = ar.take<int32_t>(L);
   int32_t *vals_in = ar.take<int32_t>(L), *vals_out = ar.take<int32_t>(L);
-  int32_t *head = ar.take<int32_t>(L), *pos = ar.take<int32_t>(L);
+  int32_t *pos = ar.take<int32_t>(L);
   int32_t *seg_start = ar.take<int32_t>(L + 1), *seg_key = ar.take<int32_t>(L + 1);
   int32_t *meta = ar.take<int32_t>(4);
   size_t c1 = cub_sort_bytes(L), c2 = cub_scan_bytes(L);
@@ -164,17 +199,18 @@ int seg_build(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int
   int blocks = (int)((L + threads - 1) / threads);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   SKGE_CUDA(cudaMemsetAsync(meta, 0, 16, st));
-  build_keys_kernel<<<blocks, threads, 0, st>>>(rm, flags, P, (int)N, sentinel, keys_in, vals_in);
+  {
+    int kb = (int)((P + threads - 1) / threads);
+    if (kb > kNumSMs * 8) kb = kNumSMs * 8;
+    build_keys_kernel<<<kb, threads, 0, st>>>(rm, flags, P, (int)N, sentinel, keys_in, vals_in);
+  }
   SKGE_LAUNCH_CHECK();
   size_t tb = cub_bytes;
   SKGE_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys_in, keys_out, vals_in, vals_out, (int)L, 0,
                                             key_bits(sentinel), st));
-  mark_heads_kernel<<<blocks, threads, 0, st>>>(keys_out, L, sentinel, head);
-  SKGE_LAUNCH_CHECK();
   tb = cub_bytes;
-  SKGE_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, head, pos, (int)L, st));
-  scatter_heads_kernel<<<blocks, threads, 0, st>>>(keys_out, head, pos, L, (int)N, sentinel, seg_start,
-                                                   seg_key, meta);
+  SKGE_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, HeadIter{HeadFlag{keys_out, sentinel}, 0}, pos, (int)L, st));
+  scatter_heads_kernel<<<blocks, threads, 0, st>>>(keys_out, pos, L, (int)N, sentinel, seg_start, seg_key, meta);
   SKGE_LAUNCH_CHECK();
   out->vals = vals_out;
   out->seg_start = seg_start;
