@@ -117,7 +117,8 @@ SKGE_API int skge_hole_pair_step(float *E, float *R, float *p2E, float *p2R, con
                         skge_stream_t stream);
 
 /*
- * HolE in the frequency domain (fused path, power-of-two d in [32, 1024]).  Ehat / Rhat hold
+ * HolE in the frequency domain (fused path; even d in [32, 1024] with d / 2 = 2^a 3^b 5^c:
+ * every power of two and e.g. 100, 150, 200, 300 -- numpy's FFT in skge/util.py:27,50 takes any length).  Ehat / Rhat hold
  * the packed spectra of the rows of E / R (d floats per row: slot 0 = (X_0, X_{d/2}), slot f =
  * (Re X_f, Im X_f)); skge_hole_spectra fills them, skge_hole_pair_step_spectral is
  * skge_hole_pair_step with every per-pair transform removed: scores by Parseval, gradient rows

@@ -279,6 +279,9 @@ if __name__ == '__main__':
     pairwise_case('hole_linear_adagrad_d256', HolE, 50, 4, 256, 32, 1.0, 23, AdaGrad, scale=0.2,
                   af=afs['linear'])
     pairwise_case('hole_relu_sgd_d10', HolE, 30, 3, 10, 64, 0.3, 24, SGD, scale=0.7, af=afs['relu'])
+    # config 2's row length: 150 = 2 * 3 * 5 * 5 (mixed-radix transform on the device)
+    pairwise_case('hole_sigmoid_adagrad_d150', HolE, 60, 5, 150, 48, 0.2, 25, AdaGrad, scale=0.3,
+                  af=afs['sigmoid'])
     logistic_case('hole_logistic_adagrad', HolE, 50, 4, 32, 90, 31, AdaGrad, 0.05)
     logistic_case('hole_logistic_sgd_d150', HolE, 50, 4, 150, 60, 32, SGD, 0.0)
     logistic_case('rescal_logistic_sgd', RESCAL, 40, 4, 20, 90, 33, SGD, 0.0)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Diagnostic: config-5-sized fused minibatch steps (P = 1M pairs, N = 1M, d = 256), timed with CUDA events.
+"""Diagnostic: config-5-sized fused minibatch steps (P = 1M pairs, N = 1M, d = 256 or argv[3]), timed with CUDA events.
+SKGE_SPECTRAL=0 forces HolE's per-pair kernels (direct O(d^2) correlations for d that is not a power of two).
 Run under `ncu --metrics gpu__time_duration.sum` for the per-kernel breakdown."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,4 +42,5 @@ def main(model='hole', N=1000000, M=1000, d=256, B=500000, steps=3):
                  byts / 1e6 / a.elapsed_time(c), B / 1e3 / a.elapsed_time(c)), flush=True)
 
 if __name__ == '__main__':
-    main(sys.argv[1] if len(sys.argv) > 1 else 'hole', steps=int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+    main(sys.argv[1] if len(sys.argv) > 1 else 'hole', steps=int(sys.argv[2]) if len(sys.argv) > 2 else 3,
+         d=int(sys.argv[3]) if len(sys.argv) > 3 else 256)

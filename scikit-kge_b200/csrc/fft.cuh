@@ -1,4 +1,4 @@
-// Shared-memory FFT building blocks for HolE (power-of-two d).
+// Shared-memory FFT building blocks for HolE (even d whose half is 2^a 3^b 5^c).
 //
 // Spectra of real rows are kept in a packed "half-complex" layout of exactly d floats:
 //   float2 slot 0      = (X_0, X_{d/2})            (both real)
@@ -18,10 +18,11 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // conj(a) * b
   return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
 
-// tw[m] = exp(-2 pi i m / N), m < N/2; index m < N by symmetry
+// tw[m] = exp(-2 pi i m / N), m < N/2; index m < N by symmetry (N even, N/2 may be odd)
 __device__ __forceinline__ float2 tw_at(const float2 *tw, int m, int half) {
-  float2 w = tw[m & (half - 1)];
-  return m >= half ? make_float2(-w.x, -w.y) : w;
+  const bool up = m >= half;
+  float2 w = tw[up ? m - half : m];
+  return up ? make_float2(-w.x, -w.y) : w;
 }
 
 __device__ __forceinline__ void fill_twiddles(float2 *tw, int N, int tid, int nthreads) {
@@ -32,18 +33,38 @@ __device__ __forceinline__ void fill_twiddles(float2 *tw, int N, int tid, int nt
   }
 }
 
-// One complex transform of length n = 1 << logn by ONE WARP: Stockham autosort, radix-4
-// stages (plus a leading radix-2 stage when logn is odd), ping-ponging between `in` and
-// `out` (n float2 each, shared memory private to the warp).  The twiddle table belongs to a
-// transform of length n * tw_stride (tw[m] = exp(-2 pi i m / (n * tw_stride))).  Returns the
-// buffer that holds the result.  Callers must __syncwarp() after filling `in`.
+// Lengths the warp transform handles: n = 2^a 3^b 5^c (numpy's FFT takes any length,
+// skge/util.py:27,50; the configurations of the reference use d = 150 = 2 * 3 * 5 * 5).
+__host__ __device__ __forceinline__ bool fft_len_ok(int n) {
+  if (n < 1) return false;
+  while ((n & 1) == 0) n >>= 1;
+  while (n % 3 == 0) n /= 3;
+  while (n % 5 == 0) n /= 5;
+  return n == 1;
+}
+// packed spectra need an even row length whose half is such a length
+__host__ __device__ __forceinline__ bool spectral_len_ok(int d) {
+  return d >= 32 && d <= 1024 && (d & 1) == 0 && fft_len_ok(d / 2);
+}
+
+// One complex transform of length n = 2^a 3^b 5^c by ONE WARP: Stockham autosort, mixed radix:
+// a leading radix-2 stage when a is odd, radix-4 stages for the rest of 2^a, then radix-3 and
+// radix-5 stages, ping-ponging between `in` and `out` (n float2 each, shared memory private to
+// the warp).  A radix-r stage with Ns = the product of the radices before it reads
+// v_t = in[j + t n/r] W_{r Ns}^{t (j mod Ns)} and writes out[(j - j mod Ns) r + j mod Ns + s Ns] =
+// sum_t v_t W_r^{s t}.  The twiddle table belongs to a transform of length n * tw_stride
+// (tw[m] = exp(-2 pi i m / (n * tw_stride)), m < n * tw_stride / 2).  Returns the buffer that
+// holds the result.  Callers must __syncwarp() after filling `in`.
 template <bool INVERSE>
-__device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float2 *tw, int tw_stride, int logn,
+__device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float2 *tw, int tw_stride, int n,
                                             int lane) {
-  const int N = 1 << logn, H = N >> 1, Qn = N >> 2;
-  const int thalf = H * tw_stride;  // table entries
+  const int thalf = (n * tw_stride) >> 1;  // table entries
+  int odd = n, log2n = 0;
+  while ((odd & 1) == 0) { odd >>= 1; ++log2n; }
+  const int N2 = n / odd;                  // the power-of-two part
   int Ns = 1;
-  if (logn & 1) {
+  if (log2n & 1) {
+    const int H = n >> 1;
     for (int j = lane; j < H; j += 32) {
       const float2 u0 = in[j], u1 = in[j + H];
       out[2 * j] = make_float2(u0.x + u1.x, u0.y + u1.y);
@@ -53,8 +74,9 @@ __device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float
     float2 *t = in; in = out; out = t;
     Ns = 2;
   }
-  for (; Ns < N; Ns <<= 2) {
-    const int tstep = (N / (4 * Ns)) * tw_stride;
+  const int Qn = n >> 2;
+  for (; Ns < N2; Ns <<= 2) {
+    const int tstep = (n / (4 * Ns)) * tw_stride;
     for (int j = lane; j < Qn; j += 32) {
       const int k = j & (Ns - 1);
       const int j0 = ((j - k) << 2) + k;
@@ -75,6 +97,62 @@ __device__ __forceinline__ float2 *warp_fft(float2 *in, float2 *out, const float
     __syncwarp();
     float2 *t = in; in = out; out = t;
   }
+  if (odd == 1) return in;   // power-of-two lengths end here
+  for (int rest = odd; rest % 3 == 0; rest /= 3, Ns *= 3) {
+    const int Tn = n / 3;
+    const int tstep = (n / (3 * Ns)) * tw_stride;
+    for (int j = lane; j < Tn; j += 32) {
+      const int k = j % Ns;
+      const int j0 = (j - k) * 3 + k;
+      float2 w1 = tw_at(tw, k * tstep, thalf), w2 = tw_at(tw, 2 * k * tstep, thalf);
+      if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; }
+      const float2 v0 = in[j];
+      const float2 v1 = cmul(in[j + Tn], w1);
+      const float2 v2 = cmul(in[j + 2 * Tn], w2);
+      const float2 s = make_float2(v1.x + v2.x, v1.y + v2.y);
+      const float c = INVERSE ? -0.86602540378443865f : 0.86602540378443865f;
+      const float2 e = make_float2(c * (v1.y - v2.y), -c * (v1.x - v2.x));   // -+ i sin(2 pi / 3) (v1 - v2)
+      const float2 m = make_float2(fmaf(-0.5f, s.x, v0.x), fmaf(-0.5f, s.y, v0.y));
+      out[j0] = make_float2(v0.x + s.x, v0.y + s.y);
+      out[j0 + Ns] = make_float2(m.x + e.x, m.y + e.y);
+      out[j0 + 2 * Ns] = make_float2(m.x - e.x, m.y - e.y);
+    }
+    __syncwarp();
+    float2 *t = in; in = out; out = t;
+  }
+  for (int rest = odd; rest % 5 == 0; rest /= 5, Ns *= 5) {
+    const int Fn = n / 5;
+    const int tstep = (n / (5 * Ns)) * tw_stride;
+    constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2 pi / 5), cos(4 pi / 5)
+    const float s1 = INVERSE ? -0.95105651629515357f : 0.95105651629515357f;  // sin(2 pi / 5)
+    const float s2 = INVERSE ? -0.58778525229247313f : 0.58778525229247313f;  // sin(4 pi / 5)
+    for (int j = lane; j < Fn; j += 32) {
+      const int k = j % Ns;
+      const int j0 = (j - k) * 5 + k;
+      float2 w1 = tw_at(tw, k * tstep, thalf), w2 = tw_at(tw, 2 * k * tstep, thalf);
+      float2 w3 = tw_at(tw, 3 * k * tstep, thalf), w4 = tw_at(tw, 4 * k * tstep, thalf);
+      if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
+      const float2 v0 = in[j];
+      const float2 v1 = cmul(in[j + Fn], w1);
+      const float2 v2 = cmul(in[j + 2 * Fn], w2);
+      const float2 v3 = cmul(in[j + 3 * Fn], w3);
+      const float2 v4 = cmul(in[j + 4 * Fn], w4);
+      const float2 a1 = make_float2(v1.x + v4.x, v1.y + v4.y), b1 = make_float2(v1.x - v4.x, v1.y - v4.y);
+      const float2 a2 = make_float2(v2.x + v3.x, v2.y + v3.y), b2 = make_float2(v2.x - v3.x, v2.y - v3.y);
+      const float2 m1 = make_float2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
+      const float2 m2 = make_float2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
+      const float2 t1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+      const float2 t2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+      const float2 e1 = make_float2(t1.y, -t1.x), e2 = make_float2(t2.y, -t2.x);   // -+ i t (the sign is in s1, s2)
+      out[j0] = make_float2(v0.x + a1.x + a2.x, v0.y + a1.y + a2.y);
+      out[j0 + Ns] = make_float2(m1.x + e1.x, m1.y + e1.y);
+      out[j0 + 2 * Ns] = make_float2(m2.x + e2.x, m2.y + e2.y);
+      out[j0 + 3 * Ns] = make_float2(m2.x - e2.x, m2.y - e2.y);
+      out[j0 + 4 * Ns] = make_float2(m1.x - e1.x, m1.y - e1.y);
+    }
+    __syncwarp();
+    float2 *t = in; in = out; out = t;
+  }
   return in;
 }
 
@@ -87,8 +165,8 @@ __host__ __device__ __forceinline__ size_t warp_fft_scratch_floats(int d) { retu
 // packed spectrum (floats pk[0..d), in shared memory; may alias b1) -> time-domain row.
 // The returned buffer, viewed as d floats, holds x_n * (d/2): scale by 2/d.
 __device__ __forceinline__ const float *warp_irfft_packed(const float *pk, float2 *b0, float2 *b1, const float2 *tw,
-                                                         int logd, int lane) {
-  const int h = 1 << (logd - 1);
+                                                         int d, int lane) {
+  const int h = d >> 1;
   __syncwarp();
   for (int f = lane; f < h; f += 32) {
     float2 z;
@@ -106,13 +184,13 @@ __device__ __forceinline__ const float *warp_irfft_packed(const float *pk, float
     b0[f] = z;
   }
   __syncwarp();
-  return reinterpret_cast<const float *>(warp_fft<true>(b0, b1, tw, 2, logd - 1, lane));
+  return reinterpret_cast<const float *>(warp_fft<true>(b0, b1, tw, 2, h, lane));
 }
 
 // b0 viewed as d floats holds the real row; returns Z (h float2), the half-length transform.
-__device__ __forceinline__ const float2 *warp_rfft_half(float2 *b0, float2 *b1, const float2 *tw, int logd, int lane) {
+__device__ __forceinline__ const float2 *warp_rfft_half(float2 *b0, float2 *b1, const float2 *tw, int d, int lane) {
   __syncwarp();
-  return warp_fft<false>(b0, b1, tw, 2, logd - 1, lane);
+  return warp_fft<false>(b0, b1, tw, 2, d >> 1, lane);
 }
 
 // packed slot f (0 <= f < h) of the length-d spectrum from the half-length transform Z

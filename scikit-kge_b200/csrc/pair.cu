@@ -518,7 +518,7 @@ static int launch_hole_fft(const float *E, const float *R, const PairIdx &ix, in
 // of 6 per pair.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hole_spectra_kernel(const float *__restrict__ X, int64_t rows, int d,
-                                                           int logd, float *__restrict__ Xhat) {
+                                                           float *__restrict__ Xhat) {
   extern __shared__ __align__(16) float sm_spec[];
   float2 *tw = reinterpret_cast<float2 *>(sm_spec);
   fill_twiddles(tw, d, threadIdx.x, blockDim.x);
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) hole_spectra_kernel(const float *__restri
     const float2 *x = reinterpret_cast<const float2 *>(X + r * d);
     __syncwarp();
     for (int m = lane; m < h; m += 32) b0[m] = __ldg(x + m);   // z_m = x_{2m} + i x_{2m+1}
-    const float2 *Z = warp_rfft_half(b0, b1, tw, logd, lane);
+    const float2 *Z = warp_rfft_half(b0, b1, tw, d, lane);
     float2 *hr = reinterpret_cast<float2 *>(Xhat + r * d);
     for (int f = lane; f < h; f += 32) hr[f] = packed_slot(Z, f, h, tw);
   }
@@ -1000,7 +1000,7 @@ static int pair_run(int model, float *E, float *R, float *p2E, float *p2R, const
     else SKGE_TRANSE_PAIR(transe_pair_kernel<1>);
 #undef SKGE_TRANSE_PAIR
   } else if (Ehat && Rhat) {
-    SKGE_REQUIRE(update && log2_exact(d) >= 5 && d <= 1024, "spectral HolE step needs a power-of-two d in [32, 1024]");
+    SKGE_REQUIRE(update && spectral_len_ok(d), "spectral HolE step needs an even d in [32, 1024] with d / 2 = 2^a 3^b 5^c");
     int64_t blocks = (P + 7) / 8;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (d == 128 || d == 256) {
@@ -1150,8 +1150,7 @@ int skge_hole_pair_step(float *E, float *R, float *p2E, float *p2R, const int32_
 
 int skge_hole_spectra(const float *X, int64_t rows, int d, float *Xhat, skge_stream_t stream) {
   SKGE_REQUIRE(X && Xhat && rows >= 0, "bad arguments");
-  int logd = log2_exact(d);
-  SKGE_REQUIRE(logd >= 5 && d <= 1024, "spectra need a power-of-two d in [32, 1024]");
+  SKGE_REQUIRE(spectral_len_ok(d), "spectra need an even d in [32, 1024] with d / 2 = 2^a 3^b 5^c");
   if (rows == 0) return 0;
   if (d == 256 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xhat)) & 15) == 0) {
     int64_t nb = (rows + 7) / 8;
@@ -1164,7 +1163,7 @@ int skge_hole_spectra(const float *X, int64_t rows, int d, float *Xhat, skge_str
   SKGE_CUDA(cudaFuncSetAttribute(hole_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = (rows + 7) / 8;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  hole_spectra_kernel<<<(int)blocks, 256, smem, as_stream(stream)>>>(X, rows, d, logd, Xhat);
+  hole_spectra_kernel<<<(int)blocks, 256, smem, as_stream(stream)>>>(X, rows, d, Xhat);
   SKGE_LAUNCH_CHECK();
   return 0;
 }

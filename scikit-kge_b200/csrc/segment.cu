@@ -303,7 +303,7 @@ struct SegArgs {
   int32_t *partial_occ; // [long_chunk_cap] occurrences behind each partial sum
   int long_seg_cap, long_chunk_cap;
   int seg_chunk;        // segments longer than this are reduced chunk-wise
-  int spec_logd;        // > 0: G rows are packed spectra of length 1 << spec_logd (see fft.cuh)
+  int spec_d;           // > 0: G rows are packed spectra of length spec_d = d (see fft.cuh)
   const int32_t *runw;  // RoleMap::runw (nullable)
   int runw_role;
   const float *coef;    // RoleMap::coef (nullable)
@@ -453,7 +453,7 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
       int col = (c * 32 + lane) * VEC;
       if (col < d) st_vec<VEC>(pk + col, acc[c]);
     }
-    const float *x = warp_irfft_packed(pk, b0, b1, tw, a.spec_logd, lane);
+    const float *x = warp_irfft_packed(pk, b0, b1, tw, a.spec_d, lane);
     const float sc = 2.0f / (float)d;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
@@ -484,7 +484,7 @@ __device__ __forceinline__ void finish_row(const SegArgs &a, int seg, int key, i
         int col = (c * 32 + lane) * VEC;
         if (col < d) st_vec<VEC>(xr + col, x[c]);
       }
-      const float2 *Z = warp_rfft_half(b0, b1, tw, a.spec_logd, lane);
+      const float2 *Z = warp_rfft_half(b0, b1, tw, a.spec_d, lane);
       float2 *hrow = reinterpret_cast<float2 *>(pd.hat + row * d);
       for (int f = lane; f < h; f += 32) hrow[f] = packed_slot(Z, f, h, tw);
     }
@@ -924,7 +924,7 @@ static void launch_seg_reduce_s(const SegArgs &a, bool update, int blocks, cudaS
 // instantiation leaves the plain update kernel with fewer registers.
 template <int VEC, int MAXC, int BATCH>
 static void launch_seg_reduce_b(const SegArgs &a, bool update, int blocks, cudaStream_t st) {
-  if (update && a.spec_logd > 0) launch_seg_reduce_s<VEC, MAXC, BATCH, true>(a, update, blocks, st);
+  if (update && a.spec_d > 0) launch_seg_reduce_s<VEC, MAXC, BATCH, true>(a, update, blocks, st);
   else launch_seg_reduce_s<VEC, MAXC, BATCH, false>(a, update, blocks, st);
 }
 
@@ -979,10 +979,10 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
   a.runw_role = rm.runw_role;
   a.coef = rm.coef;
   SKGE_REQUIRE(P * (int64_t)rows_per_unit < ((int64_t)1 << 31), "minibatch too large");
-  a.spec_logd = 0;
+  a.spec_d = 0;
   if (spectral) {
-    a.spec_logd = log2_exact(d);
-    SKGE_REQUIRE(update && a.spec_logd >= 5 && d <= 1024, "spectral mode needs update mode and a power-of-two d in [32, 1024]");
+    a.spec_d = d;
+    SKGE_REQUIRE(update && spectral_len_ok(d), "spectral mode needs update mode and an even d in [32, 1024] with d / 2 = 2^a 3^b 5^c");
   }
   a.seg_start = sl.seg_start;
   a.seg_key = sl.seg_key;
@@ -1005,7 +1005,11 @@ int seg_run(const RoleMap &rm, const uint8_t *flags, int64_t P, int64_t N, int64
   int64_t blocks = (maxseg + 7) / 8;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   if (blocks < 1) blocks = 1;
-  switch (pick_vec(d)) {
+  int vec = pick_vec(d);
+  // the <4, 2> spectral instantiation is the register-resident d = 256 transform: other row lengths
+  // of that shape (129..255 floats, e.g. d = 200) take 64-bit accesses and the shared-memory transform
+  if (a.spec_d > 0 && vec == 4 && d > 128 && d < 256) vec = 2;
+  switch (vec) {
     case 4: rc = dispatch_seg_reduce<4>(a, update, (int)blocks, st); break;
     case 2: rc = dispatch_seg_reduce<2>(a, update, (int)blocks, st); break;
     default: rc = dispatch_seg_reduce<1>(a, update, (int)blocks, st); break;

@@ -8,6 +8,18 @@ from .param import normless1, DevArray, post_code
 from ._modelutil import idx_tensor, unzip_device, updater_args
 
 
+def spectral_len_ok(d):
+    """Row lengths the device transforms take (csrc/fft.cuh): even, 32..1024, d / 2 = 2^a 3^b 5^c
+    -- every power of two, and e.g. 100, 150, 200, 300."""
+    if d < 32 or d > 1024 or d % 2:
+        return False
+    h = d // 2
+    for r in (2, 3, 5):
+        while h % r == 0:
+            h //= r
+    return h == 1
+
+
 class HolE(Model):
     """Holographic embeddings.
 
@@ -57,14 +69,14 @@ class HolE(Model):
         tc = self.track_counters and opt == _ext.OPT_ADAGRAD
         return (self.E._update_counts if tc else None), (self.R._update_counts if tc else None)
 
-    # -- frequency-domain training state (power-of-two ncomp) ------------------------------
+    # -- frequency-domain training state (even ncomp with ncomp / 2 = 2^a 3^b 5^c) -----------
     spectral = True         # set False to force the per-pair FFT / direct kernels
 
     def _prepare_fused(self):
         """Called by the trainers at the start of every fused epoch: (re)build the packed
         spectra of E and R that the spectral step reads and keeps current."""
         d = self.ncomp
-        if self.spectral and d >= 32 and d <= 1024 and (d & (d - 1)) == 0:
+        if self.spectral and spectral_len_ok(d):
             old = getattr(self, '_spec', None)      # refresh in place: captured graphs keep the pointers
             if old is None or old[0].shape != self.E.data.shape or old[0].device != self.E.data.device:
                 old = (torch.empty_like(self.E.data), torch.empty_like(self.R.data))

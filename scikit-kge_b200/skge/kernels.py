@@ -95,7 +95,7 @@ def pair_step(model, E, R, p2E, p2R, pos, neg, valid, margin, l1_or_af, rparam, 
 
 
 def hole_spectra(X, out=None):
-    """Packed spectra of the rows of X (power-of-two d), see csrc/fft.cuh."""
+    """Packed spectra of the rows of X (even d in [32, 1024] with d / 2 = 2^a 3^b 5^c), see csrc/fft.cuh."""
     if out is None:
         out = torch.empty_like(X)
     _count('scores')

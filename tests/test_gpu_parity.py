@@ -19,7 +19,8 @@ GRAD_TOL = dict(rtol=1e-4, atol=2e-6)
 PARAM_TOL = dict(rtol=1e-5, atol=2e-6)
 
 PAIRWISE = ['transe_l1_adagrad', 'transe_l2_sgd', 'transe_l1_sgd_d7', 'hole_sigmoid_adagrad',
-            'hole_tanh_sgd_rparam', 'hole_linear_adagrad_d256', 'hole_relu_sgd_d10']
+            'hole_tanh_sgd_rparam', 'hole_linear_adagrad_d256', 'hole_relu_sgd_d10',
+            'hole_sigmoid_adagrad_d150']
 LOGISTIC = ['hole_logistic_adagrad', 'hole_logistic_sgd_d150', 'rescal_logistic_sgd',
             'rescal_logistic_adagrad_rparam']
 
@@ -123,7 +124,8 @@ def test_hole_spectra_match_numpy_rfft():
     """Packed spectra (csrc/fft.cuh): slot 0 = (X_0, X_{d/2}), slot f = (Re X_f, Im X_f)."""
     from skge import kernels
     rng = np.random.default_rng(0)
-    for d in (32, 64, 128, 256, 512, 1024):
+    # powers of two, and mixed radix: d / 2 = 2^a 3^b 5^c (config 2 of BASELINE.json trains d = 150)
+    for d in (32, 64, 128, 256, 512, 1024, 36, 48, 50, 54, 60, 90, 96, 100, 150, 160, 200, 250, 300, 486, 750, 1000):
         x = rng.normal(size=(37, d)).astype(np.float32)
         got = kernels.hole_spectra(torch.from_numpy(x).cuda()).cpu().numpy().astype(np.float64)
         F = np.fft.rfft(x.astype(np.float64), axis=1)
@@ -133,9 +135,9 @@ def test_hole_spectra_match_numpy_rfft():
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
 
 
-@pytest.mark.parametrize('name', ['hole_linear_adagrad_d256'])
+@pytest.mark.parametrize('name', ['hole_linear_adagrad_d256', 'hole_sigmoid_adagrad_d150'])
 def test_hole_frequency_domain_step_matches_reference_golden(golden, name):
-    """The spectral fused step (what fit() runs for power-of-two ncomp): two steps vs the
+    """The spectral fused step (what fit() runs for even ncomp with ncomp / 2 = 2^a 3^b 5^c): two steps vs the
     reference's parameters, and the spectra must stay equal to the FFT of the updated tables."""
     import skge
     from skge import kernels
@@ -304,7 +306,12 @@ def _near_margin(info, margin, tol):
     # power-of-two d: the shared-memory FFT path (SGD: the update is continuous in g, so the
     # whole table can be compared without excusing AdaGrad's clamp region)
     ('hole', 256, 0.2, None, 'sgd'), ('hole', 128, 0.2, None, 'sgd'), ('hole', 32, 0.2, None, 'sgd'),
-    ('hole', 1024, 0.2, None, 'sgd'), ('hole', 256, 0.2, None, 'adagrad')])
+    ('hole', 1024, 0.2, None, 'sgd'), ('hole', 256, 0.2, None, 'adagrad'),
+    # mixed-radix row lengths (d / 2 = 2^a 3^b 5^c): 150 is config 2; 200 and 160 have the access shape of
+    # d = 256 (two 128-bit chunks per lane) and must NOT take its register-resident transform
+    ('hole', 150, 0.2, None, 'sgd'), ('hole', 200, 0.2, None, 'sgd'), ('hole', 100, 0.2, None, 'sgd'),
+    ('hole', 96, 0.2, None, 'sgd'), ('hole', 160, 0.2, None, 'sgd'), ('hole', 250, 0.2, None, 'sgd'),
+    ('hole', 54, 0.2, None, 'sgd'), ('hole', 600, 0.2, None, 'sgd')])
 def test_wn18_shaped_minibatch_against_oracle(kind, d, margin, l1, opt):
     """Config-1/2/4-sized minibatch (B = 1414 -> P = 2828 pairs) vs the oracle."""
     import skge
@@ -488,6 +495,24 @@ def test_hot_rows_use_the_chunked_segment_reduction(kind, d):
     orc.sgd_update(R, ograds['R'][0], ograds['R'][1], 0.1, None)
     np.testing.assert_allclose(np.asarray(m.E), E, **PARAM_TOL)
     np.testing.assert_allclose(np.asarray(m.R), R, **PARAM_TOL)
+    if kind == 'hole':
+        # the same minibatch through the frequency-domain step: hub rows finish in
+        # seg_long_finish_kernel's spectral branch (mixed-radix transform for d = 150)
+        from skge import kernels
+        m2 = skge.HolE((N, N, M), d, rparam=0.05)
+        m2.E[...] = E0
+        m2.R[...] = R0
+        t2 = skge.PairwiseStochasticTrainer(m2, nbatches=1, margin=margin, learning_rate=0.1, param_update=SGD)
+        t2._setup_fused()
+        m2._prepare_fused()
+        assert m2._spec is not None
+        m2._fused_pair_step(t2._updaters, tuple(idx_tensor(pos[:, i]) for i in range(3)),
+                            tuple(idx_tensor(neg[:, i]) for i in range(3)), None, t2._counts, t2._nviol_dev)
+        np.testing.assert_allclose(np.asarray(m2.E), E, **PARAM_TOL)
+        np.testing.assert_allclose(np.asarray(m2.R), R, **PARAM_TOL)
+        for tab, hat in ((m2.E.data, m2._spec[0]), (m2.R.data, m2._spec[1])):
+            ref = kernels.hole_spectra(tab)
+            torch.testing.assert_close(hat, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
 
 
 def test_rescal_wn18_shaped_minibatch_against_oracle():
@@ -704,7 +729,7 @@ def test_hole_twin_rows_fold_for_every_sharing_pattern(d):
     t2 = skge.PairwiseStochasticTrainer(m2, nbatches=1, margin=margin, learning_rate=0.1, param_update=SGD)
     t2._setup_fused()
     m2._prepare_fused()
-    assert (m2._spec is not None) == (d in (64, 128, 256))
+    assert (m2._spec is not None) == (d != 24)      # 150 = 2 * 3 * 5 * 5: mixed-radix transform; 24 < 32: direct kernel
     m2._fused_pair_step(t2._updaters, tuple(idx_tensor(pos[:, i]) for i in range(3)),
                         tuple(idx_tensor(neg[:, i]) for i in range(3)), None, t2._counts, t2._nviol_dev)
     assert int(t2._nviol_dev.item()) == info['nviolations']
