@@ -154,28 +154,47 @@ __global__ void __launch_bounds__(THREADS, 2) rank_sweep_tma_kernel(const float 
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
-    // epilogue: compare against the per-query thresholds; a score is never stored
+    // epilogue: compare against the per-query thresholds; a score is never stored.  Two predicate
+    // bits per accumulator (bit j of `gt`: counted, of `ge`: at or above the band's lower edge), one
+    // popc per query row; the rare band elements (ge & ~gt) are pushed from a loop over the set bits,
+    // so the code stays a few KB: with the candidate push inlined per element the epilogue was
+    // 46 KB of straight-line code that every warp walked once per tile and that evicted the 8 KB
+    // loop body from the instruction cache (ncu at config 1: 38 % of the stall samples there).
     const int nvalid = (int)min((int64_t)TILE, n_shard - et * TILE);
     const int ebase = (int)(shard_base + et * TILE);
+    // valid entity rows of this thread: 4 tx + j (j < 4) and 64 + 4 tx + (j - 4)
+    const unsigned vm = ((1u << min(4, max(0, nvalid - 4 * tx))) - 1u) |
+                        (((1u << min(4, max(0, nvalid - 64 - 4 * tx))) - 1u) << 4);
+    unsigned long long bands = 0;   // bit 8 i + j: accumulator (i, j) is inside its query's band
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int qr = (i < 4 ? 0 : 60) + 4 * ty + i;          // rows 4 ty + i, 64 + 4 ty + (i - 4)
-      const float thi = sm.thi[qr], tlo = sm.tlo[qr];
+      // L1: score = -acc, so score > thi <=> acc < -thi and score >= tlo <=> acc <= -tlo (exact)
+      const float thi = OP == SKGE_RANK_L1 ? -sm.thi[qr] : sm.thi[qr];
+      const float tlo = OP == SKGE_RANK_L1 ? -sm.tlo[qr] : sm.tlo[qr];
+      unsigned gt = 0, ge = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int er = (j < 4 ? 0 : 60) + 4 * tx + j;
-        const float s = OP == SKGE_RANK_L1 ? -acc[i][j] : acc[i][j];
-        if (er < nvalid) {
-          if (s > thi) {
-            ++cnt[i];
-          } else if (s >= tlo) {
-            unsigned long long slot = atomicAdd(cand_count, 1ull);
-            if ((int64_t)slot < cand_cap) {
-              cand_q[slot] = (int32_t)(q0 + qr);
-              cand_e[slot] = ebase + er;
-            }
-          }
+        if (OP == SKGE_RANK_L1) {
+          gt |= acc[i][j] < thi ? (1u << j) : 0u;
+          ge |= acc[i][j] <= tlo ? (1u << j) : 0u;
+        } else {
+          gt |= acc[i][j] > thi ? (1u << j) : 0u;
+          ge |= acc[i][j] >= tlo ? (1u << j) : 0u;
         }
+      }
+      gt &= vm;
+      cnt[i] += __popc(gt);
+      bands |= (unsigned long long)(ge & ~gt & vm) << (8 * i);
+    }
+    while (bands) {   // rare: a handful of pairs per query over the whole table
+      const int b = __ffsll((long long)bands) - 1;
+      bands &= bands - 1;
+      const int i = b >> 3, j = b & 7;
+      const unsigned long long slot = atomicAdd(cand_count, 1ull);
+      if ((int64_t)slot < cand_cap) {
+        cand_q[slot] = (int32_t)(q0 + (i < 4 ? 0 : 60) + 4 * ty + i);
+        cand_e[slot] = ebase + (j < 4 ? 0 : 60) + 4 * tx + j;
       }
     }
   }
