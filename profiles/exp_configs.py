@@ -37,7 +37,9 @@ def run(name, shape, model, d, pairwise, upd, margin=None, epochs=6):
              2 * len(g['test']) / rk / 1e6, ev.last_stats['engine']), flush=True)
 
 if __name__ == '__main__':
-    run('cfg1', 'wn18', 'transe', 50, True, AdaGrad, 2.0)
-    run('cfg2', 'wn18', 'hole', 150, True, AdaGrad, 0.2)
-    run('cfg3', 'wn18', 'rescal', 100, False, SGD)
-    run('cfg4', 'fb15k', 'transe', 200, True, AdaGrad, 2.0)
+    only = sys.argv[1:]          # e.g. `exp_configs.py cfg3` (under ncu: SKGE_EPOCHS=2)
+    ep = int(os.environ.get('SKGE_EPOCHS', '6'))
+    for cfg in (('cfg1', 'wn18', 'transe', 50, True, AdaGrad, 2.0), ('cfg2', 'wn18', 'hole', 150, True, AdaGrad, 0.2),
+                ('cfg3', 'wn18', 'rescal', 100, False, SGD, None), ('cfg4', 'fb15k', 'transe', 200, True, AdaGrad, 2.0)):
+        if not only or cfg[0] in only:
+            run(*cfg, epochs=ep)

@@ -119,6 +119,155 @@ __global__ void rescal_logistic_kernel(const float *__restrict__ E, const float 
   }
 }
 
+// The same per-example math for minibatches already grouped by relation (the sorted example list
+// the W update needs anyway).  The one-CTA-per-example kernel above re-reads the d x d relation
+// matrix from L2 twice per example (80 KB at d = 100: 145 us of a 313 us config-3 minibatch); here a
+// CTA takes a chunk of EB consecutive examples of the sorted list, keeps W[p] in shared memory for the
+// run of examples that share it (rows padded to an odd stride: row- and column-wise reads are both
+// conflict-free) and computes both products for the run as two small register-tiled GEMMs:
+//   thread (g, c): 16 examples of group g x (row c of W . E[o]  and  E[s] . column c of W).
+// The reference memoises per-relation products for the same reason (skge/rescal.py:43-57).
+template <int CW>
+struct RescalGrouped {
+  static constexpr int GROUPS = 256 / CW;   // CW column slots per example group: 128 (d <= 128) or 256
+  static constexpr int EPT = 16;            // examples per thread
+  static constexpr int EB = EPT * GROUPS;   // examples per chunk
+  static constexpr int WPG = CW / 32;       // warps per group
+  __host__ __device__ static size_t smem_bytes(int d) {
+    const size_t DS = (size_t)((d + 3) & ~3);
+    return (DS * (DS + 1) + 2 * EB * DS + EB * 8 + 2 * EB) * sizeof(float) + 2 * EB * sizeof(int32_t);
+  }
+};
+
+template <int CW, bool MASKED>
+__device__ __forceinline__ void rescal_run_products(const float *__restrict__ Ws, const float *__restrict__ es,
+                                                    const float *__restrict__ eo, int DS, int WS, int c, int e0,
+                                                    unsigned emask, float (&we)[16], float (&ew)[16]) {
+  for (int k = 0; k < DS; k += 4) {
+    float wr[4], wc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wr[i] = Ws[c * WS + k + i];     // W[c][k + i]
+      wc[i] = Ws[(k + i) * WS + c];   // W[k + i][c]
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      if (MASKED && !((emask >> e) & 1u)) continue;
+      const float4 vo = *reinterpret_cast<const float4 *>(eo + (e0 + e) * DS + k);
+      const float4 vs = *reinterpret_cast<const float4 *>(es + (e0 + e) * DS + k);
+      we[e] = fmaf(wr[3], vo.w, fmaf(wr[2], vo.z, fmaf(wr[1], vo.y, fmaf(wr[0], vo.x, we[e]))));
+      ew[e] = fmaf(wc[3], vs.w, fmaf(wc[2], vs.z, fmaf(wc[1], vs.y, fmaf(wc[0], vs.x, ew[e]))));
+    }
+  }
+}
+
+template <int CW>
+__global__ void __launch_bounds__(256) rescal_logistic_grouped_kernel(
+    const float *__restrict__ E, const float *__restrict__ W, const int32_t *__restrict__ s,
+    const int32_t *__restrict__ o, const int32_t *__restrict__ p, const float *__restrict__ y,
+    const int32_t *__restrict__ sorted_vals, const int32_t *__restrict__ meta, int d, float *__restrict__ G,
+    float *__restrict__ fsv, double *__restrict__ loss, double *__restrict__ loss_accum, int32_t *__restrict__ counts) {
+  using RG = RescalGrouped<CW>;
+  constexpr int EPT = RG::EPT, EB = RG::EB, WPG = RG::WPG;
+  extern __shared__ __align__(16) float smg[];
+  const int DS = (d + 3) & ~3, WS = DS + 1;
+  float *Ws = smg;                     // [DS][WS], zero beyond d
+  float *es = Ws + DS * WS;            // [EB][DS]
+  float *eo = es + EB * DS;            // [EB][DS]
+  float *part = eo + EB * DS;          // [EB][8] per-warp partial scores
+  float *fsm = part + EB * 8;          // [EB]
+  float *lsm = fsm + EB;               // [EB]
+  int32_t *exs = reinterpret_cast<int32_t *>(lsm + EB);   // [EB] example ids of the chunk
+  int32_t *rels = exs + EB;                                // [EB] their relations
+  const int total = meta[3];           // valid examples in the sorted list
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = t / CW, c = t % CW, e0 = g * EPT;
+  double lsum = 0.0;
+  int nval = 0;
+  for (int chunk = blockIdx.x; chunk * EB < total; chunk += gridDim.x) {
+    const int cbeg = chunk * EB, cn = min(EB, total - cbeg);
+    __syncthreads();
+    if (t < EB) {
+      const int ex = t < cn ? (sorted_vals[cbeg + t] >> 4) : -1;
+      exs[t] = ex;
+      rels[t] = ex >= 0 ? p[ex] : -1;
+    }
+    __syncthreads();
+    for (int row = warp; row < 2 * EB; row += 8) {
+      const int e = row >> 1;
+      float *dst = ((row & 1) ? eo : es) + e * DS;
+      if (e < cn) {
+        const int ex = exs[e];
+        const float *src = E + (int64_t)((row & 1) ? o[ex] : s[ex]) * d;
+        for (int j = lane; j < DS; j += 32) dst[j] = j < d ? __ldg(src + j) : 0.f;
+      } else {
+        for (int j = lane; j < DS; j += 32) dst[j] = 0.f;
+      }
+    }
+    int rb = 0;
+    while (rb < cn) {   // runs of one relation inside the chunk (usually the whole chunk)
+      const int rel = rels[rb];
+      int re = rb + 1;
+      while (re < cn && rels[re] == rel) ++re;
+      __syncthreads();   // the previous run is done with Ws; es / eo are in place
+      const float *w = W + (int64_t)rel * d * d;
+      for (int r = warp; r < DS; r += 8)
+        for (int j = lane; j < WS; j += 32) Ws[r * WS + j] = (r < d && j < d) ? __ldg(w + (int64_t)r * d + j) : 0.f;
+      __syncthreads();
+      // examples of this thread's group that belong to the run
+      const int lo = max(rb, e0) - e0, hi = min(re, e0 + EPT) - e0;
+      const unsigned emask = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+      float we[EPT], ew[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) we[e] = ew[e] = 0.f;
+      if (c < DS && emask) {
+        if (emask == 0xffffu) rescal_run_products<CW, false>(Ws, es, eo, DS, WS, c, e0, emask, we, ew);
+        else rescal_run_products<CW, true>(Ws, es, eo, DS, WS, c, e0, emask, we, ew);
+      }
+      // raw score = E[s] . (W E[o]): per-warp partial sums, combined in warp order
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        if (!((emask >> e) & 1u)) continue;   // uniform over the group's warps
+        float pr = c < DS ? es[(e0 + e) * DS + c] * we[e] : 0.f;
+        pr = warp_sum(pr);
+        if (lane == 0) part[(e0 + e) * 8 + (warp % WPG)] = pr;
+      }
+      __syncthreads();
+      if (t >= rb && t < re) {
+        float raw = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < WPG; ++wq) raw += part[t * 8 + wq];
+        const int ex = exs[t];
+        float l, fs;
+        logistic_terms(y[ex], raw, &l, &fs);
+        fsm[t] = fs;
+        lsm[t] = l;
+        fsv[ex] = fs;
+      }
+      __syncthreads();
+      if (t == 0)
+        for (int e = rb; e < re; ++e) lsum += (double)lsm[e];
+      if (c < d) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          if (!((emask >> e) & 1u)) continue;
+          const float fs = fsm[e0 + e];
+          float *gr = G + (int64_t)exs[e0 + e] * 2 * d;
+          gr[c] = fs * we[e];        // -> s   (skge/rescal.py:72)
+          gr[d + c] = fs * ew[e];    // -> o   (skge/rescal.py:73)
+        }
+      }
+      rb = re;
+    }
+    nval += cn;
+  }
+  if (t == 0 && nval) {
+    if (loss) atomicAdd(loss, lsum);
+    if (loss_accum) atomicAdd(loss_accum, lsum);
+    atomicAdd(counts, nval);
+  }
+}
+
 // gw[u] = mean_{i in relation u} fs_i E[s_i] E[o_i]^T + rparam W[p_u]   (skge/rescal.py:61-70)
 // A frequent relation owns a large share of the minibatch, so its examples are cut into
 // kGwSlices slices reduced by different CTAs into partial sums (pass 1, grid = (tiles_b,
@@ -302,20 +451,39 @@ static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const
   }
   SKGE_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
   if (loss) SKGE_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
-  int threads = block_threads(d);
-  if (threads * 4 < d) threads = 256;
-  SKGE_REQUIRE(threads * 4 >= d, "d too large");
-  size_t smem = (3 * (size_t)d + 40) * sizeof(float);
-  int64_t blocks = n > kNumSMs * 16 ? kNumSMs * 16 : n;
-  rescal_logistic_kernel<<<(int)blocks, threads, smem, st>>>(E, W, s, o, p, y, valid, n, d, G, fsv, loss, loss_accum,
-                                                             counts);
-  SKGE_LAUNCH_CHECK();
-  // group examples by relation, then the per-relation outer-product mean (reads the OLD E)
+  // group examples by relation first: the per-relation outer-product mean needs the lists, and the
+  // grouped logistic kernel keeps W[p] in shared memory over a run of them
   RoleMap rmw;
   rmw.idx[0] = p; rmw.is_rel[0] = 0; rmw.grow[0] = 0; rmw.gsign[0] = 1.f; rmw.nroles = 1;
   SegLists sl;
   int rc = seg_build(rmw, valid, n, M, 0, ar, st, &sl);
   if (rc) return rc;
+  const size_t sm128 = RescalGrouped<128>::smem_bytes(d), sm256 = RescalGrouped<256>::smem_bytes(d);
+  if (d <= 128 && sm128 <= 200 * 1024) {
+    using RG = RescalGrouped<128>;
+    SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm128));
+    int64_t chunks = (n + RG::EB - 1) / RG::EB;
+    if (chunks > kNumSMs * 4) chunks = kNumSMs * 4;
+    rescal_logistic_grouped_kernel<128><<<(int)chunks, 256, sm128, st>>>(E, W, s, o, p, y, sl.vals, sl.meta, d, G, fsv, loss,
+                                                                       loss_accum, counts);
+  } else if (d <= 256 && sm256 <= 200 * 1024) {
+    using RG = RescalGrouped<256>;
+    SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm256));
+    int64_t chunks = (n + RG::EB - 1) / RG::EB;
+    if (chunks > kNumSMs * 4) chunks = kNumSMs * 4;
+    rescal_logistic_grouped_kernel<256><<<(int)chunks, 256, sm256, st>>>(E, W, s, o, p, y, sl.vals, sl.meta, d, G, fsv, loss,
+                                                                       loss_accum, counts);
+  } else {   // W[p] does not fit in shared memory: one CTA per example, W streamed from L2
+    int threads = block_threads(d);
+    if (threads * 4 < d) threads = 256;
+    SKGE_REQUIRE(threads * 4 >= d, "d too large");
+    size_t smem = (3 * (size_t)d + 40) * sizeof(float);
+    int64_t blocks = n > kNumSMs * 16 ? kNumSMs * 16 : n;
+    rescal_logistic_kernel<<<(int)blocks, threads, smem, st>>>(E, W, s, o, p, y, valid, n, d, G, fsv, loss, loss_accum,
+                                                               counts);
+  }
+  SKGE_LAUNCH_CHECK();
+  // the per-relation outer-product mean (reads the OLD E)
   int tiles = (d + 31) / 32;
   int64_t items = uw * kGwSlices;
   dim3 grid(tiles, tiles, (unsigned)(items > 65535 ? 65535 : items));

@@ -348,20 +348,32 @@ class StochasticTrainer(object):
         philox = torch.zeros(1, dtype=torch.int64, device=dev)
         per_pos = sampler.n * len(sampler.modes) if sampler is not None else 0
 
+        bufs = {}   # per minibatch length: positives followed by their negatives (captured graphs keep the pointers)
+
         def body(idx):
             bl = idx.long()
-            bs, bo, bp, by = s[bl], o[bl], p[bl], y[bl]
-            valid = None
-            if sampler is not None:
-                # xys += samplef(xys): positives, then their negatives labelled -1 (skge/base.py:1295-1296);
-                # negatives that exhausted their tries are masked out instead of compacted (no host sync)
-                _, neg, ok = sampler.device_sample(None, idx.numel(), 0, src=(bs, bo, bp), offset_dev=philox)
-                philox.add_(idx.numel() * per_pos)
-                bs, bo, bp = torch.cat([bs, neg[0]]), torch.cat([bo, neg[1]]), torch.cat([bp, neg[2]])
-                by = torch.cat([by, torch.full((neg[0].numel(),), -1.0, device=dev)])
-                valid = torch.cat([torch.ones(idx.numel(), dtype=torch.uint8, device=dev), ok])
-            self.model._fused_logistic_step(self._updaters, bs.contiguous(), bo.contiguous(), bp.contiguous(),
-                                            by.contiguous(), self._counts, self._loss_dev, valid=valid)
+            nb = idx.numel()
+            if sampler is None:
+                self.model._fused_logistic_step(self._updaters, s[bl].contiguous(), o[bl].contiguous(),
+                                                p[bl].contiguous(), y[bl].contiguous(), self._counts,
+                                                self._loss_dev, valid=None)
+                return
+            # xys += samplef(xys): positives, then their negatives labelled -1 (skge/base.py:1295-1296);
+            # negatives that exhausted their tries are masked out instead of compacted (no host sync).
+            # The sampler writes the negatives straight into the tail of the minibatch arrays.
+            if nb not in bufs:
+                nneg = nb * per_pos
+                bufs[nb] = ([torch.empty(nb + nneg, dtype=torch.int32, device=dev) for _ in range(3)],
+                            torch.full((nb + nneg,), -1.0, dtype=torch.float32, device=dev),
+                            torch.ones(nb + nneg, dtype=torch.uint8, device=dev),
+                            [torch.empty(nneg, dtype=torch.int32, device=dev) for _ in range(3)])
+            (bs, bo, bp), by, valid, scratch = bufs[nb]
+            for src_t, dst in ((s, bs), (o, bo), (p, bp), (y, by)):
+                torch.index_select(src_t, 0, bl, out=dst[:nb])
+            sampler.device_sample(None, nb, 0, src=(bs[:nb], bo[:nb], bp[:nb]), offset_dev=philox,
+                                  outs=scratch + [bs[nb:], bo[nb:], bp[nb:]], valid=valid[nb:])
+            philox.add_(nb * per_pos)
+            self.model._fused_logistic_step(self._updaters, bs, bo, bp, by, self._counts, self._loss_dev, valid=valid)
 
         self._run_epochs(n, _GraphedStep(body, self.cuda_graphs, self._graph_signature))
 

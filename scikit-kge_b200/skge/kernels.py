@@ -173,16 +173,26 @@ class TripleSet(object):
                                             ptr(out), stream()))
         return out
 
-    def sample(self, batch_idx, B, n_per, modes_mask, ntries, seed, offset, src=None, offset_dev=None):
+    def sample(self, batch_idx, B, n_per, modes_mask, ntries, seed, offset, src=None, offset_dev=None,
+               outs=None, valid=None):
         """Returns (pos, neg, valid): pos/neg are (s, o, p) int32 tensors of
         B * n_per * nmodes pairs.  ``src`` overrides the (s, o, p) arrays the
         positives are read from (default: the training arrays).  ``offset_dev`` (int64
-        CUDA scalar, optional) is added to the Philox counter on the device."""
+        CUDA scalar, optional) is added to the Philox counter on the device.  ``outs`` (six
+        contiguous int32 tensors or views of n entries) and ``valid`` (uint8) let the caller have the
+        result written in place, e.g. into the tail of a minibatch buffer."""
         s, o, p = src if src is not None else (self.s, self.o, self.p)
         nm = bin(modes_mask & 7).count('1')
         n = B * n_per * nm
-        outs = [_i32(n) for _ in range(6)]
-        valid = torch.empty(n, dtype=torch.uint8, device=_ext.device())
+        if outs is None:
+            outs = [_i32(n) for _ in range(6)]
+        else:
+            outs = list(outs)
+            assert len(outs) == 6 and all(t.numel() == n and t.dtype == torch.int32 and t.is_contiguous() for t in outs)
+        if valid is None:
+            valid = torch.empty(n, dtype=torch.uint8, device=_ext.device())
+        else:
+            assert valid.numel() == n and valid.dtype == torch.uint8 and valid.is_contiguous()
         _count('sample')
         check(lib().skge_sample_corrupt(ptr(self.table), self.table.numel(), ptr(self.sp_table),
                                         self.sp_table.numel() if self.sp_table is not None else 0, ptr(s), ptr(o),

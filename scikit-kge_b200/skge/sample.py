@@ -49,14 +49,14 @@ class Sampler(object):
             raise ValueError('modes must be an ascending subset of [0, 1, 2], got %r' % (self.modes,))
         return sum(1 << m for m in modes)
 
-    def device_sample(self, batch_idx, B, call_no, src=None, offset_dev=None):
+    def device_sample(self, batch_idx, B, call_no, src=None, offset_dev=None, outs=None, valid=None):
         """(pos, neg, valid) for B positives: indices ``batch_idx`` into the
         training arrays, or the explicit ``src`` = (s, o, p) tensors.  Calls get
         disjoint Philox counter ranges: by ``call_no`` (host) or by ``offset_dev``, an
         int64 CUDA scalar the caller advances (graph-captured steps)."""
         ts = self.ensure_device()
         return ts.sample(batch_idx, B, self.n, self._modes_mask(), self.ntries, self.seed,
-                         (call_no << 40), src=src, offset_dev=offset_dev)
+                         (call_no << 40), src=src, offset_dev=offset_dev, outs=outs, valid=valid)
 
     # -- reference API ------------------------------------------------------------
     def sample(self, xys):

@@ -515,11 +515,16 @@ def test_hot_rows_use_the_chunked_segment_reduction(kind, d):
             torch.testing.assert_close(hat, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
 
 
-def test_rescal_wn18_shaped_minibatch_against_oracle():
-    """Config 3: d = 100, 1414 positives + 2828 negatives, logistic loss, SGD."""
+@pytest.mark.parametrize('N,M,d,B', [
+    (40943, 18, 100, 1414),     # config 3: d = 100, 1414 positives + 2828 negatives
+    (3000, 700, 36, 500),       # many relations: several runs of W[p] inside one 32-example chunk
+    (2000, 5, 160, 300),        # 128 < d: the 256-column layout (16 examples per chunk)
+    (600, 3, 7, 100),           # tiny odd row length (padded to 8 in shared memory)
+    (500, 3, 230, 100)])        # W[p] too large for shared memory: one CTA per example
+def test_rescal_wn18_shaped_minibatch_against_oracle(N, M, d, B):
+    """Logistic loss, SGD, relation-grouped kernel (csrc/logistic.cu::rescal_logistic_grouped_kernel)."""
     import skge
     from skge.param import SGD
-    N, M, d, B = 40943, 18, 100, 1414
     rng = np.random.default_rng(3)
     E0 = (rng.uniform(-1, 1, (N, d)) * 0.1).astype(np.float32).astype(np.float64)
     W0 = (rng.uniform(-1, 1, (M, d, d)) * 0.1).astype(np.float32).astype(np.float64)
