@@ -123,66 +123,114 @@ __global__ void rescal_logistic_kernel(const float *__restrict__ E, const float 
 // the W update needs anyway).  The one-CTA-per-example kernel above re-reads the d x d relation
 // matrix from L2 twice per example (80 KB at d = 100: 145 us of a 313 us config-3 minibatch); here a
 // CTA takes a chunk of EB consecutive examples of the sorted list, keeps W[p] in shared memory for the
-// run of examples that share it (rows padded to an odd stride: row- and column-wise reads are both
-// conflict-free) and computes both products for the run as two small register-tiled GEMMs:
-//   thread (g, c): 16 examples of group g x (row c of W . E[o]  and  E[s] . column c of W).
+// run of examples that share it and computes both products for the run as two small register-tiled
+// GEMMs.  Warp g owns EX examples, lane q owns MR rows of W . E[o] (rows q, q + 32, ...: eight lanes of a
+// 128-bit phase read eight consecutive rows, whose stride is chosen so that they fall in different bank
+// groups) and MR columns of E[s] . W (columns MR q ..: contiguous 128-bit reads), so one k-step of four
+// moves 4 MR + 2 EX 128-bit words through shared memory for 8 MR EX FMAs.  The score is a warp sum (a
+// warp holds all rows of its examples): no block-level exchange, fs goes round by shuffle.
 // The reference memoises per-relation products for the same reason (skge/rescal.py:43-57).
-template <int CW>
+template <int MR>
 struct RescalGrouped {
-  static constexpr int GROUPS = 256 / CW;   // CW column slots per example group: 128 (d <= 128) or 256
-  static constexpr int EPT = 16;            // examples per thread
-  static constexpr int EB = EPT * GROUPS;   // examples per chunk
-  static constexpr int WPG = CW / 32;       // warps per group
+  static constexpr int EX = 16 / MR;        // examples per warp: 4 (d <= 128) or 2 (d <= 256)
+  static constexpr int EB = 8 * EX;         // examples per chunk (8 warps)
+  static constexpr int RUN_SPLIT = 4;       // CTAs per chunk: run r of a chunk goes to CTA r % RUN_SPLIT
+  static constexpr int DMAX = 32 * MR;
+  // row stride of W in shared memory: a multiple of 4 floats whose quarter is odd (see above)
+  __host__ __device__ static int w_stride(int DS) { return ((DS >> 2) & 1) ? DS : DS + 4; }
   __host__ __device__ static size_t smem_bytes(int d) {
     const size_t DS = (size_t)((d + 3) & ~3);
-    return (DS * (DS + 1) + 2 * EB * DS + EB * 8 + 2 * EB) * sizeof(float) + 2 * EB * sizeof(int32_t);
+    return (DS * (DS + 4) + 2 * EB * DS + 8) * sizeof(float) + 2 * EB * sizeof(int32_t) + 8 * sizeof(double);
   }
 };
 
-template <int CW, bool MASKED>
-__device__ __forceinline__ void rescal_run_products(const float *__restrict__ Ws, const float *__restrict__ es,
-                                                    const float *__restrict__ eo, int DS, int WS, int c, int e0,
-                                                    unsigned emask, float (&we)[16], float (&ew)[16]) {
-  for (int k = 0; k < DS; k += 4) {
-    float wr[4], wc[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      wr[i] = Ws[c * WS + k + i];     // W[c][k + i]
-      wc[i] = Ws[(k + i) * WS + c];   // W[k + i][c]
-    }
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      if (MASKED && !((emask >> e) & 1u)) continue;
-      const float4 vo = *reinterpret_cast<const float4 *>(eo + (e0 + e) * DS + k);
-      const float4 vs = *reinterpret_cast<const float4 *>(es + (e0 + e) * DS + k);
-      we[e] = fmaf(wr[3], vo.w, fmaf(wr[2], vo.z, fmaf(wr[1], vo.y, fmaf(wr[0], vo.x, we[e]))));
-      ew[e] = fmaf(wc[3], vs.w, fmaf(wc[2], vs.z, fmaf(wc[1], vs.y, fmaf(wc[0], vs.x, ew[e]))));
+// asynchronous global -> shared copies: a thread puts all of its elements of a gather in flight at once
+// (no registers); the gathers here are latency-, not bandwidth-bound
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_f32x4(float *smem_dst, const float *gsrc) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// one row of d floats -> shared memory (zero padded to DS); vec16: d % 4 == 0 and 16-byte aligned source
+__device__ __forceinline__ void row_to_smem_async(float *dst, const float *src, int d, int DS, int lane, bool vec16) {
+  if (vec16) {
+    for (int q = lane; q < (d >> 2); q += 32) cp_async_f32x4(dst + 4 * q, src + 4 * q);
+  } else {
+    for (int j = lane; j < DS; j += 32) {
+      if (j < d) cp_async_f32(dst + j, src + j);
+      else dst[j] = 0.f;
     }
   }
 }
 
-template <int CW>
+template <int MR, bool MASKED>
+__device__ __forceinline__ void rescal_run_products(const float *__restrict__ Ws, const float *__restrict__ es,
+                                                    const float *__restrict__ eo, int DS, int WS, int q, int e0,
+                                                    unsigned emask, float (&we)[16 / MR][MR], float (&ew)[16 / MR][MR]) {
+  constexpr int EX = 16 / MR, CH = MR / 4;
+  bool rok[MR], cok[CH];
+#pragma unroll
+  for (int m = 0; m < MR; ++m) rok[m] = q + 32 * m < DS;
+#pragma unroll
+  for (int h = 0; h < CH; ++h) cok[h] = MR * q + 4 * h < DS;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < DS; k += 4) {
+    float4 wr[MR], wc[4][CH];
+#pragma unroll
+    for (int m = 0; m < MR; ++m)      // W[q + 32 m][k .. k + 3]
+      wr[m] = rok[m] ? *reinterpret_cast<const float4 *>(Ws + (q + 32 * m) * WS + k) : zero4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int h = 0; h < CH; ++h)    // W[k + i][MR q + 4 h .. + 3]
+        wc[i][h] = cok[h] ? *reinterpret_cast<const float4 *>(Ws + (k + i) * WS + MR * q + 4 * h) : zero4;
+#pragma unroll
+    for (int e = 0; e < EX; ++e) {
+      if (MASKED && !((emask >> e) & 1u)) continue;
+      const float4 vo = *reinterpret_cast<const float4 *>(eo + (e0 + e) * DS + k);
+      const float4 vs = *reinterpret_cast<const float4 *>(es + (e0 + e) * DS + k);
+#pragma unroll
+      for (int m = 0; m < MR; ++m)
+        we[e][m] = fmaf(wr[m].w, vo.w, fmaf(wr[m].z, vo.z, fmaf(wr[m].y, vo.y, fmaf(wr[m].x, vo.x, we[e][m]))));
+#pragma unroll
+      for (int h = 0; h < CH; ++h) {
+        ew[e][4 * h + 0] = fmaf(wc[3][h].x, vs.w, fmaf(wc[2][h].x, vs.z, fmaf(wc[1][h].x, vs.y, fmaf(wc[0][h].x, vs.x, ew[e][4 * h + 0]))));
+        ew[e][4 * h + 1] = fmaf(wc[3][h].y, vs.w, fmaf(wc[2][h].y, vs.z, fmaf(wc[1][h].y, vs.y, fmaf(wc[0][h].y, vs.x, ew[e][4 * h + 1]))));
+        ew[e][4 * h + 2] = fmaf(wc[3][h].z, vs.w, fmaf(wc[2][h].z, vs.z, fmaf(wc[1][h].z, vs.y, fmaf(wc[0][h].z, vs.x, ew[e][4 * h + 2]))));
+        ew[e][4 * h + 3] = fmaf(wc[3][h].w, vs.w, fmaf(wc[2][h].w, vs.z, fmaf(wc[1][h].w, vs.y, fmaf(wc[0][h].w, vs.x, ew[e][4 * h + 3]))));
+      }
+    }
+  }
+}
+
+template <int MR>
 __global__ void __launch_bounds__(256) rescal_logistic_grouped_kernel(
     const float *__restrict__ E, const float *__restrict__ W, const int32_t *__restrict__ s,
     const int32_t *__restrict__ o, const int32_t *__restrict__ p, const float *__restrict__ y,
-    const int32_t *__restrict__ sorted_vals, const int32_t *__restrict__ meta, int d, float *__restrict__ G,
-    float *__restrict__ fsv, double *__restrict__ loss, double *__restrict__ loss_accum, int32_t *__restrict__ counts) {
-  using RG = RescalGrouped<CW>;
-  constexpr int EPT = RG::EPT, EB = RG::EB, WPG = RG::WPG;
+    const int32_t *__restrict__ sorted_vals, const int32_t *__restrict__ meta, int d, int vec16,
+    float *__restrict__ G, float *__restrict__ fsv, double *__restrict__ loss, double *__restrict__ loss_accum,
+    int32_t *__restrict__ counts) {
+  using RG = RescalGrouped<MR>;
+  constexpr int EX = RG::EX, EB = RG::EB, CH = MR / 4;
   extern __shared__ __align__(16) float smg[];
-  const int DS = (d + 3) & ~3, WS = DS + 1;
+  const int DS = (d + 3) & ~3, WS = RG::w_stride(DS);
   float *Ws = smg;                     // [DS][WS], zero beyond d
   float *es = Ws + DS * WS;            // [EB][DS]
   float *eo = es + EB * DS;            // [EB][DS]
-  float *part = eo + EB * DS;          // [EB][8] per-warp partial scores
-  float *fsm = part + EB * 8;          // [EB]
-  float *lsm = fsm + EB;               // [EB]
-  int32_t *exs = reinterpret_cast<int32_t *>(lsm + EB);   // [EB] example ids of the chunk
-  int32_t *rels = exs + EB;                                // [EB] their relations
+  double *lred = reinterpret_cast<double *>(eo + EB * DS);            // [8] per-warp loss sums (8-byte aligned)
+  int32_t *exs = reinterpret_cast<int32_t *>(lred + 8);               // [EB] example ids of the chunk
+  int32_t *rels = exs + EB;                                            // [EB] their relations
   const int total = meta[3];           // valid examples in the sorted list
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int g = t / CW, c = t % CW, e0 = g * EPT;
-  double lsum = 0.0;
+  const int t = threadIdx.x, q = t & 31, warp = t >> 5, e0 = warp * EX;
+  double lsum = 0.0;                   // lane 0 of each warp: the losses of the warp's examples
   int nval = 0;
   for (int chunk = blockIdx.x; chunk * EB < total; chunk += gridDim.x) {
     const int cbeg = chunk * EB, cn = min(EB, total - cbeg);
@@ -193,78 +241,99 @@ __global__ void __launch_bounds__(256) rescal_logistic_grouped_kernel(
       rels[t] = ex >= 0 ? p[ex] : -1;
     }
     __syncthreads();
+    if (blockIdx.y == 0) nval += cn;
+    int nruns = 1;
+    for (int e = 1; e < cn; ++e) nruns += rels[e] != rels[e - 1];
+    if ((int)blockIdx.y >= nruns) continue;   // this CTA owns runs y, y + RUN_SPLIT, ...: none here
     for (int row = warp; row < 2 * EB; row += 8) {
       const int e = row >> 1;
       float *dst = ((row & 1) ? eo : es) + e * DS;
       if (e < cn) {
         const int ex = exs[e];
-        const float *src = E + (int64_t)((row & 1) ? o[ex] : s[ex]) * d;
-        for (int j = lane; j < DS; j += 32) dst[j] = j < d ? __ldg(src + j) : 0.f;
+        row_to_smem_async(dst, E + (int64_t)((row & 1) ? o[ex] : s[ex]) * d, d, DS, q, vec16 != 0);
       } else {
-        for (int j = lane; j < DS; j += 32) dst[j] = 0.f;
+        for (int j = q; j < DS; j += 32) dst[j] = 0.f;
       }
     }
-    int rb = 0;
+    int rb = 0, ri = 0;
     while (rb < cn) {   // runs of one relation inside the chunk (usually the whole chunk)
       const int rel = rels[rb];
       int re = rb + 1;
       while (re < cn && rels[re] == rel) ++re;
-      __syncthreads();   // the previous run is done with Ws; es / eo are in place
+      if (ri++ % (int)gridDim.y != (int)blockIdx.y) { rb = re; continue; }
+      __syncthreads();   // the previous run is done with Ws
       const float *w = W + (int64_t)rel * d * d;
-      for (int r = warp; r < DS; r += 8)
-        for (int j = lane; j < WS; j += 32) Ws[r * WS + j] = (r < d && j < d) ? __ldg(w + (int64_t)r * d + j) : 0.f;
-      __syncthreads();
-      // examples of this thread's group that belong to the run
-      const int lo = max(rb, e0) - e0, hi = min(re, e0 + EPT) - e0;
-      const unsigned emask = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
-      float we[EPT], ew[EPT];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) we[e] = ew[e] = 0.f;
-      if (c < DS && emask) {
-        if (emask == 0xffffu) rescal_run_products<CW, false>(Ws, es, eo, DS, WS, c, e0, emask, we, ew);
-        else rescal_run_products<CW, true>(Ws, es, eo, DS, WS, c, e0, emask, we, ew);
+      if (vec16) {
+        for (int r = warp; r < d; r += 8)
+          for (int j4 = q; j4 < (d >> 2); j4 += 32) cp_async_f32x4(Ws + r * WS + 4 * j4, w + (int64_t)r * d + 4 * j4);
+      } else {
+        for (int r = warp; r < DS; r += 8)
+          for (int j = q; j < DS; j += 32) {
+            if (r < d && j < d) cp_async_f32(Ws + r * WS + j, w + (int64_t)r * d + j);
+            else Ws[r * WS + j] = 0.f;
+          }
       }
-      // raw score = E[s] . (W E[o]): per-warp partial sums, combined in warp order
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        if (!((emask >> e) & 1u)) continue;   // uniform over the group's warps
-        float pr = c < DS ? es[(e0 + e) * DS + c] * we[e] : 0.f;
-        pr = warp_sum(pr);
-        if (lane == 0) part[(e0 + e) * 8 + (warp % WPG)] = pr;
-      }
+      cp_async_wait_all();   // also the chunk's E rows, issued above
       __syncthreads();
-      if (t >= rb && t < re) {
-        float raw = 0.f;
+      // examples of this warp that belong to the run
+      const int lo = max(rb, e0) - e0, hi = min(re, e0 + EX) - e0;
+      const unsigned emask = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;   // warp-uniform
+      if (emask) {
+        float we[EX][MR], ew[EX][MR];
 #pragma unroll
-        for (int wq = 0; wq < WPG; ++wq) raw += part[t * 8 + wq];
-        const int ex = exs[t];
-        float l, fs;
-        logistic_terms(y[ex], raw, &l, &fs);
-        fsm[t] = fs;
-        lsm[t] = l;
-        fsv[ex] = fs;
-      }
-      __syncthreads();
-      if (t == 0)
-        for (int e = rb; e < re; ++e) lsum += (double)lsm[e];
-      if (c < d) {
+        for (int e = 0; e < EX; ++e)
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
+          for (int m = 0; m < MR; ++m) we[e][m] = ew[e][m] = 0.f;
+        if (emask == (1u << EX) - 1u) rescal_run_products<MR, false>(Ws, es, eo, DS, WS, q, e0, emask, we, ew);
+        else rescal_run_products<MR, true>(Ws, es, eo, DS, WS, q, e0, emask, we, ew);
+#pragma unroll
+        for (int e = 0; e < EX; ++e) {
           if (!((emask >> e) & 1u)) continue;
-          const float fs = fsm[e0 + e];
-          float *gr = G + (int64_t)exs[e0 + e] * 2 * d;
-          gr[c] = fs * we[e];        // -> s   (skge/rescal.py:72)
-          gr[d + c] = fs * ew[e];    // -> o   (skge/rescal.py:73)
+          // raw score = E[s] . (W E[o]): the warp holds every row of the example
+          float pr = 0.f;
+#pragma unroll
+          for (int m = 0; m < MR; ++m)
+            if (q + 32 * m < DS) pr = fmaf(es[(e0 + e) * DS + q + 32 * m], we[e][m], pr);
+          const float raw = warp_sum(pr);
+          const int ex = exs[e0 + e];
+          float l, fs;
+          logistic_terms(y[ex], raw, &l, &fs);
+          if (q == 0) {
+            fsv[ex] = fs;
+            lsum += (double)l;
+          }
+          float *gr = G + (int64_t)ex * 2 * d;
+#pragma unroll
+          for (int m = 0; m < MR; ++m)
+            if (q + 32 * m < d) gr[q + 32 * m] = fs * we[e][m];            // -> s   (skge/rescal.py:72)
+#pragma unroll
+          for (int h = 0; h < CH; ++h) {                                   // -> o   (skge/rescal.py:73)
+            const int c0 = MR * q + 4 * h;
+            if (vec16) {
+              if (c0 < d)
+                *reinterpret_cast<float4 *>(gr + d + c0) =
+                    make_float4(fs * ew[e][4 * h], fs * ew[e][4 * h + 1], fs * ew[e][4 * h + 2], fs * ew[e][4 * h + 3]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                if (c0 + v < d) gr[d + c0 + v] = fs * ew[e][4 * h + v];
+            }
+          }
         }
       }
       rb = re;
     }
-    nval += cn;
   }
-  if (t == 0 && nval) {
-    if (loss) atomicAdd(loss, lsum);
-    if (loss_accum) atomicAdd(loss_accum, lsum);
-    atomicAdd(counts, nval);
+  // losses: per-warp sums combined in warp order
+  __syncthreads();
+  if (q == 0) lred[warp] = lsum;
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) tot += lred[w8];
+    if (loss && tot != 0.0) atomicAdd(loss, tot);
+    if (loss_accum && tot != 0.0) atomicAdd(loss_accum, tot);
+    if (nval) atomicAdd(counts, nval);
   }
 }
 
@@ -458,21 +527,27 @@ static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const
   SegLists sl;
   int rc = seg_build(rmw, valid, n, M, 0, ar, st, &sl);
   if (rc) return rc;
-  const size_t sm128 = RescalGrouped<128>::smem_bytes(d), sm256 = RescalGrouped<256>::smem_bytes(d);
-  if (d <= 128 && sm128 <= 200 * 1024) {
-    using RG = RescalGrouped<128>;
-    SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm128));
+  const size_t sm4 = RescalGrouped<4>::smem_bytes(d), sm8 = RescalGrouped<8>::smem_bytes(d);
+  const int vec16 = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(W) |
+                                    reinterpret_cast<uintptr_t>(G)) & 15) == 0;
+  if (d <= RescalGrouped<4>::DMAX && sm4 <= 200 * 1024) {
+    using RG = RescalGrouped<4>;
+    // ask for more than half of the SM's shared memory: one CTA per SM, so that the ~n / 32 chunk CTAs of a
+    // small minibatch spread over the SMs instead of pairing up
+    const size_t smem = sm4 > 120 * 1024 ? sm4 : 120 * 1024;
+    SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t chunks = (n + RG::EB - 1) / RG::EB;
     if (chunks > kNumSMs * 4) chunks = kNumSMs * 4;
-    rescal_logistic_grouped_kernel<128><<<(int)chunks, 256, sm128, st>>>(E, W, s, o, p, y, sl.vals, sl.meta, d, G, fsv, loss,
-                                                                       loss_accum, counts);
-  } else if (d <= 256 && sm256 <= 200 * 1024) {
-    using RG = RescalGrouped<256>;
-    SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm256));
+    rescal_logistic_grouped_kernel<4><<<dim3((unsigned)chunks, RG::RUN_SPLIT), 256, smem, st>>>(
+        E, W, s, o, p, y, sl.vals, sl.meta, d, vec16, G, fsv, loss, loss_accum, counts);
+  } else if (d <= RescalGrouped<8>::DMAX && sm8 <= 200 * 1024) {
+    using RG = RescalGrouped<8>;
+    const size_t smem = sm8 > 120 * 1024 ? sm8 : 120 * 1024;
+    SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t chunks = (n + RG::EB - 1) / RG::EB;
     if (chunks > kNumSMs * 4) chunks = kNumSMs * 4;
-    rescal_logistic_grouped_kernel<256><<<(int)chunks, 256, sm256, st>>>(E, W, s, o, p, y, sl.vals, sl.meta, d, G, fsv, loss,
-                                                                       loss_accum, counts);
+    rescal_logistic_grouped_kernel<8><<<dim3((unsigned)chunks, RG::RUN_SPLIT), 256, smem, st>>>(
+        E, W, s, o, p, y, sl.vals, sl.meta, d, vec16, G, fsv, loss, loss_accum, counts);
   } else {   // W[p] does not fit in shared memory: one CTA per example, W streamed from L2
     int threads = block_threads(d);
     if (threads * 4 < d) threads = 256;

@@ -349,6 +349,8 @@ class StochasticTrainer(object):
         per_pos = sampler.n * len(sampler.modes) if sampler is not None else 0
 
         bufs = {}   # per minibatch length: positives followed by their negatives (captured graphs keep the pointers)
+        # (s, o, p, y) as the rows of one table: a minibatch's positives are ONE column gather
+        soa = torch.stack([s, o, p, y.view(torch.int32)]) if sampler is not None else None
 
         def body(idx):
             bl = idx.long()
@@ -363,13 +365,13 @@ class StochasticTrainer(object):
             # The sampler writes the negatives straight into the tail of the minibatch arrays.
             if nb not in bufs:
                 nneg = nb * per_pos
-                bufs[nb] = ([torch.empty(nb + nneg, dtype=torch.int32, device=dev) for _ in range(3)],
-                            torch.full((nb + nneg,), -1.0, dtype=torch.float32, device=dev),
-                            torch.ones(nb + nneg, dtype=torch.uint8, device=dev),
+                tab = torch.empty(4, nb + nneg, dtype=torch.int32, device=dev)     # rows s, o, p, y (bit pattern)
+                tab[3].view(torch.float32).fill_(-1.0)
+                bufs[nb] = (tab, torch.ones(nb + nneg, dtype=torch.uint8, device=dev),
                             [torch.empty(nneg, dtype=torch.int32, device=dev) for _ in range(3)])
-            (bs, bo, bp), by, valid, scratch = bufs[nb]
-            for src_t, dst in ((s, bs), (o, bo), (p, bp), (y, by)):
-                torch.index_select(src_t, 0, bl, out=dst[:nb])
+            tab, valid, scratch = bufs[nb]
+            bs, bo, bp, by = tab[0], tab[1], tab[2], tab[3].view(torch.float32)
+            tab[:, :nb].copy_(soa.index_select(1, bl))
             sampler.device_sample(None, nb, 0, src=(bs[:nb], bo[:nb], bp[:nb]), offset_dev=philox,
                                   outs=scratch + [bs[nb:], bo[nb:], bp[nb:]], valid=valid[nb:])
             philox.add_(nb * per_pos)
