@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(256) rescal_gw_partial_kernel(const float *__r
                                                                 const float *__restrict__ fsv, SegLists sl, int d,
                                                                 float *__restrict__ part, int maxseg) {
   __shared__ float ts[32][33], to[32][33], tf[32];
+  __shared__ int32_t srow[32], orow[32];
   const int nseg = sl.meta[0];
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty in 0..7, rows ty, ty+8, ty+16, ty+24
@@ -362,18 +363,27 @@ __global__ void __launch_bounds__(256) rescal_gw_partial_kernel(const float *__r
     for (int j0 = beg; j0 < end; j0 += 32) {
       int cnt = min(32, end - j0);
       __syncthreads();
-      for (int t = threadIdx.x; t < 32 * 32; t += 256) {
-        int e = t >> 5, c = t & 31;
-        float vs = 0.f, vo = 0.f;
-        if (e < cnt) {
-          int ex = sl.vals[j0 + e] >> 4;
-          if (a0 + c < d) vs = __ldg(E + (int64_t)s[ex] * d + a0 + c);
-          if (b0 + c < d) vo = __ldg(E + (int64_t)o[ex] * d + b0 + c);
-        }
-        ts[e][c] = vs;
-        to[e][c] = vo;
+      // the batch's example ids and row numbers first, so that the tile loads below are independent
+      // (payload -> id -> row was a chain of three dependent loads per element)
+      if (threadIdx.x < 32) {
+        const int ex = threadIdx.x < cnt ? (sl.vals[j0 + threadIdx.x] >> 4) : -1;
+        srow[threadIdx.x] = ex >= 0 ? s[ex] : 0;
+        orow[threadIdx.x] = ex >= 0 ? o[ex] : 0;
+        tf[threadIdx.x] = ex >= 0 ? fsv[ex] : 0.f;
       }
-      if (threadIdx.x < 32) tf[threadIdx.x] = threadIdx.x < cnt ? fsv[sl.vals[j0 + threadIdx.x] >> 4] : 0.f;
+      __syncthreads();
+      float vs[4], vo[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int e = ty + 8 * it;
+        vs[it] = (e < cnt && a0 + tx < d) ? __ldg(E + (int64_t)srow[e] * d + a0 + tx) : 0.f;
+        vo[it] = (e < cnt && b0 + tx < d) ? __ldg(E + (int64_t)orow[e] * d + b0 + tx) : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        ts[ty + 8 * it][tx] = vs[it];
+        to[ty + 8 * it][tx] = vo[it];
+      }
       __syncthreads();
       for (int e = 0; e < cnt; ++e) {
         float fo = tf[e] * to[e][tx];
