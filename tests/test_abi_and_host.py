@@ -271,3 +271,54 @@ def test_table_checksum_detects_any_change_on_both_paths():
         u = t.clone()
         u[0, 0] = -u[0, 0]
         assert ranking._checksum(u) != a
+
+
+def test_spectral_row_lengths_and_mixed_radix_plan():
+    """Row lengths HolE's frequency-domain step takes (csrc/fft.cuh::spectral_len_ok, skge/hole.py), and the
+    stage plan of the warp transform (a radix-2 stage if needed, radix-4, radix-3, radix-5 Stockham stages)
+    restated in numpy against numpy's FFT -- the reference transforms any length (skge/util.py:27,50)."""
+    from skge.hole import spectral_len_ok
+    ok = [d for d in range(1, 1100) if spectral_len_ok(d)]
+    assert {32, 64, 100, 128, 150, 200, 256, 300, 512, 1000, 1024} <= set(ok)
+    assert not any(spectral_len_ok(d) for d in (10, 16, 24, 30, 33, 44, 70, 98, 149, 151, 154, 1026, 2048))
+    for d in ok:
+        h = d // 2
+        for r in (2, 3, 5):
+            while h % r == 0:
+                h //= r
+        assert d % 2 == 0 and 32 <= d <= 1024 and h == 1
+    src = open(os.path.join(ROOT, 'scikit-kge_b200', 'csrc', 'fft.cuh')).read()
+    assert 'd >= 32 && d <= 1024 && (d & 1) == 0 && fft_len_ok(d / 2)' in src      # the same rule on the device side
+
+    def plan(n):
+        m, n2, st = n, 0, []
+        while m % 2 == 0:
+            m //= 2
+            n2 += 1
+        st += [2] * (n2 & 1) + [4] * (n2 // 2)
+        for r in (3, 5):
+            while m % r == 0:
+                st.append(r)
+                m //= r
+        assert m == 1
+        return st
+
+    def stockham(x, inverse):
+        n, a, Ns = len(x), np.asarray(x, dtype=complex).copy(), 1
+        sg = 1j if inverse else -1j
+        for r in plan(n):
+            out, q = np.zeros(n, complex), n // r
+            for j in range(q):
+                k = j % Ns
+                j0 = (j - k) * r + k
+                v = [a[j + t * q] * np.exp(sg * 2 * np.pi * t * k / (r * Ns)) for t in range(r)]
+                for s_ in range(r):
+                    out[j0 + s_ * Ns] = sum(v[t] * np.exp(sg * 2 * np.pi * s_ * t / r) for t in range(r))
+            a, Ns = out, Ns * r
+        return a
+
+    rng = np.random.default_rng(5)
+    for n in (16, 32, 75, 50, 125, 48, 27, 150):
+        x = rng.normal(size=n) + 1j * rng.normal(size=n)
+        np.testing.assert_allclose(stockham(x, False), np.fft.fft(x), atol=1e-10)
+        np.testing.assert_allclose(stockham(x, True), np.fft.ifft(x) * n, atol=1e-10)
