@@ -546,8 +546,7 @@ static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const
     // small minibatch spread over the SMs instead of pairing up
     const size_t smem = sm4 > 120 * 1024 ? sm4 : 120 * 1024;
     SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t chunks = (n + RG::EB - 1) / RG::EB;
-    if (chunks > kNumSMs * 4) chunks = kNumSMs * 4;
+    const int64_t chunks = (n + RG::EB - 1) / RG::EB;   // one CTA row per chunk (n < 2^27: seg_build)
     rescal_logistic_grouped_kernel<4><<<dim3((unsigned)chunks, RG::RUN_SPLIT), 256, smem, st>>>(
         E, W, s, o, p, y, sl.vals, sl.meta, d, vec16, G, fsv, loss, loss_accum, counts);
   } else if (d <= RescalGrouped<8>::DMAX && sm8 <= 200 * 1024) {
@@ -555,7 +554,6 @@ static int rescal_logistic_run(float *E, float *W, float *p2E, float *p2W, const
     const size_t smem = sm8 > 120 * 1024 ? sm8 : 120 * 1024;
     SKGE_CUDA(cudaFuncSetAttribute(rescal_logistic_grouped_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t chunks = (n + RG::EB - 1) / RG::EB;
-    if (chunks > kNumSMs * 4) chunks = kNumSMs * 4;
     rescal_logistic_grouped_kernel<8><<<dim3((unsigned)chunks, RG::RUN_SPLIT), 256, smem, st>>>(
         E, W, s, o, p, y, sl.vals, sl.meta, d, vec16, G, fsv, loss, loss_accum, counts);
   } else {   // W[p] does not fit in shared memory: one CTA per example, W streamed from L2
